@@ -1,0 +1,32 @@
+# Builds libgfb200.so (C-ABI device layer + host front end bindings) for sm_100a, in tree.
+CUDA ?= /usr/local/cuda
+NVCC := $(CUDA)/bin/nvcc
+CXX ?= g++
+PKG := graph_framework_b200
+SRC := $(PKG)/csrc
+LIB := $(PKG)/libgfb200.so
+CXXFLAGS := -std=c++20 -O2 -fPIC -Wall -Wno-unused-function -I$(CUDA)/include -Iinclude
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+
+all: $(LIB)
+
+$(SRC)/skeleton_text.inc: $(SRC)/skeleton.cuh
+	( printf 'R"GFBSKEL(' ; cat $< ; printf ')GFBSKEL"\n' ) > $@
+
+build/kernels.o: $(SRC)/kernels.cu
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+build/runtime.o: $(SRC)/runtime.cpp $(SRC)/skeleton_text.inc include/gfb200.h
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+build/c_binding.o: $(SRC)/c_binding.cpp $(wildcard $(SRC)/graph/*.hpp) include/gfb200.h include/graph_c_binding.h include/gfb_rays.h
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIB): build/kernels.o build/runtime.o build/c_binding.o
+	$(CXX) -shared -o $@ $^ -L$(CUDA)/lib64 -lcudart_static -lnvrtc -ldl -lrt -lpthread
+
+clean:
+	rm -rf build $(LIB) $(SRC)/skeleton_text.inc

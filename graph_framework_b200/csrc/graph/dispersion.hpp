@@ -1,0 +1,317 @@
+//------------------------------------------------------------------------------
+//  dispersion.hpp -- dispersion functions D(w, k, x, t) and the ray equations.
+//
+//  Mirrors /root/reference/graph_framework/dispersion.hpp: the
+//  dispersion_function interface (:160-189), simple (:449-477), physics
+//  constants (:486-502), bohm_gross (:510-575), light_wave (:583-625),
+//  acoustic_wave (:633-690), gaussian_well (:698-731), ion_cyclotron (:739-783),
+//  ordinary_wave (:785-829), extra_ordinary_wave (:838-895), cold_plasma
+//  (:903-1008) and dispersion_interface (:1321-1634) which derives
+//      dx/dt = -dD/dk / dD/dw,   dk/dt = (dD/dx - dD/dk_vec . dk_vec/dx) / dD/dw
+//  by symbolic differentiation.
+//------------------------------------------------------------------------------
+#ifndef gfb_graph_dispersion_hpp
+#define gfb_graph_dispersion_hpp
+
+#include "equilibrium.hpp"
+
+namespace dispersion {
+    using graph::leaf_ptr;
+    using graph::vector_ptr;
+
+///  w_p^2/c^2 for a species (dispersion.hpp:108-117).
+    inline leaf_ptr build_plasma_frequency(leaf_ptr n, const double q, const double m, const double c,
+                                           const double epsilon0) {
+        return n*q*q/(epsilon0*m*c*c);
+    }
+///  w_c/c for a species (dispersion.hpp:132-139).
+    inline leaf_ptr build_cyclotron_frequency(const double q, leaf_ptr b, const double m, const double c) {
+        return q*b/(m*c);
+    }
+
+    template<typename T=double, bool SAFE_MATH=false>
+    class dispersion_function {
+    public:
+        virtual ~dispersion_function() {}
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr t,
+                           equilibrium::shared<T, SAFE_MATH> &eq) = 0;
+        typedef T base;
+        static constexpr bool safe_math = SAFE_MATH;
+    };
+
+///  D = (1000 (x - e^-t) - e^-t) kx + w  (dispersion.hpp:197-229).
+    template<typename T=double, bool SAFE_MATH=false>
+    class stiff final : public dispersion_function<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr, leaf_ptr, leaf_ptr t,
+                           equilibrium::shared<T, SAFE_MATH> &) {
+            return (1.0E3*(x - graph::exp(-t)) - graph::exp(-t))*k_vec->get_x() + w;
+        }
+    };
+
+///  D = n_par^2 + n_perp^2 - 1 with c = 1.
+    template<typename T=double, bool SAFE_MATH=false>
+    class simple final : public dispersion_function<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr, leaf_ptr, leaf_ptr, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &) {
+            const T c = 1.0;
+            auto npar2 = k_vec->get_z()*k_vec->get_z()*c*c/(w*w);
+            auto nperp2 = (k_vec->get_x()*k_vec->get_x() + k_vec->get_y()*k_vec->get_y())*c*c/(w*w);
+            return npar2 + nperp2 - c;
+        }
+    };
+
+    template<typename T=double, bool SAFE_MATH=false>
+    class physics : public dispersion_function<T, SAFE_MATH> {
+    protected:
+        const T epsilon0 = 8.8541878138E-12;
+        const T mu0 = M_PI*4.0E-7;
+        const T q = 1.602176634E-19;
+        const T me = 9.1093837015E-31;
+        const T c = static_cast<T> (1.0)/std::sqrt(epsilon0*mu0);
+
+///  k_par^2 with the reference's "no field -> |k|^2" rule (dispersion.hpp:552-560).
+        leaf_ptr kpara2(vector_ptr b_vec, vector_ptr k_vec) {
+            if (b_vec->length()->is_match(graph::zero())) return k_vec->dot(k_vec);
+            auto kpara = b_vec->unit()->dot(k_vec);
+            return kpara*kpara;
+        }
+    };
+
+///  D = w_pe^2 + 3/2 k_par^2 v_th^2 - w^2.
+    template<typename T=double, bool SAFE_MATH=false>
+    class bohm_gross final : public physics<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            auto wpe2 = build_plasma_frequency(eq->get_electron_density(x, y, z), this->q, this->me, this->c, this->epsilon0);
+            auto te = eq->get_electron_temperature(x, y, z);
+            auto vterm2 = static_cast<T> (2.0)*this->q*te/(this->me*this->c*this->c);
+            return wpe2 + 3.0/2.0*this->kpara2(eq->get_magnetic_field(x, y, z), k_vec)*vterm2 - w*w;
+        }
+    };
+
+///  D = w_pe^2 + k^2 - w^2.
+    template<typename T=double, bool SAFE_MATH=false>
+    class light_wave final : public physics<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            auto wpe2 = build_plasma_frequency(eq->get_electron_density(x, y, z), this->q, this->me, this->c, this->epsilon0);
+            assert(eq->get_magnetic_field(x, y, z)->length()->is_match(graph::zero()) &&
+                   "Expected equilibrium with no magnetic field.");
+            return wpe2 + k_vec->dot(k_vec) - w*w;
+        }
+    };
+
+///  D = k_par^2 v_s^2 - w^2.
+    template<typename T=double, bool SAFE_MATH=false>
+    class acoustic_wave final : public physics<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            const T mi = eq->get_ion_mass(0);
+            auto te = eq->get_electron_temperature(x, y, z);
+            auto ti = eq->get_ion_temperature(0, x, y, z);
+            const T gamma = 3.0;
+            auto vs2 = (this->q*te + gamma*this->q*ti)/(mi*this->c*this->c);
+            return this->kpara2(eq->get_magnetic_field(x, y, z), k_vec)*vs2 - w*w;
+        }
+    };
+
+///  D = n_par^2 + n_perp^2 - (1 - exp(-(x^2 + y^2)/0.1)/2).
+    template<typename T=double, bool SAFE_MATH=false>
+    class gaussian_well final : public dispersion_function<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &) {
+            const T c = 1.0;
+            auto well = c - 0.5*graph::exp(-(x*x + y*y)/0.1);
+            auto npar2 = k_vec->get_z()*k_vec->get_z()*c*c/(w*w);
+            auto nperp2 = (k_vec->get_x()*k_vec->get_x() + k_vec->get_y()*k_vec->get_y())*c*c/(w*w);
+            return npar2 + nperp2 - well;
+        }
+    };
+
+///  D = w_ce - k_perp^2 v_s^2 - w^2  (as written in the reference, dispersion.hpp:739-783).
+    template<typename T=double, bool SAFE_MATH=false>
+    class ion_cyclotron final : public physics<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            const T mi = eq->get_ion_mass(0);
+            auto te = eq->get_electron_temperature(x, y, z);
+            auto ti = eq->get_ion_temperature(0, x, y, z);
+            const T gamma = 3.0;
+            auto vs2 = (this->q*te + gamma*this->q*ti)/(mi*this->c*this->c);
+            auto b_vec = eq->get_magnetic_field(x, y, z);
+            auto wce = build_cyclotron_frequency(-this->q, b_vec->length(), this->me, this->c);
+            auto kperp = b_vec->unit()->cross(k_vec)->length();
+            return wce - kperp*kperp*vs2 - w*w;
+        }
+    };
+
+///  O-mode: D = 1 - w_pe^2/w^2 - n_perp^2.
+    template<typename T=double, bool SAFE_MATH=false>
+    class ordinary_wave final : public physics<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            auto wpe2 = build_plasma_frequency(eq->get_electron_density(x, y, z), this->q, this->me, this->c, this->epsilon0);
+            auto n = k_vec/w;
+            auto b_hat = eq->get_magnetic_field(x, y, z)->unit();
+            auto nperp = b_hat->cross(n);
+            auto nperp2 = nperp->dot(nperp);
+            return 1.0 - wpe2/(w*w) - nperp2;
+        }
+    };
+
+///  X-mode: D = 1 - w_pe^2/w^2 (w^2 - w_pe^2)/(w^2 - w_h^2) - n_perp^2.
+    template<typename T=double, bool SAFE_MATH=false>
+    class extra_ordinary_wave final : public physics<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            auto wpe2 = build_plasma_frequency(eq->get_electron_density(x, y, z), this->q, this->me, this->c, this->epsilon0);
+            auto b_vec = eq->get_magnetic_field(x, y, z);
+            auto wec = build_cyclotron_frequency(-this->q, b_vec->length(), this->me, this->c);
+            auto n = k_vec/w;
+            auto nperp = b_vec->unit()->cross(n);
+            auto nperp2 = nperp->dot(nperp);
+            auto wh = wpe2 + wec*wec;
+            auto w2 = w*w;
+            return 1.0 - wpe2/w2*(w2 - wpe2)/(w2 - wh) - nperp2;
+        }
+    };
+
+///  Cold plasma determinant with electrons and every ion species of the equilibrium.
+    template<typename T=double, bool SAFE_MATH=false>
+    class cold_plasma : public physics<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            auto wpe2 = build_plasma_frequency(eq->get_electron_density(x, y, z), this->q, this->me, this->c, this->epsilon0);
+            auto b_vec = eq->get_magnetic_field(x, y, z);
+            auto b_len = b_vec->length();
+            auto ec = build_cyclotron_frequency(-this->q, b_len, this->me, this->c);
+
+            auto w2 = w*w;
+            auto denome = 1.0 - ec*ec/w2;
+            auto e11 = 1.0 - (wpe2/w2)/denome;
+            auto e12 = ((ec/w)*(wpe2/w2))/denome;
+            auto e33 = wpe2;
+            for (size_t i = 0, ie = eq->get_num_ion_species(); i < ie; i++) {
+                const T mi = eq->get_ion_mass(i);
+                const T charge = static_cast<T> (eq->get_ion_charge(i))*this->q;
+                auto wpi2 = build_plasma_frequency(eq->get_ion_density(i, x, y, z), charge, mi, this->c, this->epsilon0);
+                auto ic = build_cyclotron_frequency(charge, b_len, mi, this->c);
+                auto denomi = 1.0 - ic*ic/w2;
+                e11 = e11 - (wpi2/w2)/denomi;
+                e12 = e12 + ((ic/w)*(wpi2/w2))/denomi;
+                e33 = e33 + wpi2;
+            }
+            e12 = -1.0*e12;
+            e33 = 1.0 - e33/w2;
+
+            auto n = k_vec/w;
+            auto b_hat = b_vec->unit();
+            auto npara = b_hat->dot(n);
+            auto npara2 = npara*npara;
+            auto nperp = b_hat->cross(n)->length();
+            auto nperp2 = nperp*nperp;
+
+            auto m11 = e11 - npara2;
+            auto m12 = e12;
+            auto m13 = npara*nperp;
+            auto m22 = e11 - npara2 - nperp2;
+            auto m33 = e33 - nperp2;
+            return (m11*m22 - m12*m12)*m33 - m22*(m13*m13);
+        }
+    };
+
+    template<class D>
+    concept function = std::is_base_of<dispersion_function<typename D::base, D::safe_math>, D>::value;
+
+//------------------------------------------------------------------------------
+///  Ray equations from a dispersion function (dispersion.hpp:1369-1434).
+//------------------------------------------------------------------------------
+    template<function DISPERSION_FUNCTION>
+    class dispersion_interface {
+    protected:
+        typedef typename DISPERSION_FUNCTION::base T;
+        static constexpr bool SAFE_MATH = DISPERSION_FUNCTION::safe_math;
+        vector_ptr k_vec;
+        leaf_ptr D;
+        leaf_ptr dxdt, dydt, dzdt, dkxdt, dkydt, dkzdt, dsdt;
+    public:
+        dispersion_interface(leaf_ptr w, leaf_ptr kx, leaf_ptr ky, leaf_ptr kz,
+                             leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr t,
+                             equilibrium::shared<T, SAFE_MATH> &eq) :
+        k_vec(kx*eq->get_esup1(x, y, z) + ky*eq->get_esup2(x, y, z) + kz*eq->get_esup3(x, y, z)),
+        D(DISPERSION_FUNCTION().D(w, k_vec, x, y, z, t, eq)) {
+//  Correction for k_vec depending on the coordinates (curvilinear equilibria).
+            auto dkdx = k_vec->df(x);
+            auto dkdy = k_vec->df(y);
+            auto dkdz = k_vec->df(z);
+            auto dDdk_vec = graph::vector(D->df(k_vec->get_x()), D->df(k_vec->get_y()), D->df(k_vec->get_z()));
+
+            auto dDdw = D->df(w);
+            auto dDdkx = D->df(kx);
+            auto dDdky = D->df(ky);
+            auto dDdkz = D->df(kz);
+            auto dDdx = D->df(x);
+            auto dDdy = D->df(y);
+            auto dDdz = D->df(z);
+
+            if (graph::pseudo_variable_cast(x).get()) {
+                dkdx = dkdx->remove_pseudo();
+                dkdy = dkdy->remove_pseudo();
+                dkdz = dkdz->remove_pseudo();
+                dDdk_vec = dDdk_vec->remove_pseudo();
+                dDdw = dDdw->remove_pseudo();
+                dDdkx = dDdkx->remove_pseudo();
+                dDdky = dDdky->remove_pseudo();
+                dDdkz = dDdkz->remove_pseudo();
+                dDdx = dDdx->remove_pseudo();
+                dDdy = dDdy->remove_pseudo();
+                dDdz = dDdz->remove_pseudo();
+            }
+
+            dxdt = -dDdkx/dDdw;
+            dydt = -dDdky/dDdw;
+            dzdt = -dDdkz/dDdw;
+            dkxdt = (dDdx - dDdk_vec->dot(dkdx))/dDdw;
+            dkydt = (dDdy - dDdk_vec->dot(dkdy))/dDdw;
+            dkzdt = (dDdz - dDdk_vec->dot(dkdz))/dDdw;
+            dsdt = graph::vector(dxdt, dydt, dzdt)->length();
+        }
+
+///  Newton solve of D = 0 for one of the inputs (dispersion.hpp:1452-1475).
+        leaf_ptr solve(leaf_ptr x, graph::input_nodes<T, SAFE_MATH> inputs, const size_t index=0,
+                       const T tolerance = 1.0E-30, const size_t max_iterations = 1000,
+                       const solver::newton_mode mode = solver::newton_mode::ensemble) {
+            auto x_var = graph::variable_cast(x);
+            workflow::manager<T, SAFE_MATH> work(index);
+            solver::newton<T, SAFE_MATH> (work, {x}, inputs, D, graph::shared_random_state<T, SAFE_MATH> (),
+                                          tolerance, max_iterations, 1.0, mode);
+            work.compile();
+            work.run();
+            work.copy_to_host(x, x_var->data());
+            return D*D;
+        }
+
+        leaf_ptr get_residual() { return D*D; }
+        leaf_ptr get_d() { return D; }
+        leaf_ptr get_dsdt() { return dsdt; }
+        leaf_ptr get_dxdt() { return dxdt; }
+        leaf_ptr get_dydt() { return dydt; }
+        leaf_ptr get_dzdt() { return dzdt; }
+        leaf_ptr get_dkxdt() { return dkxdt; }
+        leaf_ptr get_dkydt() { return dkydt; }
+        leaf_ptr get_dkzdt() { return dkzdt; }
+        void print_dispersion() { D->to_latex(); std::cout << std::endl; }
+    };
+}
+
+#endif /* gfb_graph_dispersion_hpp */

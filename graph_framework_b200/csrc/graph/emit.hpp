@@ -1,0 +1,448 @@
+//------------------------------------------------------------------------------
+//  emit.hpp -- CUDA code generation for the sm_100a skeletons.
+//
+//  Turns the interned expression DAG of one work item into a traits struct for
+//  skeleton.cuh: a straight-line `body` (one SSA statement per live node),
+//  load/apply/store glue and the packed spline-table groups it reads.
+//
+//  Reference counterpart: the per-node compile() methods plus
+//  cuda_context::create_kernel_prefix/postfix
+//  (/root/reference/graph_framework/cuda_context.hpp:713-946,
+//   arithmetic.hpp:645-669 etc., piecewise.hpp:348-437, 1071-1208).
+//  Differences that matter for speed:
+//    * a reciprocal is computed once per distinct denominator and multiplied;
+//    * the table index is computed once per distinct (argument, grid);
+//    * all coefficient tables that share an index are packed cell-major
+//      (array-of-structs) so one cell is a contiguous row, read with 16-byte
+//      loads from L1/L2 or staged into shared memory by TMA when small;
+//    * the body is a device function, not a whole kernel: the Runge-Kutta
+//      stage loop calls ONE right-hand-side body instead of four inlined copies.
+//------------------------------------------------------------------------------
+#ifndef gfb_graph_emit_hpp
+#define gfb_graph_emit_hpp
+
+#include <algorithm>
+#include <cstdio>
+#include <set>
+#include <unordered_set>
+
+#include "node.hpp"
+
+namespace jit {
+    enum class kernel_kind { generic, rk2, rk4, newton };
+
+//------------------------------------------------------------------------------
+///  One packed group of coefficient tables sharing a cell index.
+//------------------------------------------------------------------------------
+    struct table_group {
+        graph::op_t op;
+        graph::leaf_ptr arg0, arg1;
+        size_t num_cols;
+        std::array<double, 2> scale, offset;
+        size_t cells;
+        std::vector<graph::table_ptr> members;
+        size_t stride;                  ///< doubles per cell row (padded)
+        bool staged;                    ///< copied to shared memory by TMA
+        size_t smem_offset;             ///< byte offset in dynamic shared memory
+        std::vector<double> packed;     ///< cells*stride doubles, cell major
+        size_t bytes() const { return packed.size()*sizeof(double); }
+    };
+
+//------------------------------------------------------------------------------
+///  Everything the runtime needs to launch one emitted kernel.
+//------------------------------------------------------------------------------
+    struct kernel_info {
+        std::string name;
+        kernel_kind kind;
+        graph::input_nodes<> inputs;
+        graph::output_nodes<> outputs;          ///< one device buffer each, after the inputs
+        std::vector<bool> input_written;
+        std::vector<table_group> groups;        ///< pointer slots after the outputs
+        size_t size;
+        size_t smem_bytes;
+        size_t num_statements;
+        size_t num_divides;
+        size_t num_reciprocals;
+    };
+
+    struct emit_options {
+        size_t stage_limit_bytes = 32*1024;     ///< largest group staged into shared memory
+        size_t stage_total_bytes = 96*1024;
+        bool share_reciprocals = true;
+        bool stage_tables = true;
+        unsigned block_size = 128;
+        unsigned min_blocks = 1;
+    };
+
+    inline std::string literal(const double d) {
+        char buf[64];
+        if (std::isinf(d)) return d > 0 ? "(1.0/0.0)" : "(-1.0/0.0)";
+        if (std::isnan(d)) return "(0.0/0.0)";
+        std::snprintf(buf, sizeof(buf), "%.17g", d);
+        std::string s(buf);
+        if (s.find_first_of(".en") == std::string::npos) s += ".0";
+        if (d < 0.0 || (d == 0.0 && std::signbit(d))) s = "(" + s + ")";
+        return s;
+    }
+
+//------------------------------------------------------------------------------
+///  Emits one kernel.
+//------------------------------------------------------------------------------
+    class body_emitter {
+    private:
+        std::ostringstream &out;
+        const emit_options &opt;
+        kernel_info &info;
+        std::unordered_map<const graph::leaf_node *, std::string> reg;
+        std::unordered_map<const graph::leaf_node *, std::string> inv_reg;
+        std::unordered_map<const graph::leaf_node *, size_t> denominators;
+        std::unordered_map<const graph::leaf_node *, std::pair<size_t, size_t>> slot;   // piecewise -> (group, member)
+        std::unordered_set<const graph::leaf_node *> visited;
+        std::vector<std::string> index_reg;
+        std::vector<std::vector<bool>> pair_loaded;
+
+        static const graph::leaf_node *strip(const graph::leaf_node *n) {
+            while (n->op == graph::op_t::pseudo) n = n->args[0].get();
+            return n;
+        }
+
+//  Pass 1: find table groups and count how often each node is a denominator.
+        void scan(const graph::leaf_node *n) {
+            n = strip(n);
+            if (!visited.insert(n).second) return;
+            if (n->op == graph::op_t::variable) {
+                bool found = false;
+                for (auto &in : info.inputs) found = found || in.get() == n;
+                if (!found) {
+                    std::cerr << "Kernel " << info.name << ": variable " << n->symbol
+                              << " is used but is not an input." << std::endl;
+                    std::exit(-1);
+                }
+            }
+            if (n->op == graph::op_t::div) denominators[strip(n->args[1].get())]++;
+            if (n->is_piecewise()) {
+                const graph::leaf_node *a0 = strip(n->args[0].get());
+                const graph::leaf_node *a1 = n->args[1].get() ? strip(n->args[1].get()) : nullptr;
+                size_t g = 0;
+                for (; g < info.groups.size(); g++) {
+                    auto &grp = info.groups[g];
+                    if (grp.op == n->op && grp.arg0.get() == a0 && grp.arg1.get() == a1 &&
+                        grp.num_cols == n->num_cols && grp.scale == n->scale && grp.offset == n->offset &&
+                        grp.cells == n->table->values.size()) break;
+                }
+                if (g == info.groups.size()) {
+                    table_group grp;
+                    grp.op = n->op;
+                    grp.arg0 = std::const_pointer_cast<graph::leaf_node> (a0->shared_from_this());
+                    if (a1) grp.arg1 = std::const_pointer_cast<graph::leaf_node> (a1->shared_from_this());
+                    grp.num_cols = n->num_cols;
+                    grp.scale = n->scale;
+                    grp.offset = n->offset;
+                    grp.cells = n->table->values.size();
+                    info.groups.push_back(grp);
+                }
+                auto &members = info.groups[g].members;
+                size_t m = 0;
+                for (; m < members.size(); m++) if (members[m] == n->table) break;
+                if (m == members.size()) members.push_back(n->table);
+                slot[n] = {g, m};
+            }
+            for (size_t i = 0, ie = n->num_args(); i < ie; i++) scan(n->args[i].get());
+        }
+
+        void pack_groups() {
+            size_t staged_total = 0;
+            size_t offset = 16;     // mbarrier lives in the first 16 bytes
+            for (auto &g : info.groups) {
+                const size_t k = g.members.size();
+                const size_t bytes_even = g.cells*(k + (k & 1))*sizeof(double);
+                g.staged = opt.stage_tables && bytes_even <= opt.stage_limit_bytes &&
+                           staged_total + bytes_even <= opt.stage_total_bytes;
+//  Shared memory rows get an odd stride: consecutive cells then start in
+//  different banks, so 32 rays in 32 different cells read one member without
+//  conflicts beyond the 2 wavefronts 64-bit accesses need anyway.  Global rows
+//  get an even stride so every pair of members is one aligned 16-byte load.
+                g.stride = g.staged ? (k | 1) : (k + (k & 1));
+                g.packed.assign(((g.cells*g.stride + 1)/2)*2, 0.0);
+                for (size_t m = 0; m < k; m++)
+                    for (size_t c = 0; c < g.cells; c++)
+                        g.packed[c*g.stride + m] = g.members[m]->values[c];
+                if (g.staged) {
+                    g.smem_offset = offset;
+                    offset += (g.bytes() + 127)/128*128;
+                    staged_total += g.bytes();
+                } else {
+                    g.smem_offset = 0;
+                }
+            }
+            info.smem_bytes = staged_total ? offset : 0;
+        }
+
+        std::string index_expr(const std::string &x, const double scale, const double offset, const size_t n) {
+//  The reference's contract: (uint)min(max((x - offset)/scale, 0), n - 1)  (piecewise.hpp:26-65).
+            return "static_cast<unsigned> (fmin(fmax((" + x + " - " + literal(offset) + ")/" + literal(scale) +
+                   ", 0.0), " + literal(static_cast<double> (n - 1)) + "))";
+        }
+
+        const std::string &emit(const graph::leaf_node *n) {
+            n = strip(n);
+            auto found = reg.find(n);
+            if (found != reg.end()) return found->second;
+            using graph::op_t;
+            std::string rhs;
+            if (n->op == op_t::constant) {
+                return reg.emplace(n, literal(n->value)).first->second;
+            }
+            if (n->op == op_t::variable) {
+                for (size_t i = 0; i < info.inputs.size(); i++)
+                    if (info.inputs[i].get() == n)
+                        return reg.emplace(n, "v[" + std::to_string(i) + "]").first->second;
+            }
+            if (n->is_piecewise()) {
+                const auto [g, m] = slot.at(n);
+                auto &grp = info.groups[g];
+                if (index_reg[g].empty()) {
+                    const std::string x = emit(grp.arg0.get());
+                    std::string expr;
+                    if (grp.op == op_t::piecewise_1d) {
+                        expr = index_expr(x, grp.scale[0], grp.offset[0], grp.cells);
+                    } else {
+                        const std::string y = emit(grp.arg1.get());
+                        expr = index_expr(x, grp.scale[0], grp.offset[0], grp.cells/grp.num_cols) + "*" +
+                               std::to_string(grp.num_cols) + "u + " +
+                               index_expr(y, grp.scale[1], grp.offset[1], grp.num_cols);
+                    }
+                    index_reg[g] = "row" + std::to_string(g);
+                    out << "        const double *" << index_reg[g] << " = ";
+                    if (grp.staged) {
+                        out << "reinterpret_cast<const double *> (gfb::smem + " << grp.smem_offset << ")";
+                    } else {
+                        out << "tg[" << g << "]";
+                    }
+                    out << " + (" << expr << ")*" << grp.stride << "u;" << std::endl;
+                    info.num_statements++;
+                }
+                const std::string name = "c" + std::to_string(g) + "_" + std::to_string(m);
+                if (grp.staged) {
+                    out << "        const double " << name << " = " << index_reg[g] << "[" << m << "];" << std::endl;
+                } else {
+                    const size_t p = m/2;
+                    const std::string pname = "p" + std::to_string(g) + "_" + std::to_string(p);
+                    if (!pair_loaded[g][p]) {
+                        pair_loaded[g][p] = true;
+                        out << "        const double2 " << pname << " = __ldg(reinterpret_cast<const double2 *> ("
+                            << index_reg[g] << ") + " << p << ");" << std::endl;
+                    }
+                    out << "        const double " << name << " = " << pname << (m & 1 ? ".y" : ".x") << ";" << std::endl;
+                }
+                info.num_statements++;
+                return reg.emplace(n, name).first->second;
+            }
+
+            std::vector<std::string> a;
+            for (size_t i = 0, ie = n->num_args(); i < ie; i++) {
+                if (n->op == op_t::div && i == 1) {
+                    const graph::leaf_node *d = strip(n->args[1].get());
+                    if (opt.share_reciprocals && denominators[d] > 1) {
+                        auto inv = inv_reg.find(d);
+                        if (inv == inv_reg.end()) {
+                            const std::string dreg = emit(d);
+                            const std::string iname = "i" + std::to_string(d->id);
+                            out << "        const double " << iname << " = 1.0/" << dreg << ";" << std::endl;
+                            info.num_statements++;
+                            info.num_reciprocals++;
+                            inv = inv_reg.emplace(d, iname).first;
+                        }
+                        a.push_back(inv->second);
+                        continue;
+                    }
+                }
+                a.push_back(emit(n->args[i].get()));
+            }
+            switch (n->op) {
+                case op_t::add: rhs = a[0] + " + " + a[1]; break;
+                case op_t::sub: rhs = a[0] + " - " + a[1]; break;
+                case op_t::mul: rhs = a[0] + "*" + a[1]; break;
+                case op_t::div:
+                    if (inv_reg.count(strip(n->args[1].get()))) {
+                        rhs = a[0] + "*" + a[1];
+                    } else {
+                        rhs = a[0] + "/" + a[1];
+                        info.num_divides++;
+                    }
+                    break;
+                case op_t::fma: rhs = "fma(" + a[0] + ", " + a[1] + ", " + a[2] + ")"; break;
+                case op_t::sqrt: rhs = "sqrt(" + a[0] + ")"; break;
+                case op_t::exp: rhs = "exp(" + a[0] + ")"; break;
+                case op_t::log: rhs = "log(" + a[0] + ")"; break;
+                case op_t::pow: rhs = "pow(" + a[0] + ", " + a[1] + ")"; break;
+                case op_t::sin: rhs = "sin(" + a[0] + ")"; break;
+                case op_t::cos: rhs = "cos(" + a[0] + ")"; break;
+                case op_t::atan: rhs = "atan2(" + a[1] + ", " + a[0] + ")"; break;
+                default: rhs = "0.0"; break;
+            }
+            const std::string name = "t" + std::to_string(n->id);
+            out << "        const double " << name << " = " << rhs << ";" << std::endl;
+            info.num_statements++;
+            return reg.emplace(n, name).first->second;
+        }
+
+    public:
+        body_emitter(std::ostringstream &out, const emit_options &opt, kernel_info &info) :
+        out(out), opt(opt), info(info) {}
+
+//------------------------------------------------------------------------------
+///  @param[in] results  expressions evaluated by body, r[j] = results[j]
+///  @param[in] apply    (input index, result index): v[first] = r[second] after each body call
+///  @param[in] store_r  (pointer slot, result index) written on exit
+///  @param[in] evolved  rk kinds: input index of each evolved component
+///  @param[in] time_idx rk kinds: input index of the time variable or -1
+//------------------------------------------------------------------------------
+        void run(const std::vector<graph::leaf_ptr> &results,
+                 const std::vector<std::pair<size_t, size_t>> &apply,
+                 const std::vector<std::pair<size_t, size_t>> &store_r,
+                 const std::vector<size_t> &evolved,
+                 const int time_idx) {
+            for (auto &r : results) scan(r.get());
+            pack_groups();
+            index_reg.assign(info.groups.size(), "");
+            pair_loaded.clear();
+            for (auto &g : info.groups) pair_loaded.emplace_back((g.stride + 1)/2, false);
+
+            const size_t ni = info.inputs.size(), nr = results.size(), ng = info.groups.size();
+            const size_t np = ni + info.outputs.size();
+            const std::string k = info.name + "_k";
+            size_t staged_bytes = 0;
+            for (auto &g : info.groups) if (g.staged) staged_bytes += g.bytes();
+            out << std::endl << "struct " << k << " {" << std::endl
+                << "    static constexpr int NI = " << ni << ", NR = " << nr << ", NG = " << ng
+                << ", NP = " << np << ", NE = " << std::max<size_t> (evolved.size(), 1) << ", TI = " << time_idx << ";" << std::endl
+                << "    static constexpr unsigned SMEM_BYTES = " << info.smem_bytes << ", STAGED_BYTES = " << staged_bytes << ";" << std::endl;
+            auto table_fn = [&] (const char *type, const char *name, auto value) {
+                out << "    __device__ static constexpr " << type << " " << name << "(const int g) { return ";
+                for (size_t g = 0; g < ng; g++) out << "g == " << g << " ? " << value(info.groups[g]) << " : ";
+                out << "0; }" << std::endl;
+            };
+            table_fn("bool", "group_staged", [] (const table_group &g) { return g.staged ? "true" : "false"; });
+            table_fn("unsigned", "group_offset", [] (const table_group &g) { return std::to_string(g.smem_offset) + "u"; });
+            table_fn("unsigned", "group_bytes", [] (const table_group &g) { return std::to_string(g.bytes()) + "u"; });
+            out << "    __device__ static constexpr int ev(const int e) { return ";
+            for (size_t e = 0; e < evolved.size(); e++) out << "e == " << e << " ? " << evolved[e] << " : ";
+            out << "0; }" << std::endl;
+
+            out << "    __device__ static __forceinline__ void load(double (&v)[NI + 1], const gfb_args &a, const unsigned long long i) {" << std::endl;
+            for (size_t j = 0; j < ni; j++) {
+                if (info.input_written[j]) {
+                    out << "        v[" << j << "] = a.ptr[" << j << "][i];" << std::endl;
+                } else {
+                    out << "        v[" << j << "] = __ldg(a.ptr[" << j << "] + i);" << std::endl;
+                }
+            }
+            out << "    }" << std::endl;
+            out << "    __device__ static __forceinline__ void apply(double (&v)[NI + 1], const double (&r)[NR + 1]) {" << std::endl;
+            for (auto &[vi, ri] : apply) out << "        v[" << vi << "] = r[" << ri << "];" << std::endl;
+            out << "    }" << std::endl;
+            out << "    __device__ static __forceinline__ void store(const double (&v)[NI + 1], const double (&r)[NR + 1], const gfb_args &a, const unsigned long long i) {" << std::endl;
+            for (size_t j = 0; j < ni; j++)
+                if (info.input_written[j]) out << "        a.ptr[" << j << "][i] = v[" << j << "];" << std::endl;
+            for (auto &[pi, ri] : store_r) out << "        a.ptr[" << pi << "][i] = r[" << ri << "];" << std::endl;
+            out << "    }" << std::endl;
+
+            out << "    __device__ static __forceinline__ void body(const double (&v)[NI + 1], double (&r)[NR + 1], const double *(&tg)[NG + 1]) {" << std::endl;
+            std::vector<std::string> regs;
+            for (auto &r : results) regs.push_back(emit(r.get()));
+            for (size_t j = 0; j < nr; j++) out << "        r[" << j << "] = " << regs[j] << ";" << std::endl;
+            out << "    }" << std::endl << "};" << std::endl;
+
+            out << "extern \"C\" __global__ void __launch_bounds__(" << opt.block_size << ", " << opt.min_blocks << ") "
+                << info.name << "(const __grid_constant__ gfb_args a) {" << std::endl;
+            switch (info.kind) {
+                case kernel_kind::generic: out << "    gfb::generic_item<" << k << "> (a);"; break;
+                case kernel_kind::newton: out << "    gfb::newton_item<" << k << "> (a);"; break;
+                case kernel_kind::rk2: out << "    gfb::runge_kutta<" << k << ", gfb::rk2_tableau> (a);"; break;
+                case kernel_kind::rk4: out << "    gfb::runge_kutta<" << k << ", gfb::rk4_tableau> (a);"; break;
+            }
+            out << std::endl << "}" << std::endl;
+        }
+    };
+
+//------------------------------------------------------------------------------
+///  Emit a reference-style work item (inputs, outputs, setters).
+//------------------------------------------------------------------------------
+    inline kernel_info emit_item(std::ostringstream &out, const emit_options &opt,
+                                 const kernel_kind kind, const std::string &name,
+                                 graph::input_nodes<> inputs, graph::output_nodes<> outputs,
+                                 graph::map_nodes<> setters, const size_t size) {
+        kernel_info info;
+        info.name = name;
+        info.kind = kind;
+        info.inputs = inputs;
+        info.size = size;
+        info.smem_bytes = 0;
+        info.num_statements = info.num_divides = info.num_reciprocals = 0;
+        info.input_written.assign(inputs.size(), false);
+
+        std::vector<graph::leaf_ptr> results;
+        std::vector<std::pair<size_t, size_t>> apply, store_r;
+        for (auto &[expr, var] : setters) {
+            if (expr.get() == var.get()) continue;      // self assignment (cpu_context.hpp:522)
+            const size_t vi = std::find(inputs.begin(), inputs.end(), var) - inputs.begin();
+            if (vi == inputs.size()) {
+                std::cerr << "Kernel " << name << ": setter target is not an input." << std::endl;
+                std::exit(-1);
+            }
+            info.input_written[vi] = true;
+            apply.push_back({vi, results.size()});
+            results.push_back(expr);
+        }
+        for (auto &o : outputs) {
+            if (graph::variable_cast(o).get() &&
+                std::find(inputs.begin(), inputs.end(), o) != inputs.end()) continue;   // already a buffer
+            store_r.push_back({inputs.size() + info.outputs.size(), results.size()});
+            info.outputs.push_back(o);
+            results.push_back(o);
+        }
+        body_emitter(out, opt, info).run(results, apply, store_r, {}, -1);
+        return info;
+    }
+
+//------------------------------------------------------------------------------
+///  Emit a staged Runge-Kutta kernel: `rates[e]` is d(evolved[e])/dt.
+//------------------------------------------------------------------------------
+    inline kernel_info emit_runge_kutta(std::ostringstream &out, const emit_options &opt,
+                                        const kernel_kind kind, const std::string &name,
+                                        graph::input_nodes<> inputs,
+                                        std::vector<graph::leaf_ptr> evolved,
+                                        std::vector<graph::leaf_ptr> rates,
+                                        graph::leaf_ptr time, graph::leaf_ptr dt,
+                                        graph::leaf_ptr residual, const size_t size) {
+        kernel_info info;
+        info.name = name;
+        info.kind = kind;
+        info.inputs = inputs;
+        info.size = size;
+        info.smem_bytes = 0;
+        info.num_statements = info.num_divides = info.num_reciprocals = 0;
+        info.input_written.assign(inputs.size(), false);
+        std::vector<size_t> ev;
+        for (auto &e : evolved) {
+            const size_t vi = std::find(inputs.begin(), inputs.end(), e) - inputs.begin();
+            assert(vi < inputs.size() && "Evolved variable must be an input.");
+            info.input_written[vi] = true;
+            ev.push_back(vi);
+        }
+        int ti = -1;
+        if (time.get()) {
+            ti = static_cast<int> (std::find(inputs.begin(), inputs.end(), time) - inputs.begin());
+            info.input_written[ti] = true;
+        }
+        std::vector<graph::leaf_ptr> results = rates;
+        results.push_back(residual);
+        results.push_back(dt);
+        info.outputs.push_back(residual);
+        body_emitter(out, opt, info).run(results, {}, {{inputs.size(), rates.size()}}, ev, ti);
+        return info;
+    }
+}
+
+#endif /* gfb_graph_emit_hpp */

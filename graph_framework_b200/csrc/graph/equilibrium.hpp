@@ -1,0 +1,348 @@
+//------------------------------------------------------------------------------
+//  equilibrium.hpp -- plasma equilibria as expression graphs.
+//
+//  Mirrors the interface of /root/reference/graph_framework/equilibrium.hpp:
+//  equilibrium::generic (:214-470) and the concrete equilibria
+//  no_magnetic_field (:482), slab (:611), slab_density (:735), slab_field (:864),
+//  gaussian_density (:991), efit (:1146-1616, make_efit :1628-1854) and
+//  vmec (:1868-2413, make_vmec :2424-2640).
+//
+//  Table files: the reference reads netCDF-4; this back end reads the GFBT
+//  container (graph_framework_b200/tools/gfbt.py) that the converter writes from
+//  the same files, variable names unchanged.
+//
+//  Reference quirks that change numbers are reproduced on purpose (SURVEY.md
+//  Appendix B): the density spline's first two tables are the temperature's
+//  (equilibrium.hpp:1478), ion density = electron temperature (:1361), the
+//  efit-local charge 1.60218E-19 (:1359).
+//------------------------------------------------------------------------------
+#ifndef gfb_graph_equilibrium_hpp
+#define gfb_graph_equilibrium_hpp
+
+#include <cstdio>
+
+#include "newton.hpp"
+#include "vector.hpp"
+
+namespace equilibrium {
+    using graph::leaf_ptr;
+    using graph::vector_ptr;
+
+//------------------------------------------------------------------------------
+///  GFBT reader.
+//------------------------------------------------------------------------------
+    struct table_file {
+        std::map<std::string, std::vector<double>> vars;
+        std::map<std::string, std::vector<size_t>> dims;
+
+        explicit table_file(const std::string &path) {
+            FILE *f = std::fopen(path.c_str(), "rb");
+            if (!f) {
+                std::cerr << "Cannot open table file " << path << std::endl;
+                std::exit(-1);
+            }
+            char magic[6];
+            uint32_t n = 0;
+            bool ok = std::fread(magic, 1, 6, f) == 6 && !std::memcmp(magic, "GFBT1\n", 6) && std::fread(&n, 4, 1, f) == 1;
+            for (uint32_t i = 0; ok && i < n; i++) {
+                uint32_t len = 0, rank = 0;
+                ok = std::fread(&len, 4, 1, f) == 1;
+                std::string name(len, '\0');
+                ok = ok && std::fread(name.data(), 1, len, f) == len && std::fread(&rank, 4, 1, f) == 1;
+                std::vector<size_t> d;
+                size_t count = 1;
+                for (uint32_t r = 0; ok && r < rank; r++) {
+                    uint64_t e = 0;
+                    ok = std::fread(&e, 8, 1, f) == 1;
+                    d.push_back(e);
+                    count *= e;
+                }
+                std::vector<double> v(count);
+                ok = ok && std::fread(v.data(), 8, count, f) == count;
+                vars[name] = std::move(v);
+                dims[name] = std::move(d);
+            }
+            std::fclose(f);
+            if (!ok) {
+                std::cerr << "Malformed table file " << path << " (expected GFBT1; convert netCDF files with "
+                             "graph_framework_b200.tools.gfbt.nc_to_gfbt)." << std::endl;
+                std::exit(-1);
+            }
+        }
+        const std::vector<double> &get(const std::string &name) const {
+            auto it = vars.find(name);
+            if (it == vars.end()) {
+                std::cerr << "Table file has no variable " << name << std::endl;
+                std::exit(-1);
+            }
+            return it->second;
+        }
+        double scalar(const std::string &name) const { return get(name).at(0); }
+        size_t dim(const std::string &name) const { return static_cast<size_t> (get("dim:" + name).at(0)); }
+    };
+
+//------------------------------------------------------------------------------
+///  Interface (equilibrium.hpp:214-470).
+//------------------------------------------------------------------------------
+    template<typename T=double, bool SAFE_MATH=false>
+    class generic {
+    protected:
+        const std::vector<T> ion_masses;
+        const std::vector<uint8_t> ion_charges;
+    public:
+        generic(const std::vector<T> &masses, const std::vector<uint8_t> &charges) :
+        ion_masses(masses), ion_charges(charges) {
+            assert(ion_masses.size() == ion_charges.size() && "Masses and charges need the same number of elements.");
+        }
+        virtual ~generic() {}
+        size_t get_num_ion_species() const { return ion_masses.size(); }
+        T get_ion_mass(const size_t index) const { return ion_masses.at(index); }
+        uint8_t get_ion_charge(const size_t index) const { return ion_charges.at(index); }
+
+        virtual leaf_ptr get_electron_density(leaf_ptr x, leaf_ptr y, leaf_ptr z) = 0;
+        virtual leaf_ptr get_ion_density(const size_t index, leaf_ptr x, leaf_ptr y, leaf_ptr z) = 0;
+        virtual leaf_ptr get_electron_temperature(leaf_ptr x, leaf_ptr y, leaf_ptr z) = 0;
+        virtual leaf_ptr get_ion_temperature(const size_t index, leaf_ptr x, leaf_ptr y, leaf_ptr z) = 0;
+        virtual vector_ptr get_magnetic_field(leaf_ptr x, leaf_ptr y, leaf_ptr z) = 0;
+        virtual leaf_ptr get_characteristic_field(const size_t device_number=0) = 0;
+
+        virtual vector_ptr get_esup1(leaf_ptr, leaf_ptr, leaf_ptr) { return graph::vector(1.0, 0.0, 0.0); }
+        virtual vector_ptr get_esup2(leaf_ptr, leaf_ptr, leaf_ptr) { return graph::vector(0.0, 1.0, 0.0); }
+        virtual vector_ptr get_esup3(leaf_ptr, leaf_ptr, leaf_ptr) { return graph::vector(0.0, 0.0, 1.0); }
+        virtual leaf_ptr get_x(leaf_ptr x1, leaf_ptr, leaf_ptr) { return x1; }
+        virtual leaf_ptr get_y(leaf_ptr, leaf_ptr x2, leaf_ptr) { return x2; }
+        virtual leaf_ptr get_z(leaf_ptr, leaf_ptr, leaf_ptr x3) { return x3; }
+    };
+
+    template<typename T=double, bool SAFE_MATH=false>
+    using shared = std::shared_ptr<generic<T, SAFE_MATH>>;
+
+///  Deuterium ion, charge one: the species every reference equilibrium uses.
+    constexpr double deuterium_mass = 3.34449469E-27;
+
+//------------------------------------------------------------------------------
+///  Analytic equilibria share one implementation parameterised by their
+///  density, temperature and field profiles in x.
+//------------------------------------------------------------------------------
+    template<typename T=double, bool SAFE_MATH=false>
+    class analytic : public generic<T, SAFE_MATH> {
+    public:
+        using profile = std::function<leaf_ptr(leaf_ptr, leaf_ptr, leaf_ptr)>;
+        using field = std::function<vector_ptr(leaf_ptr, leaf_ptr, leaf_ptr)>;
+    private:
+        profile density, temperature;
+        field b;
+    public:
+        analytic(profile density, profile temperature, field b) :
+        generic<T, SAFE_MATH> ({deuterium_mass}, {1}), density(density), temperature(temperature), b(b) {}
+        virtual leaf_ptr get_electron_density(leaf_ptr x, leaf_ptr y, leaf_ptr z) final { return density(x, y, z); }
+        virtual leaf_ptr get_ion_density(const size_t, leaf_ptr x, leaf_ptr y, leaf_ptr z) final { return density(x, y, z); }
+        virtual leaf_ptr get_electron_temperature(leaf_ptr x, leaf_ptr y, leaf_ptr z) final { return temperature(x, y, z); }
+        virtual leaf_ptr get_ion_temperature(const size_t, leaf_ptr x, leaf_ptr y, leaf_ptr z) final { return temperature(x, y, z); }
+        virtual vector_ptr get_magnetic_field(leaf_ptr x, leaf_ptr y, leaf_ptr z) final { return b(x, y, z); }
+        virtual leaf_ptr get_characteristic_field(const size_t=0) final { return graph::one(); }
+    };
+
+    namespace profiles {
+        inline leaf_ptr linear(leaf_ptr x, const double amplitude, const double slope) {
+            return graph::constant(amplitude)*(graph::constant(slope)*x + graph::one());
+        }
+    }
+
+///  ne = 1e19 (0.1 x + 1), Te = 1000, B = 0  (equilibrium.hpp:482-600).
+    template<typename T=double, bool SAFE_MATH=false>
+    shared<T, SAFE_MATH> make_no_magnetic_field() {
+        return std::make_shared<analytic<T, SAFE_MATH>> (
+            [] (leaf_ptr x, leaf_ptr, leaf_ptr) { return profiles::linear(x, 1.0E19, 0.1); },
+            [] (leaf_ptr, leaf_ptr, leaf_ptr) { return graph::constant(1000.0); },
+            [] (leaf_ptr, leaf_ptr, leaf_ptr) { return graph::vector(0.0, 0.0, 0.0); });
+    }
+///  ne = 1e19, Te = 1000, B = (0, 0, 0.1 x + 1)  (equilibrium.hpp:611-724).
+    template<typename T=double, bool SAFE_MATH=false>
+    shared<T, SAFE_MATH> make_slab() {
+        return std::make_shared<analytic<T, SAFE_MATH>> (
+            [] (leaf_ptr, leaf_ptr, leaf_ptr) { return graph::constant(1.0E19); },
+            [] (leaf_ptr, leaf_ptr, leaf_ptr) { return graph::constant(1000.0); },
+            [] (leaf_ptr x, leaf_ptr, leaf_ptr) { return graph::vector(0.0, 0.0, 0.1*x + 1.0); });
+    }
+///  ne = 1e19 (0.1 x + 1), Te = 1000, B = (0, 0, 1)  (equilibrium.hpp:735-853).
+    template<typename T=double, bool SAFE_MATH=false>
+    shared<T, SAFE_MATH> make_slab_density() {
+        return std::make_shared<analytic<T, SAFE_MATH>> (
+            [] (leaf_ptr x, leaf_ptr, leaf_ptr) { return profiles::linear(x, 1.0E19, 0.1); },
+            [] (leaf_ptr, leaf_ptr, leaf_ptr) { return graph::constant(1000.0); },
+            [] (leaf_ptr, leaf_ptr, leaf_ptr) { return graph::vector(0.0, 0.0, 1.0); });
+    }
+///  ne = 1e19 (0.01 x + 1), Te = 2000 (0.01 x + 1), B = (0, 0, 0.01 x + 1)  (equilibrium.hpp:864-980).
+    template<typename T=double, bool SAFE_MATH=false>
+    shared<T, SAFE_MATH> make_slab_field() {
+        return std::make_shared<analytic<T, SAFE_MATH>> (
+            [] (leaf_ptr x, leaf_ptr, leaf_ptr) { return profiles::linear(x, 1.0E19, 0.01); },
+            [] (leaf_ptr x, leaf_ptr, leaf_ptr) { return profiles::linear(x, 2000.0, 0.01); },
+            [] (leaf_ptr x, leaf_ptr, leaf_ptr) { return graph::vector(0.0, 0.0, 0.01*x + 1.0); });
+    }
+///  ne = 1e19 exp((x^2 + y^2)/-0.2), Te = 1000, B = (1, 0, 0)  (equilibrium.hpp:991-1108).
+    template<typename T=double, bool SAFE_MATH=false>
+    shared<T, SAFE_MATH> make_gaussian_density() {
+        return std::make_shared<analytic<T, SAFE_MATH>> (
+            [] (leaf_ptr x, leaf_ptr y, leaf_ptr) {
+                return graph::constant(1.0E19)*graph::exp((x*x + y*y)/graph::constant(-0.2));
+            },
+            [] (leaf_ptr, leaf_ptr, leaf_ptr) { return graph::constant(1000.0); },
+            [] (leaf_ptr, leaf_ptr, leaf_ptr) { return graph::vector(1.0, 0.0, 0.0); });
+    }
+
+//------------------------------------------------------------------------------
+///  Cubic spline in the *un-normalised* argument: the cell's coefficients are
+///  rewritten on the host so that  p(x) = ((c3 x + c2) x + c1) x + c0  with x the
+///  physical coordinate (equilibrium.hpp:1121-1133).  The rewrite happens in
+///  table space (fold_tables_scope), giving four tables on the same cells.
+//------------------------------------------------------------------------------
+    inline leaf_ptr build_1D_spline(graph::output_nodes<> c, leaf_ptr x, const double scale, const double offset) {
+        leaf_ptr c0, c1, c2, c3;
+        {
+            graph::fold_tables_scope fold;
+            const double s2 = scale*scale, s3 = scale*scale*scale;
+            c3 = c[3]/s3;
+            c2 = c[2]/s2 - 3.0*offset*c[3]/s3;
+            c1 = c[1]/scale - 2.0*offset*c[2]/s2 + 3.0*offset*offset*c[3]/s3;
+            c0 = c[0] - offset*c[1]/scale + offset*offset*c[2]/s2 - offset*offset*offset*c[3]/s3;
+        }
+        return graph::fma(graph::fma(graph::fma(c3, x, c2), x, c1), x, c0);
+    }
+
+//------------------------------------------------------------------------------
+///  EFIT tokamak equilibrium: bicubic psi(R, Z), cubic profiles in psi.
+//------------------------------------------------------------------------------
+    template<typename T=double, bool SAFE_MATH=false>
+    class efit final : public generic<T, SAFE_MATH> {
+    public:
+        struct tables {
+            double psimin, dpsi, rmin, dr, zmin, dz;
+            double te_scale, ne_scale, pres_scale;
+            size_t num_cols;
+            std::array<std::vector<double>, 4> te, ne, pres, fpol;
+            std::array<std::array<std::vector<double>, 4>, 4> psi;     // psi[i][j] = c_ij, i: power of R, j: power of Z
+        };
+    private:
+        const tables tab;
+        leaf_ptr x_cache, y_cache, z_cache;
+        leaf_ptr ne_cache, ni_cache, te_cache, ti_cache, psi_cache;
+        vector_ptr b_cache;
+
+        leaf_ptr profile(const std::array<std::vector<double>, 4> &c, leaf_ptr psi) {
+            return build_1D_spline({graph::piecewise_1D(c[0], psi, tab.dpsi, tab.psimin),
+                                    graph::piecewise_1D(c[1], psi, tab.dpsi, tab.psimin),
+                                    graph::piecewise_1D(c[2], psi, tab.dpsi, tab.psimin),
+                                    graph::piecewise_1D(c[3], psi, tab.dpsi, tab.psimin)},
+                                   psi, tab.dpsi, tab.psimin);
+        }
+
+///  equilibrium.hpp:1279-1313.
+        leaf_ptr build_psi(leaf_ptr r, leaf_ptr z) {
+            std::array<leaf_ptr, 4> c;
+            for (size_t i = 0; i < 4; i++) {
+                graph::output_nodes<> row;
+                for (size_t j = 0; j < 4; j++) {
+                    row.push_back(graph::piecewise_2D(tab.psi[i][j], tab.num_cols, r, tab.dr, tab.rmin, z, tab.dz, tab.zmin));
+                }
+                c[i] = build_1D_spline(row, z, tab.dz, tab.zmin);
+            }
+            auto r_norm = (r - tab.rmin)/tab.dr;
+            return ((c[3]*r_norm + c[2])*r_norm + c[1])*r_norm + c[0];
+        }
+
+///  equilibrium.hpp:1324-1384.
+        void set_cache(leaf_ptr x, leaf_ptr y, leaf_ptr z) {
+            if (x->is_match(x_cache) && y->is_match(y_cache) && z->is_match(z_cache)) return;
+            x_cache = x;
+            y_cache = y;
+            z_cache = z;
+            auto r = graph::sqrt(x*x + y*y);
+            psi_cache = build_psi(r, z);
+            ne_cache = graph::constant(tab.ne_scale)*profile(tab.ne, psi_cache);
+            te_cache = graph::constant(tab.te_scale)*profile(tab.te, psi_cache);
+            auto pressure = graph::constant(tab.pres_scale)*profile(tab.pres, psi_cache);
+            auto q = graph::constant(1.60218E-19);
+            ni_cache = te_cache;
+            ti_cache = (pressure - ne_cache*te_cache*q)/(ni_cache*q);
+
+            auto phi = graph::atan(x, y);
+            auto br = psi_cache->df(z)/r;
+            auto bp = profile(tab.fpol, psi_cache)/r;
+            auto bz = -psi_cache->df(r)/r;
+            auto cos = graph::cos(phi);
+            auto sin = graph::sin(phi);
+            b_cache = graph::vector(br*cos - bp*sin, br*sin + bp*cos, bz);
+        }
+
+    public:
+        efit(const tables &t) : generic<T, SAFE_MATH> ({deuterium_mass}, {1}), tab(t) {
+            x_cache = y_cache = z_cache = graph::zero();
+        }
+        virtual leaf_ptr get_electron_density(leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return ne_cache; }
+        virtual leaf_ptr get_ion_density(const size_t, leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return ni_cache; }
+        virtual leaf_ptr get_electron_temperature(leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return te_cache; }
+        virtual leaf_ptr get_ion_temperature(const size_t, leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return ti_cache; }
+        virtual vector_ptr get_magnetic_field(leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return b_cache; }
+        leaf_ptr get_psi(leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return psi_cache; }
+
+///  |B| on the magnetic axis, found by a damped Newton search (step 0.1) for the
+///  minimum of the normalised flux starting from (1.7, 0, 0)  (equilibrium.hpp:1584-1615).
+        virtual leaf_ptr get_characteristic_field(const size_t device_number=0) final {
+            auto x_axis = graph::variable(1, "x");
+            auto y_axis = graph::variable(1, "y");
+            auto z_axis = graph::variable(1, "z");
+            x_axis->set(1.7);
+            y_axis->set(0.0);
+            z_axis->set(0.0);
+            auto b_mod = get_magnetic_field(x_axis, y_axis, z_axis)->length();
+            graph::input_nodes<> inputs {x_axis, y_axis, z_axis};
+            workflow::manager<T, SAFE_MATH> work(device_number);
+            solver::newton<T, SAFE_MATH> (work, {x_axis, z_axis}, inputs, (psi_cache - tab.psimin)/tab.dpsi,
+                                          graph::shared_random_state<T, SAFE_MATH> (), 1.0E-30, 1000, 0.1);
+            work.add_item(inputs, {b_mod}, {}, graph::shared_random_state<T, SAFE_MATH> (), "bmod_at_axis", 1);
+            work.compile();
+            work.run();
+            T result;
+            work.copy_to_host(b_mod, &result);
+            return graph::constant(result);
+        }
+    };
+
+///  Load EFIT tables (variable names of equilibrium.hpp:1628-1854) from a GFBT file.
+    inline efit<>::tables load_efit_tables(const std::string &spline_file) {
+        table_file f(spline_file);
+        efit<>::tables t;
+        t.rmin = f.scalar("rmin"); t.dr = f.scalar("dr");
+        t.zmin = f.scalar("zmin"); t.dz = f.scalar("dz");
+        t.psimin = f.scalar("psimin"); t.dpsi = f.scalar("dpsi");
+        t.pres_scale = f.scalar("pres_scale");
+        t.ne_scale = f.scalar("ne_scale");
+        t.te_scale = f.scalar("te_scale");
+        t.num_cols = f.dim("numz");
+        for (size_t i = 0; i < 4; i++) {
+            const std::string n = std::to_string(i);
+            t.fpol[i] = f.get("fpol_c" + n);
+            t.pres[i] = f.get("pressure_c" + n);
+            t.te[i] = f.get("te_c" + n);
+            t.ne[i] = f.get("ne_c" + n);
+            for (size_t j = 0; j < 4; j++) t.psi[i][j] = f.get("psi_c" + n + std::to_string(j));
+        }
+//  Reference constructor quirk: ne_c0(te_c0), ne_c1(te_c1)  (equilibrium.hpp:1478).
+        t.ne[0] = t.te[0];
+        t.ne[1] = t.te[1];
+        return t;
+    }
+
+    template<typename T=double, bool SAFE_MATH=false>
+    shared<T, SAFE_MATH> make_efit(const std::string &spline_file) {
+        return std::make_shared<efit<T, SAFE_MATH>> (load_efit_tables(spline_file));
+    }
+    template<typename T=double, bool SAFE_MATH=false>
+    shared<T, SAFE_MATH> make_efit(const efit<>::tables &t) {
+        return std::make_shared<efit<T, SAFE_MATH>> (t);
+    }
+}
+
+#endif /* gfb_graph_equilibrium_hpp */

@@ -1,0 +1,138 @@
+//------------------------------------------------------------------------------
+//  kernels.cu -- statically compiled sm_100a helper kernels of libgfb200.
+//
+//    * max reduction (replaces the generated single-block `max_reduction` of
+//      /root/reference/graph_framework/cuda_context.hpp:954-995),
+//    * power-deposition histogram (algorithm of /root/reference/utilities/bin.py:53-106),
+//    * FP64 FMA peak probe (roofline denominator),
+//    * L2 flush.
+//------------------------------------------------------------------------------
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace {
+//  Order preserving map double -> uint64 so atomicMax works on any sign.
+__device__ __forceinline__ unsigned long long ordered(const double d) {
+    const unsigned long long u = static_cast<unsigned long long> (__double_as_longlong(d));
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(256) max_kernel(const double *__restrict__ in, const unsigned long long n,
+                                                  unsigned long long *__restrict__ result) {
+    double m = -1.7976931348623157e308;
+    bool any_nan = false;
+    for (unsigned long long i = static_cast<unsigned long long> (blockIdx.x)*blockDim.x + threadIdx.x; i < n;
+         i += static_cast<unsigned long long> (gridDim.x)*blockDim.x) {
+        const double v = __ldg(in + i);
+        any_nan = any_nan || (v != v);
+        m = fmax(m, v);
+    }
+    if (any_nan) {
+        m = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    unsigned long long key = any_nan ? 0xffffffffffffffffull : ordered(m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    __shared__ unsigned long long warp_max[8];
+    if ((threadIdx.x & 31) == 0) {
+        warp_max[threadIdx.x >> 5] = key;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        key = warp_max[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_down_sync(0xffu, key, o);
+            key = other > key ? other : key;
+        }
+        if (threadIdx.x == 0) {
+            atomicMax(result, key);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) deposit_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                                      const double *__restrict__ z, const double *__restrict__ w,
+                                                      const unsigned long long n, double *__restrict__ hist,
+                                                      const double x0, const double y0, const double z0,
+                                                      const double ix, const double iy, const double iz,
+                                                      const int nx, const int ny, const int nz) {
+    for (unsigned long long i = static_cast<unsigned long long> (blockIdx.x)*blockDim.x + threadIdx.x; i < n;
+         i += static_cast<unsigned long long> (gridDim.x)*blockDim.x) {
+        const double fx = floor((__ldg(x + i) - x0)*ix);
+        const double fy = floor((__ldg(y + i) - y0)*iy);
+        const double fz = floor((__ldg(z + i) - z0)*iz);
+        if (fx >= 0.0 && fx < nx && fy >= 0.0 && fy < ny && fz >= 0.0 && fz < nz) {
+            const size_t bin = (static_cast<size_t> (fx)*ny + static_cast<size_t> (fy))*nz + static_cast<size_t> (fz);
+            atomicAdd(hist + bin, __ldg(w + i));
+        }
+    }
+}
+
+//  8 independent FMA chains per thread keep the FP64 pipe saturated.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, const int iters, const double a, const double b) {
+    double r0 = threadIdx.x, r1 = r0 + 1.0, r2 = r0 + 2.0, r3 = r0 + 3.0;
+    double r4 = r0 + 4.0, r5 = r0 + 5.0, r6 = r0 + 6.0, r7 = r0 + 7.0;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+            r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+        }
+    }
+    const double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    if (s == 12345.678) {
+        out[0] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(double *p, const size_t n, const double v) {
+    for (size_t i = static_cast<size_t> (blockIdx.x)*blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t> (gridDim.x)*blockDim.x) {
+        p[i] = v;
+    }
+}
+}  // namespace
+
+extern "C" {
+int gfb_k_max(const double *in, unsigned long long n, unsigned long long *result, int sms, cudaStream_t s) {
+    const unsigned long long blocks_needed = (n + 255)/256;
+    const unsigned grid = static_cast<unsigned> (blocks_needed < static_cast<unsigned long long> (sms)*8 ? blocks_needed : sms*8);
+    cudaMemsetAsync(result, 0, sizeof(unsigned long long), s);
+    max_kernel<<<grid ? grid : 1, 256, 0, s>>> (in, n, result);
+    return static_cast<int> (cudaGetLastError());
+}
+double gfb_k_unorder(unsigned long long key) {
+    if (key == 0xffffffffffffffffull) {
+        const unsigned long long nan_bits = 0x7ff8000000000000ull;
+        double d;
+        __builtin_memcpy(&d, &nan_bits, 8);
+        return d;
+    }
+    const unsigned long long u = (key & 0x8000000000000000ull) ? (key & 0x7fffffffffffffffull) : ~key;
+    double d;
+    __builtin_memcpy(&d, &u, 8);
+    return d;
+}
+int gfb_k_deposit(const double *x, const double *y, const double *z, const double *w, unsigned long long n,
+                  double *hist, const double *lo, const double *hi, const int *bins, int sms, cudaStream_t s) {
+    const unsigned long long blocks_needed = (n + 255)/256;
+    const unsigned grid = static_cast<unsigned> (blocks_needed < static_cast<unsigned long long> (sms)*8 ? blocks_needed : sms*8);
+    deposit_kernel<<<grid ? grid : 1, 256, 0, s>>> (x, y, z, w, n, hist, lo[0], lo[1], lo[2],
+                                                     bins[0]/(hi[0] - lo[0]), bins[1]/(hi[1] - lo[1]), bins[2]/(hi[2] - lo[2]),
+                                                     bins[0], bins[1], bins[2]);
+    return static_cast<int> (cudaGetLastError());
+}
+int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s) {
+    fp64_peak_kernel<<<sms*8, 256, 0, s>>> (scratch, iters, 0.999999, 1.0e-6);
+    return static_cast<int> (cudaGetLastError());
+}
+int gfb_k_fill(double *p, size_t n, double v, int sms, cudaStream_t s) {
+    fill_kernel<<<sms*8, 256, 0, s>>> (p, n, v);
+    return static_cast<int> (cudaGetLastError());
+}
+}

@@ -1,0 +1,565 @@
+//------------------------------------------------------------------------------
+//  runtime.cpp -- implementation of include/gfb200.h (the device layer).
+//
+//  B200-native replacement for the device half of
+//  /root/reference/graph_framework/cuda_context.hpp: NVRTC straight to an
+//  sm_100a cubin (the reference goes through generic compute_XY PTX with a
+//  128-register cap, cuda_context.hpp:21,218-299), explicit device buffers with
+//  pinned host mirrors (the reference uses managed memory for everything,
+//  :334-356), a grid-wide max reduction (the reference uses one block, :566-575)
+//  and deferred launches that fuse consecutive steps of one kernel into a
+//  single register-resident multi-step launch.
+//
+//  The CUDA driver is reached through cudaGetDriverEntryPoint so the library
+//  loads (and NVRTC-only entry points work) on machines without libcuda.
+//------------------------------------------------------------------------------
+#include "../../include/gfb200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+extern "C" {
+int gfb_k_max(const double *in, unsigned long long n, unsigned long long *result, int sms, cudaStream_t s);
+double gfb_k_unorder(unsigned long long key);
+int gfb_k_deposit(const double *x, const double *y, const double *z, const double *w, unsigned long long n,
+                  double *hist, const double *lo, const double *hi, const int *bins, int sms, cudaStream_t s);
+int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s);
+int gfb_k_fill(double *p, size_t n, double v, int sms, cudaStream_t s);
+}
+
+namespace {
+const char *skeleton_text =
+#include "skeleton_text.inc"
+;
+
+thread_local std::string last_error;
+
+int fail(const std::string &what) {
+    last_error = what;
+    return 1;
+}
+int check(const cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return 0;
+    return fail(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+//  Mirror of the device-side argument block in skeleton.cuh.
+constexpr int max_ptrs = 56;
+struct device_args {
+    void *ptr[max_ptrs];
+    unsigned long long n;
+    unsigned steps;
+    unsigned flags;
+    double scalar[4];
+};
+
+struct driver_api {
+    CUresult (*ModuleLoadData)(CUmodule *, const void *) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             unsigned, CUstream, void **, void **) = nullptr;
+    CUresult (*FuncGetAttribute)(int *, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    bool loaded = false;
+};
+driver_api driver;
+
+template<typename F>
+bool entry(const char *name, F &f) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+    f = reinterpret_cast<F> (p);
+    return true;
+}
+int load_driver() {
+    if (driver.loaded) return 0;
+    if (!entry("cuModuleLoadData", driver.ModuleLoadData) ||
+        !entry("cuModuleUnload", driver.ModuleUnload) ||
+        !entry("cuModuleGetFunction", driver.ModuleGetFunction) ||
+        !entry("cuLaunchKernel", driver.LaunchKernel) ||
+        !entry("cuFuncGetAttribute", driver.FuncGetAttribute) ||
+        !entry("cuFuncSetAttribute", driver.FuncSetAttribute) ||
+        !entry("cuGetErrorString", driver.GetErrorString)) {
+        return fail("CUDA driver entry points unavailable (no NVIDIA driver?)");
+    }
+    driver.loaded = true;
+    return 0;
+}
+int check_cu(const CUresult r, const char *what) {
+    if (r == CUDA_SUCCESS) return 0;
+    const char *s = nullptr;
+    if (driver.GetErrorString) driver.GetErrorString(r, &s);
+    return fail(std::string(what) + ": " + (s ? s : "unknown driver error"));
+}
+
+struct buffer {
+    void *dev = nullptr;
+    size_t bytes = 0;
+    bool owned = true;
+    void *host = nullptr;       // pinned mirror, created on demand
+};
+
+int nvrtc_compile(const std::string &full_source, const char *options, std::vector<char> &cubin, std::string &log) {
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, full_source.c_str(), "gfb_kernels.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+        return fail("nvrtcCreateProgram failed");
+    }
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
+    bool has_unroll = false;
+    if (options) {
+        std::istringstream is(options);
+        std::string o;
+        while (is >> o) {
+            opts.push_back(o);
+            if (o.rfind("-DGFB_UNROLL_STAGES", 0) == 0) has_unroll = true;
+        }
+    }
+    if (!has_unroll) opts.push_back("-DGFB_UNROLL_STAGES=0");
+    std::vector<const char *> copts;
+    for (auto &o : opts) copts.push_back(o.c_str());
+    const nvrtcResult r = nvrtcCompileProgram(prog, static_cast<int> (copts.size()), copts.data());
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    log.assign(log_size, '\0');
+    if (log_size) nvrtcGetProgramLog(prog, log.data());
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return fail(std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + log);
+    }
+    size_t size = 0;
+    nvrtcGetCUBINSize(prog, &size);
+    cubin.resize(size);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    return 0;
+}
+}  // namespace
+
+struct gfb_kernel {
+    gfb_ctx *ctx;
+    std::string name;
+    CUfunction function;
+    device_args args;
+    unsigned block;
+    unsigned grid;
+    size_t smem;
+    int kind;
+    bool can_repeat;
+};
+
+struct gfb_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    CUmodule module = nullptr;
+    std::map<uint64_t, buffer> buffers;
+    std::vector<std::unique_ptr<gfb_kernel>> kernels;
+    std::string source, log;
+    gfb_kernel *pending = nullptr;
+    unsigned pending_steps = 0;
+    unsigned max_fused = 1024;
+    uint64_t launches = 0;
+    unsigned long long *scratch = nullptr;      // device scalar for reductions
+    unsigned long long *scratch_host = nullptr; // pinned
+    double *flush_buffer = nullptr;
+    size_t flush_count = 0;
+};
+
+namespace {
+int launch_now(gfb_kernel *k, const unsigned steps) {
+    gfb_ctx *c = k->ctx;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    k->args.steps = k->can_repeat || k->kind == 2 ? steps : (steps ? 1u : 0u);
+    void *params[] = {&k->args};
+    c->launches++;
+    return check_cu(driver.LaunchKernel(k->function, k->grid, 1, 1, k->block, 1, 1,
+                                        static_cast<unsigned> (k->smem), reinterpret_cast<CUstream> (c->stream),
+                                        params, nullptr), k->name.c_str());
+}
+int flush(gfb_ctx *c) {
+    if (!c->pending) return 0;
+    gfb_kernel *k = c->pending;
+    const unsigned steps = c->pending_steps;
+    c->pending = nullptr;
+    c->pending_steps = 0;
+    return launch_now(k, steps);
+}
+}  // namespace
+
+extern "C" {
+
+const char *gfb_last_error(void) { return last_error.c_str(); }
+void gfb_set_last_error(const char *text) { last_error = text ? text : ""; }
+const char *gfb_version(void) { return "gfb200 0.1 (sm_100a)"; }
+
+int gfb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+gfb_ctx *gfb_ctx_create(int device) {
+    int n = gfb_device_count();
+    if (n <= 0) {
+        fail("no CUDA device: the B200 back end has no CPU fallback");
+        return nullptr;
+    }
+    device = device%n;
+    if (check(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+    if (check(cudaFree(nullptr), "context init")) return nullptr;
+    if (load_driver()) return nullptr;
+    auto c = std::make_unique<gfb_ctx> ();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return nullptr;
+    if (prop.major != 10) {
+        fail(std::string("device ") + prop.name + " is not sm_100: this back end targets B200 only");
+        return nullptr;
+    }
+    c->sms = prop.multiProcessorCount;
+    if (check(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
+    cudaEventCreate(&c->ev_start);
+    cudaEventCreate(&c->ev_stop);
+    if (check(cudaMalloc(&c->scratch, 64), "cudaMalloc")) return nullptr;
+    if (check(cudaMallocHost(&c->scratch_host, 64), "cudaMallocHost")) return nullptr;
+    return c.release();
+}
+
+void gfb_ctx_destroy(gfb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    flush(c);
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->buffers) {
+        if (kv.second.owned && kv.second.dev) cudaFree(kv.second.dev);
+        if (kv.second.host) cudaFreeHost(kv.second.host);
+    }
+    if (c->module) driver.ModuleUnload(c->module);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->scratch_host) cudaFreeHost(c->scratch_host);
+    if (c->flush_buffer) cudaFree(c->flush_buffer);
+    cudaEventDestroy(c->ev_start);
+    cudaEventDestroy(c->ev_stop);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int gfb_ctx_device_info(gfb_ctx *c, char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor) {
+    cudaDeviceProp prop;
+    if (check(cudaGetDeviceProperties(&prop, c->device), "cudaGetDeviceProperties")) return 1;
+    if (name && name_len) {
+        std::strncpy(name, prop.name, name_len - 1);
+        name[name_len - 1] = '\0';
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+int gfb_compile_to_cubin(const char *source, const char *options, void **cubin, size_t *cubin_size, char **log) {
+    std::vector<char> image;
+    std::string text;
+    const int r = nvrtc_compile(std::string(skeleton_text) + source, options, image, text);
+    if (log) {
+        const std::string &msg = r ? last_error : text;
+        *log = static_cast<char *> (std::malloc(msg.size() + 1));
+        std::memcpy(*log, msg.c_str(), msg.size() + 1);
+    }
+    if (r) return r;
+    *cubin = std::malloc(image.size());
+    std::memcpy(*cubin, image.data(), image.size());
+    *cubin_size = image.size();
+    return 0;
+}
+void gfb_free(void *p) { std::free(p); }
+
+int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int num_names, const char *options) {
+    (void)names; (void)num_names;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    if (flush(c)) return 1;
+    c->source = std::string(skeleton_text) + source;
+    std::vector<char> image;
+    if (nvrtc_compile(c->source, options, image, c->log)) {
+        std::fprintf(stderr, "%s\n", last_error.c_str());
+        return 1;
+    }
+    if (c->module) {
+        cudaStreamSynchronize(c->stream);
+        driver.ModuleUnload(c->module);
+        c->module = nullptr;
+        c->kernels.clear();
+    }
+    return check_cu(driver.ModuleLoadData(&c->module, image.data()), "cuModuleLoadData");
+}
+const char *gfb_source(gfb_ctx *c) { return c->source.c_str(); }
+const char *gfb_compile_log(gfb_ctx *c) { return c->log.c_str(); }
+
+int gfb_buffer(gfb_ctx *c, uint64_t key, size_t bytes, const void *init, void **device_ptr) {
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    auto it = c->buffers.find(key);
+    if (it == c->buffers.end()) {
+        buffer b;
+        b.bytes = bytes;
+        if (check(cudaMalloc(&b.dev, bytes ? bytes : 8), "cudaMalloc")) return 1;
+        if (init) {
+            if (check(cudaMemcpyAsync(b.dev, init, bytes, cudaMemcpyHostToDevice, c->stream), "upload")) return 1;
+            if (check(cudaStreamSynchronize(c->stream), "upload sync")) return 1;   // `init` may be a temporary
+        } else {
+            if (check(cudaMemsetAsync(b.dev, 0, bytes, c->stream), "cudaMemset")) return 1;
+        }
+        it = c->buffers.emplace(key, b).first;
+    } else if (it->second.bytes < bytes) {
+        return fail("gfb_buffer: key exists with a smaller size");
+    }
+    if (device_ptr) *device_ptr = it->second.dev;
+    return 0;
+}
+
+int gfb_buffer_import(gfb_ctx *c, uint64_t key, void *device_ptr, size_t bytes) {
+    auto it = c->buffers.find(key);
+    if (it != c->buffers.end()) {
+        if (flush(c)) return 1;
+        if (it->second.owned && it->second.dev) {
+            cudaStreamSynchronize(c->stream);
+            cudaFree(it->second.dev);
+        }
+        it->second.dev = device_ptr;
+        it->second.bytes = bytes;
+        it->second.owned = false;
+        for (auto &k : c->kernels) (void)k;
+        return 0;
+    }
+    buffer b;
+    b.dev = device_ptr;
+    b.bytes = bytes;
+    b.owned = false;
+    c->buffers.emplace(key, b);
+    return 0;
+}
+
+int gfb_buffer_lookup(gfb_ctx *c, uint64_t key, void **device_ptr, size_t *bytes) {
+    auto it = c->buffers.find(key);
+    if (it == c->buffers.end()) {
+        if (device_ptr) *device_ptr = nullptr;
+        if (bytes) *bytes = 0;
+        return fail("gfb_buffer_lookup: unknown key");
+    }
+    if (device_ptr) *device_ptr = it->second.dev;
+    if (bytes) *bytes = it->second.bytes;
+    return 0;
+}
+
+int gfb_kernel_create(gfb_ctx *c, const char *name, const uint64_t *ptr_keys, int num_ptrs,
+                      size_t num_rays, unsigned block_size, size_t dynamic_smem, int kind, int can_repeat,
+                      gfb_kernel **kernel) {
+    if (!c->module) return fail("gfb_kernel_create: nothing compiled");
+    if (num_ptrs > max_ptrs) return fail("gfb_kernel_create: too many pointer arguments");
+    auto k = std::make_unique<gfb_kernel> ();
+    k->ctx = c;
+    k->name = name;
+    if (check_cu(driver.ModuleGetFunction(&k->function, c->module, name), name)) return 1;
+    std::memset(&k->args, 0, sizeof(k->args));
+    for (int i = 0; i < num_ptrs; i++) {
+        auto it = c->buffers.find(ptr_keys[i]);
+        if (it == c->buffers.end()) return fail(std::string("gfb_kernel_create: missing buffer for ") + name);
+        k->args.ptr[i] = it->second.dev;
+    }
+    k->args.n = num_rays;
+    k->block = block_size;
+    k->grid = static_cast<unsigned> ((num_rays + block_size - 1)/block_size);
+    if (k->grid == 0) k->grid = 1;
+    k->smem = dynamic_smem;
+    k->kind = kind;
+    k->can_repeat = can_repeat != 0;
+    if (dynamic_smem > 48*1024) {
+        if (check_cu(driver.FuncSetAttribute(k->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                             static_cast<int> (dynamic_smem)), "smem attribute")) return 1;
+    }
+    *kernel = k.get();
+    c->kernels.push_back(std::move(k));
+    return 0;
+}
+
+int gfb_kernel_run(gfb_kernel *k) {
+    gfb_ctx *c = k->ctx;
+    if (c->pending == k && c->pending_steps < c->max_fused && (k->kind != 2)) {
+        c->pending_steps++;
+        return 0;
+    }
+    if (flush(c)) return 1;
+    if (k->kind == 2) {
+        return launch_now(k, k->args.steps);    // Newton: steps holds max iterations
+    }
+    c->pending = k;
+    c->pending_steps = 1;
+    return 0;
+}
+
+int gfb_kernel_launch(gfb_kernel *k, unsigned steps) {
+    if (flush(k->ctx)) return 1;
+    return launch_now(k, steps);
+}
+
+int gfb_kernel_set_scalar(gfb_kernel *k, int index, double value) {
+    if (index < 0 || index >= 4) return fail("scalar index out of range");
+    if (flush(k->ctx)) return 1;
+    k->args.scalar[index] = value;
+    return 0;
+}
+
+int gfb_kernel_attributes(gfb_kernel *k, int *regs, int *static_smem, int *local_bytes, int *max_threads) {
+    int v = 0;
+    if (regs) { if (check_cu(driver.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, k->function), "attr")) return 1; *regs = v; }
+    if (static_smem) { if (check_cu(driver.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, k->function), "attr")) return 1; *static_smem = v; }
+    if (local_bytes) { if (check_cu(driver.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, k->function), "attr")) return 1; *local_bytes = v; }
+    if (max_threads) { if (check_cu(driver.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, k->function), "attr")) return 1; *max_threads = v; }
+    return 0;
+}
+
+uint64_t gfb_launch_count(gfb_ctx *c) { return c->launches; }
+int gfb_set_max_fused_steps(gfb_ctx *c, unsigned steps) {
+    if (flush(c)) return 1;
+    c->max_fused = steps ? steps : 1;
+    return 0;
+}
+int gfb_flush(gfb_ctx *c) { return flush(c); }
+
+int gfb_max(gfb_ctx *c, uint64_t key, size_t n, double *result) {
+    if (flush(c)) return 1;
+    auto it = c->buffers.find(key);
+    if (it == c->buffers.end()) return fail("gfb_max: unknown key");
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    c->launches++;
+    if (gfb_k_max(static_cast<const double *> (it->second.dev), n, c->scratch, c->sms, c->stream)) return fail("max kernel launch failed");
+    if (check(cudaMemcpyAsync(c->scratch_host, c->scratch, 8, cudaMemcpyDeviceToHost, c->stream), "max readback")) return 1;
+    if (check(cudaStreamSynchronize(c->stream), "max sync")) return 1;
+    *result = gfb_k_unorder(*c->scratch_host);
+    return 0;
+}
+
+int gfb_wait(gfb_ctx *c) {
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    for (auto &kv : c->buffers) {
+        if (kv.second.host) {
+            if (check(cudaMemcpyAsync(kv.second.host, kv.second.dev, kv.second.bytes, cudaMemcpyDeviceToHost, c->stream), "mirror")) return 1;
+        }
+    }
+    return check(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+}
+
+int gfb_copy_h2d(gfb_ctx *c, uint64_t key, const void *source, size_t bytes) {
+    if (flush(c)) return 1;
+    auto it = c->buffers.find(key);
+    if (it == c->buffers.end()) return fail("gfb_copy_h2d: unknown key");
+    if (bytes == 0 || bytes > it->second.bytes) bytes = it->second.bytes;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    if (check(cudaMemcpyAsync(it->second.dev, source, bytes, cudaMemcpyHostToDevice, c->stream), "h2d")) return 1;
+    return check(cudaStreamSynchronize(c->stream), "h2d sync");
+}
+
+int gfb_copy_d2h(gfb_ctx *c, uint64_t key, void *destination, size_t bytes) {
+    if (flush(c)) return 1;
+    auto it = c->buffers.find(key);
+    if (it == c->buffers.end()) return fail("gfb_copy_d2h: unknown key");
+    if (bytes == 0 || bytes > it->second.bytes) bytes = it->second.bytes;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    if (check(cudaMemcpyAsync(destination, it->second.dev, bytes, cudaMemcpyDeviceToHost, c->stream), "d2h")) return 1;
+    return check(cudaStreamSynchronize(c->stream), "d2h sync");
+}
+
+int gfb_host_ptr(gfb_ctx *c, uint64_t key, void **host_ptr) {
+    auto it = c->buffers.find(key);
+    if (it == c->buffers.end()) return fail("gfb_host_ptr: unknown key");
+    if (!it->second.host) {
+        if (check(cudaMallocHost(&it->second.host, it->second.bytes ? it->second.bytes : 8), "cudaMallocHost")) return 1;
+        if (gfb_copy_d2h(c, key, it->second.host, 0)) return 1;
+    }
+    *host_ptr = it->second.host;
+    return 0;
+}
+
+int gfb_check_value(gfb_ctx *c, uint64_t key, size_t index, double *value) {
+    if (flush(c)) return 1;
+    auto it = c->buffers.find(key);
+    if (it == c->buffers.end()) return fail("gfb_check_value: unknown key");
+    if ((index + 1)*sizeof(double) > it->second.bytes) return fail("gfb_check_value: index out of range");
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    if (check(cudaMemcpyAsync(value, static_cast<const double *> (it->second.dev) + index, sizeof(double),
+                              cudaMemcpyDeviceToHost, c->stream), "check_value")) return 1;
+    return check(cudaStreamSynchronize(c->stream), "check_value sync");
+}
+
+int gfb_timer_start(gfb_ctx *c) {
+    if (flush(c)) return 1;
+    return check(cudaEventRecord(c->ev_start, c->stream), "cudaEventRecord");
+}
+int gfb_timer_stop(gfb_ctx *c, float *ms) {
+    if (flush(c)) return 1;
+    if (check(cudaEventRecord(c->ev_stop, c->stream), "cudaEventRecord")) return 1;
+    if (check(cudaEventSynchronize(c->ev_stop), "cudaEventSynchronize")) return 1;
+    return check(cudaEventElapsedTime(ms, c->ev_start, c->ev_stop), "cudaEventElapsedTime");
+}
+void *gfb_stream(gfb_ctx *c) { return c->stream; }
+
+int gfb_deposit(gfb_ctx *c, const double *x, const double *y, const double *z, const double *weight,
+                size_t n, double *hist, const double *lo, const double *hi, const int *bins) {
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    c->launches++;
+    if (gfb_k_deposit(x, y, z, weight, n, hist, lo, hi, bins, c->sms, c->stream)) return fail("deposit launch failed");
+    return 0;
+}
+
+int gfb_measure_fp64_peak(gfb_ctx *c, double *tflops, float *milliseconds) {
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    const int iters = 4096;
+    double *scratch = reinterpret_cast<double *> (c->scratch);
+    gfb_k_fp64_peak(scratch, 64, c->sms, c->stream);      // warm up
+    float best = 1.0e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(c->ev_start, c->stream);
+        if (gfb_k_fp64_peak(scratch, iters, c->sms, c->stream)) return fail("peak kernel launch failed");
+        cudaEventRecord(c->ev_stop, c->stream);
+        if (check(cudaEventSynchronize(c->ev_stop), "peak sync")) return 1;
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop);
+        if (ms < best) best = ms;
+    }
+    const double flops = 2.0*8.0*16.0*static_cast<double> (iters)*256.0*8.0*c->sms;
+    *tflops = flops/(best*1.0e-3)/1.0e12;
+    if (milliseconds) *milliseconds = best;
+    return 0;
+}
+
+int gfb_flush_l2(gfb_ctx *c) {
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    if (!c->flush_buffer) {
+        c->flush_count = (256ull << 20)/sizeof(double);    // 256 MiB > 126 MB L2
+        if (check(cudaMalloc(&c->flush_buffer, c->flush_count*sizeof(double)), "cudaMalloc")) return 1;
+    }
+    if (gfb_k_fill(c->flush_buffer, c->flush_count, 0.0, c->sms, c->stream)) return fail("fill launch failed");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+"""Python view of the ray tracing hot path (include/gfb_rays.h).
+
+Mirrors the call sequence of the reference benchmark
+(/root/reference/graph_benchmark/xrays_bench.cpp:53-101):
+variables -> equilibrium -> solver::rk4 -> init(kx) -> compile -> step()* -> sync_host.
+All computation happens in libgfb200.so on the GPU; this module only moves
+numpy arrays across the C ABI.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from ._lib import lib, check, c_double_p, GfbError
+
+STATE = ("t", "w", "x", "y", "z", "kx", "ky", "kz")
+_DEFAULT_EFIT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                             "tests", "golden", "efit.gfbt")
+
+
+def _ptr_array(arrays, n):
+    arr_t = c_double_p * n
+    return arr_t(*[a.ctypes.data_as(c_double_p) if a is not None else None for a in arrays])
+
+
+class RayTracer:
+    """solver::rk4<dispersion::X> on one GPU (solver.hpp:677-870)."""
+
+    def __init__(self, dispersion, equilibrium, num_rays, dt, solver="rk4", table_file=None,
+                 device=0, options=None):
+        if equilibrium == "efit" and table_file is None:
+            table_file = _DEFAULT_EFIT
+        self.n = int(num_rays)
+        self.h = lib.gfb_rays_create(dispersion.encode(), equilibrium.encode(),
+                                     (table_file or "").encode(), solver.encode(), self.n,
+                                     float(dt), int(device), options.encode() if options else None)
+        if not self.h:
+            raise GfbError("gfb_rays_create failed: %s" % lib.gfb_last_error().decode())
+        self.ctx = lib.gfb_rays_ctx(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.gfb_rays_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    # -- state ---------------------------------------------------------------
+    def _as_arrays(self, state):
+        out = []
+        for name in STATE:
+            v = state.get(name) if isinstance(state, dict) else state[STATE.index(name)]
+            if v is None:
+                out.append(None)
+                continue
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (self.n,)))
+            out.append(a)
+        return out
+
+    def set_state(self, state):
+        """variable->set(...) (xrays_bench.cpp:62-71); dict of name->array/scalar or list in STATE order."""
+        arrs = self._as_arrays(state)
+        check(lib.gfb_rays_set_state(self.h, _ptr_array(arrs, 8)), "set_state")
+
+    def put_state(self, state):
+        """Host->device copy of state arrays (solver_interface::sync_device)."""
+        arrs = self._as_arrays(state)
+        check(lib.gfb_rays_put_state(self.h, _ptr_array(arrs, 8)), "put_state")
+
+    def init(self, var="kx", tolerance=1.0e-30, max_iterations=1000, mode="per_ray"):
+        """solver_interface::init (solver.hpp:254-274): Newton solve of D = 0 for `var`."""
+        check(lib.gfb_rays_init(self.h, (var or "").encode(), tolerance, max_iterations,
+                                0 if mode == "per_ray" else 1), "init")
+
+    def compile(self):
+        check(lib.gfb_rays_compile(self.h), "compile")
+
+    def step(self, num_steps=1):
+        check(lib.gfb_rays_step(self.h, int(num_steps)), "step")
+
+    def wait(self):
+        check(lib.gfb_rays_wait(self.h), "wait")
+
+    def get_state(self, residual=True, out=None):
+        """sync_host (solver.hpp:368-377): returns dict of arrays (+ 'residual').
+        `out` may hold preallocated (e.g. pinned) arrays keyed like the result."""
+        arrs = [out[k] if out is not None and k in out else np.empty(self.n, dtype=np.float64) for k in STATE]
+        res = None
+        if residual:
+            res = out["residual"] if out is not None and "residual" in out else np.empty(self.n, dtype=np.float64)
+        check(lib.gfb_rays_get_state(self.h, _ptr_array(arrs, 8),
+                                     res.ctypes.data_as(c_double_p) if residual else None), "get_state")
+        out = dict(zip(STATE, arrs))
+        if residual:
+            out["residual"] = res
+        return out
+
+    def rhs(self):
+        """dx/dt, dy/dt, dz/dt, dkx/dt, dky/dt, dkz/dt, D at the current host state."""
+        arrs = [np.empty(self.n, dtype=np.float64) for _ in range(7)]
+        check(lib.gfb_rays_rhs(self.h, _ptr_array(arrs, 7)), "rhs")
+        return dict(zip(("dxdt", "dydt", "dzdt", "dkxdt", "dkydt", "dkzdt", "D"), arrs))
+
+    def device_ptr(self, name):
+        which = 8 if name == "residual" else STATE.index(name)
+        p = ctypes.c_void_p()
+        check(lib.gfb_rays_device_ptr(self.h, which, ctypes.byref(p)), "device_ptr")
+        return p.value
+
+    def source(self):
+        return lib.gfb_rays_source(self.h).decode()
+
+    def kernel_stats(self):
+        v = [ctypes.c_int(0) for _ in range(6)]
+        check(lib.gfb_rays_kernel_stats(self.h, *[ctypes.byref(x) for x in v]), "kernel_stats")
+        keys = ("statements", "divides", "reciprocals", "registers", "local_bytes", "smem_bytes")
+        return dict(zip(keys, [x.value for x in v]))
+
+    # -- device helpers --------------------------------------------------------
+    def timer_start(self):
+        check(lib.gfb_timer_start(self.ctx), "timer_start")
+
+    def timer_stop(self):
+        ms = ctypes.c_float(0)
+        check(lib.gfb_timer_stop(self.ctx, ctypes.byref(ms)), "timer_stop")
+        return ms.value
+
+    def launch_count(self):
+        return int(lib.gfb_launch_count(self.ctx))
+
+    def flush_l2(self):
+        check(lib.gfb_flush_l2(self.ctx), "flush_l2")
+
+    def fp64_peak(self):
+        t = ctypes.c_double(0)
+        ms = ctypes.c_float(0)
+        check(lib.gfb_measure_fp64_peak(self.ctx, ctypes.byref(t), ctypes.byref(ms)), "fp64_peak")
+        return t.value
+
+
+class BorisPusher:
+    """The xkorc step graph (graph_korc/xkorc.cpp:40-121) on one GPU."""
+
+    NAMES = ("x", "y", "z", "ux", "uy", "uz", "gamma")
+
+    def __init__(self, equilibrium, num_particles, dt=0.5, table_file=None, device=0, options=None):
+        if equilibrium == "efit" and table_file is None:
+            table_file = _DEFAULT_EFIT
+        self.n = int(num_particles)
+        self.h = lib.gfb_boris_create(equilibrium.encode(), (table_file or "").encode(), self.n, float(dt),
+                                      int(device), options.encode() if options else None)
+        if not self.h:
+            raise GfbError("gfb_boris_create failed: %s" % lib.gfb_last_error().decode())
+        self.ctx = lib.gfb_boris_ctx(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.gfb_boris_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_state(self, x, y, z, ux, uy, uz):
+        arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (self.n,)))
+                for v in (x, y, z, ux, uy, uz)]
+        check(lib.gfb_boris_set_state(self.h, _ptr_array(arrs, 6)), "boris set_state")
+
+    def compile(self):
+        check(lib.gfb_boris_compile(self.h), "boris compile")
+
+    def step(self, n=1):
+        check(lib.gfb_boris_step(self.h, int(n)), "boris step")
+
+    def get_state(self):
+        arrs = [np.empty(self.n, dtype=np.float64) for _ in range(7)]
+        check(lib.gfb_boris_get_state(self.h, _ptr_array(arrs, 7)), "boris get_state")
+        return dict(zip(self.NAMES, arrs))
+
+    def info(self):
+        b0 = ctypes.c_double(0)
+        rl = ctypes.c_double(0)
+        check(lib.gfb_boris_info(self.h, ctypes.byref(b0), ctypes.byref(rl)), "boris info")
+        return {"b0": b0.value, "larmor_radius": rl.value}
+
+    def timer_start(self):
+        check(lib.gfb_timer_start(self.ctx), "timer_start")
+
+    def timer_stop(self):
+        ms = ctypes.c_float(0)
+        check(lib.gfb_timer_stop(self.ctx, ctypes.byref(ms)), "timer_stop")
+        return ms.value
+
+    def launch_count(self):
+        return int(lib.gfb_launch_count(self.ctx))
+
+
+def shard_sizes(total, shards):
+    """The reference's split: batch = N/G, first N%G shards get one more (xrays.cpp:423-432)."""
+    batch, extra = divmod(int(total), int(shards))
+    return [batch + (1 if g < extra else 0) for g in range(shards)]
+
+
+def shard_offsets(total, shards):
+    sizes = shard_sizes(total, shards)
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    return offs

@@ -1,4 +1,4 @@
-"""Minimal read-only HDF5 (netCDF-4) reader -- TEST INFRASTRUCTURE, not product code.
+"""Minimal read-only HDF5 (netCDF-4) reader used by the netCDF -> GFBT table converter.
 
 The reference's fixtures (`graph_tests/efit.nc`, `efit_gold.nc`, `vmec.nc`) are
 netCDF-4 = HDF5 files and this image has neither libnetcdf, h5py nor netCDF4.
@@ -7,8 +7,8 @@ object headers ("OHDR"/"OCHK"), link messages (compact or inside fractal-heap
 direct blocks), little-endian IEEE f8/f4/i4/i8 datasets with compact,
 contiguous or chunked (v1 B-tree, unfiltered) layout.
 
-It is used once, in this container, by `oracle/make_fixtures.py` to turn the
-fixtures into flat arrays; nothing on the GPU box reads HDF5.
+It is a data-format utility: `gfbt.nc_to_gfbt` uses it to turn an equilibrium file into the flat
+container the back end reads.  The compute path never touches HDF5.
 """
 import struct
 import numpy as np

@@ -1,0 +1,124 @@
+/*------------------------------------------------------------------------------
+ *  gfb200.h -- C ABI of the B200 device layer (libgfb200.so).
+ *
+ *  This is the drop-in boundary: every entry point replaces one member of the
+ *  reference's device context, `gpu::cuda_context<T, SAFE_MATH>`
+ *  (/root/reference/graph_framework/cuda_context.hpp), which is the only class
+ *  of the reference that touches a device API.  `jit::context` (jit.hpp:80-338)
+ *  is its only caller.  Signatures use plain pointers and sizes only.
+ *
+ *  Error behaviour: the reference asserts in debug builds and ignores CUresults
+ *  in release builds (cuda_context.hpp:30-53).  Here every call returns 0 on
+ *  success, non-zero on failure, and gfb_last_error() returns the text; the C++
+ *  adapters print it and abort, so a failure is never silent.  There is no CPU
+ *  fallback: without a CUDA device gfb_ctx_create fails.
+ *----------------------------------------------------------------------------*/
+#ifndef GFB200_H
+#define GFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gfb_ctx gfb_ctx;          /* one device context (cuda_context object) */
+typedef struct gfb_kernel gfb_kernel;    /* one launchable (the lambda of create_kernel_call) */
+
+/* cuda_context::max_concurrency  (cuda_context.hpp:121-126): number of CUDA devices. */
+int gfb_device_count(void);
+/* Text of the last failure on this thread ("" if none). */
+const char *gfb_last_error(void);
+/* Used by the host-side bindings of this library to report their own failures. */
+void gfb_set_last_error(const char *text);
+/* Library version string. */
+const char *gfb_version(void);
+
+/* cuda_context::cuda_context(index)  (cuda_context.hpp:139-148). */
+gfb_ctx *gfb_ctx_create(int device);
+/* cuda_context::~cuda_context  (cuda_context.hpp:153-185): frees module, buffers, stream. */
+void gfb_ctx_destroy(gfb_ctx *ctx);
+/* Device name / SM count / clock of the context's device. */
+int gfb_ctx_device_info(gfb_ctx *ctx, char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor);
+
+/* cuda_context::compile  (cuda_context.hpp:194-302): NVRTC for sm_100a -> cubin -> module.
+ * `source` is the emitted bodies; the hand-written skeleton text is prepended by
+ * the library.  `options` may be NULL or a space separated list of extra NVRTC flags. */
+int gfb_compile(gfb_ctx *ctx, const char *source, const char *const *names, int num_names, const char *options);
+/* NVRTC only, no device needed: used by the CPU test-suite and by tools.  On success
+ * *cubin (malloc'ed, caller frees with gfb_free) holds the sm_100a cubin. */
+int gfb_compile_to_cubin(const char *source, const char *options, void **cubin, size_t *cubin_size, char **log);
+void gfb_free(void *p);
+/* Full text (skeleton + bodies) of the last gfb_compile on this context; jit::context::print_source. */
+const char *gfb_source(gfb_ctx *ctx);
+const char *gfb_compile_log(gfb_ctx *ctx);
+
+/* Buffers are keyed by a 64-bit key (the host node address, as the reference keys its
+ * std::map<leaf_node *, CUdeviceptr>, cuda_context.hpp:82).  First call allocates `bytes`
+ * and uploads `init` (may be NULL = zero fill); later calls return the same buffer.
+ * (create_kernel_call's allocation loop, cuda_context.hpp:330-364.) */
+int gfb_buffer(gfb_ctx *ctx, uint64_t key, size_t bytes, const void *init, void **device_ptr);
+/* Adopt externally owned device memory (e.g. a torch tensor) under a key. */
+int gfb_buffer_import(gfb_ctx *ctx, uint64_t key, void *device_ptr, size_t bytes);
+/* Device pointer and size of a buffer, 0 size if unknown. */
+int gfb_buffer_lookup(gfb_ctx *ctx, uint64_t key, void **device_ptr, size_t *bytes);
+
+/* cuda_context::create_kernel_call  (cuda_context.hpp:316-531).
+ * ptr_keys: buffer keys in kernel pointer order (inputs, outputs, table groups).
+ * kind: 0 generic item, 1 runge-kutta item, 2 device-resident Newton item.
+ * can_repeat: non-zero when repeated runs may be fused into one multi-step launch
+ * (the item has setters); zero makes repeated runs collapse to a single step. */
+int gfb_kernel_create(gfb_ctx *ctx, const char *name, const uint64_t *ptr_keys, int num_ptrs,
+                      size_t num_rays, unsigned block_size, size_t dynamic_smem, int kind, int can_repeat,
+                      gfb_kernel **kernel);
+/* The launch lambda.  Launches are DEFERRED: consecutive runs of the same kernel are
+ * counted and issued as one launch whose step loop stays in registers; any
+ * observation (wait, copies, max, host pointer, a different kernel) flushes. */
+int gfb_kernel_run(gfb_kernel *kernel);
+/* Immediate launch of `steps` fused steps (flushes anything pending first). */
+int gfb_kernel_launch(gfb_kernel *kernel, unsigned steps);
+/* Set scalar[index] passed to the kernel (Newton tolerance, ...). */
+int gfb_kernel_set_scalar(gfb_kernel *kernel, int index, double value);
+/* registers/thread, static smem, local (spill) bytes/thread, max threads/block. */
+int gfb_kernel_attributes(gfb_kernel *kernel, int *regs, int *static_smem, int *local_bytes, int *max_threads);
+/* Number of device launches issued so far by this context (bench.py's gpu_launches). */
+uint64_t gfb_launch_count(gfb_ctx *ctx);
+/* Upper bound of fused steps per launch (default 1024). */
+int gfb_set_max_fused_steps(gfb_ctx *ctx, unsigned steps);
+int gfb_flush(gfb_ctx *ctx);
+
+/* cuda_context::create_max_call  (cuda_context.hpp:540-576) + create_reduction (:954-995):
+ * maximum of n doubles of a buffer, returned to the host. */
+int gfb_max(gfb_ctx *ctx, uint64_t key, size_t n, double *result);
+/* cuda_context::wait  (cuda_context.hpp:581-584). */
+int gfb_wait(gfb_ctx *ctx);
+/* cuda_context::copy_to_device / copy_to_host  (cuda_context.hpp:625-643). bytes == 0 copies the whole buffer. */
+int gfb_copy_h2d(gfb_ctx *ctx, uint64_t key, const void *source, size_t bytes);
+int gfb_copy_d2h(gfb_ctx *ctx, uint64_t key, void *destination, size_t bytes);
+/* cuda_context::get_buffer  (cuda_context.hpp:1002-1004): host-dereferenceable view, a
+ * pinned mirror refreshed by gfb_wait (the reference returns managed memory). */
+int gfb_host_ptr(gfb_ctx *ctx, uint64_t key, void **host_ptr);
+/* cuda_context::check_value  (cuda_context.hpp:613-617). */
+int gfb_check_value(gfb_ctx *ctx, uint64_t key, size_t index, double *value);
+
+/* Device timing on the context's stream (CUDA events). */
+int gfb_timer_start(gfb_ctx *ctx);
+int gfb_timer_stop(gfb_ctx *ctx, float *milliseconds);
+/* The context's cudaStream_t, for callers that share it with torch. */
+void *gfb_stream(gfb_ctx *ctx);
+
+/* Power-deposition profile (north-star config 3; algorithm of utilities/bin.py:53-106):
+ * hist[ix, iy, iz] += weight[i] for rays inside the half-open box. All device pointers. */
+int gfb_deposit(gfb_ctx *ctx, const double *x, const double *y, const double *z, const double *weight,
+                size_t n, double *hist, const double *lo, const double *hi, const int *bins);
+
+/* Measured FP64 FMA peak of the device in TFLOP/s (roofline denominator). */
+int gfb_measure_fp64_peak(gfb_ctx *ctx, double *tflops, float *milliseconds);
+/* L2 flush helper for benchmarks: writes a buffer larger than L2. */
+int gfb_flush_l2(gfb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFB200_H */

@@ -1,0 +1,87 @@
+/*------------------------------------------------------------------------------
+ *  gfb_rays.h -- C ABI of the ray tracing hot path.
+ *
+ *  The reference exposes this path only as C++ templates
+ *  (solver::rk4<dispersion::cold_plasma<T>> etc.) driven by
+ *  /root/reference/graph_benchmark/xrays_bench.cpp:34-104 and
+ *  /root/reference/graph_driver/xrays.cpp:413-529.  This header is the flat C
+ *  view of exactly that call sequence so that Python (ctypes), C or Fortran can
+ *  drive it:   create -> set_state -> init (Newton) -> compile -> step ... -> get_state.
+ *  Every function returns 0 on success; gfb_last_error() (gfb200.h) has the text.
+ *----------------------------------------------------------------------------*/
+#ifndef GFB_RAYS_H
+#define GFB_RAYS_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "gfb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gfb_rays gfb_rays;
+
+/* State array order everywhere: t, w, x, y, z, kx, ky, kz  (solver.hpp:304-314). */
+enum { GFB_T = 0, GFB_W, GFB_X, GFB_Y, GFB_Z, GFB_KX, GFB_KY, GFB_KZ, GFB_NUM_STATE };
+
+/* dispersion : "cold_plasma" | "ordinary_wave" | "extra_ordinary_wave" | "bohm_gross" | "simple" |
+ *              "light_wave" | "acoustic_wave" | "gaussian_well" | "ion_cyclotron" | "stiff"
+ * equilibrium: "efit" (table_file = GFBT path) | "slab" | "slab_density" | "slab_field" |
+ *              "no_magnetic_field" | "gaussian_density"
+ * solver     : "rk4" | "rk2" (staged skeleton) | "rk4_graph" | "rk2_graph" (stages unrolled in the
+ *              graph, the reference's construction)
+ * options    : NULL or space separated key=value list:
+ *              block=<threads> minblocks=<n> stage_tables=<0|1> share_rcp=<0|1> unroll_stages=<0|1>
+ *              fused_steps=<max steps per launch>
+ * Mirrors the constructor sequence of xrays_bench.cpp:53-85. */
+gfb_rays *gfb_rays_create(const char *dispersion, const char *equilibrium, const char *table_file,
+                          const char *solver, size_t num_rays, double dt, int device, const char *options);
+void gfb_rays_destroy(gfb_rays *r);
+
+/* variable->set(...) for the eight state arrays (host pointers, num_rays doubles each). */
+int gfb_rays_set_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]);
+/* solver_interface::init(var, tol, max_iter)  (solver.hpp:254-274).  var = "kx"|"ky"|"kz"|"w"|"x"|"y"|"z"
+ * or "" for init() without a solve.  mode 0 = device-resident per-ray Newton, 1 = the reference's
+ * host-driven ensemble-maximum loop (workflow.hpp:179-205). */
+int gfb_rays_init(gfb_rays *r, const char *var, double tolerance, size_t max_iterations, int mode);
+/* solver_interface::compile  (solver.hpp:303-349). */
+int gfb_rays_compile(gfb_rays *r);
+/* num_steps calls of solver_interface::step  (solver.hpp:382-384). */
+int gfb_rays_step(gfb_rays *r, size_t num_steps);
+/* work.wait(). */
+int gfb_rays_wait(gfb_rays *r);
+/* solver_interface::sync_host + read back  (solver.hpp:368-377). Any pointer may be NULL. */
+int gfb_rays_get_state(gfb_rays *r, double *const state[GFB_NUM_STATE], double *residual);
+/* solver_interface::sync_device from caller memory  (solver.hpp:354-363). */
+int gfb_rays_put_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]);
+/* Device pointer of state array `which` (GFB_T..GFB_KZ) or of the residual (which = GFB_NUM_STATE). */
+int gfb_rays_device_ptr(gfb_rays *r, int which, void **device_ptr);
+/* The underlying device context (timers, launch counters, deposit, ...). */
+gfb_ctx *gfb_rays_ctx(gfb_rays *r);
+/* Emitted CUDA text of the step kernel; statements / remaining divides / shared reciprocals in it. */
+const char *gfb_rays_source(gfb_rays *r);
+int gfb_rays_kernel_stats(gfb_rays *r, int *statements, int *divides, int *reciprocals,
+                          int *registers, int *local_bytes, int *smem_bytes);
+
+/* Right-hand side only: evaluates dx/dt,dy/dt,dz/dt,dkx/dt,dky/dt,dkz/dt,D (dispersion.hpp:1387-1433)
+ * for host states; out = 7 arrays of num_rays doubles.  Used by parity tests. */
+int gfb_rays_rhs(gfb_rays *r, double *const out[7]);
+
+/* Boris push in an equilibrium field exactly as graph_korc/xkorc.cpp:40-121 builds it.
+ * state order: x, y, z, ux, uy, uz (u in units of c), then gamma is produced by the pre-item. */
+typedef struct gfb_boris gfb_boris;
+gfb_boris *gfb_boris_create(const char *equilibrium, const char *table_file, size_t num_particles,
+                            double dt, int device, const char *options);
+void gfb_boris_destroy(gfb_boris *b);
+int gfb_boris_set_state(gfb_boris *b, const double *const state[6]);
+int gfb_boris_compile(gfb_boris *b);          /* also runs the initialize_gamma pre-item */
+int gfb_boris_step(gfb_boris *b, size_t num_steps);
+int gfb_boris_get_state(gfb_boris *b, double *const state[7]);
+int gfb_boris_info(gfb_boris *b, double *b0, double *larmor_radius);
+gfb_ctx *gfb_boris_ctx(gfb_boris *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFB_RAYS_H */

@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Generate golden input/output vectors from the reference itself (oracle/_ref/ref_driver).
+
+TEST INFRASTRUCTURE.  Run in the build container (needs /root/reference to have been compiled
+into oracle/_ref by `make -C oracle ref`).  The .npz files written to tests/golden/ are
+committed so the CPU and GPU test-suites never need /root/reference at run time.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import reference                    # noqa: E402
+from graph_framework_b200 import workloads      # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def rhs_cases():
+    n = 64
+    cases = [("ordinary_wave", "efit"), ("extra_ordinary_wave", "efit"), ("cold_plasma", "efit"),
+             ("cold_plasma", "slab"), ("cold_plasma", "slab_density"), ("ordinary_wave", "slab_density"),
+             ("bohm_gross", "no_magnetic_field"), ("simple", "slab"), ("cold_plasma", "gaussian_density")]
+    for disp, eq in cases:
+        if eq == "efit":
+            s = workloads.interior_states(n, seed=1)
+        else:
+            s = workloads.slab_ensemble(n, seed=2)
+            if eq == "gaussian_density":
+                s["x"] = s["x"]*0.5
+        out = reference.rhs(disp, eq, s)
+        save("ref_rhs_%s_%s" % (disp, eq), state=workloads.pack(s), rhs=out)
+
+
+def trace_cases():
+    n = 32
+    cases = [("extra_ordinary_wave", "efit", 2.0e-5, "kx", "rk4"),
+             ("ordinary_wave", "efit", 2.0e-5, "kx", "rk4"),
+             ("cold_plasma", "efit", 2.0e-5, "kx", "rk4"),
+             ("cold_plasma", "slab_density", 1.0e-3, "kx", "rk4"),
+             ("ordinary_wave", "slab_density", 1.0e-3, "kx", "rk4"),
+             ("cold_plasma", "slab", 1.0e-3, "kx", "rk2"),
+             ("simple", "slab", 1.0e-2, "kx", "rk4")]
+    for disp, eq, dt, init, solver in cases:
+        s = workloads.efit_ensemble(n, seed=5) if eq == "efit" else workloads.slab_ensemble(n, seed=6)
+        if disp == "simple":
+            s["w"][:] = 1.0
+            s["kx"][:] = 0.6
+            s["ky"] = np.abs(s["ky"])*0.01 + 0.2
+            s["kz"] = np.abs(s["kz"])*0.01 + 0.2
+        per_step = reference.trace(disp, eq, s, dt, 5, save_every=1, init=init, solver=solver)
+        long = reference.trace(disp, eq, s, dt, 200, save_every=100, init=init, solver=solver)
+        save("ref_trace_%s_%s_%s" % (disp, eq, solver), state=workloads.pack(s), dt=np.array(dt),
+             per_step=per_step, long=long)
+
+
+def bench_case():
+    # xrays_bench initial conditions (every ray identical), xrays_bench.cpp:62-79
+    s = workloads.bench_rays(8)
+    rec = reference.trace("cold_plasma", "efit", s, 1.0e-3, 10, save_every=5, init="kx")
+    save("ref_trace_xrays_bench", state=workloads.pack(s), dt=np.array(1.0e-3), records=rec)
+
+
+def korc_case():
+    n = 16
+    x, y, z, ux, uy, uz = workloads.boris_ensemble(n, seed=4)
+    out, info = reference.korc("efit", x, y, z, ux, uy, uz, 50)
+    save("ref_korc_efit", start=np.stack([x, y, z, ux, uy, uz]), end=out,
+         b0=np.array(info["b0"]), larmor_radius=np.array(info["larmor_radius"]))
+
+
+if __name__ == "__main__":
+    if not reference.available():
+        raise SystemExit("oracle/_ref/ref_driver missing: run `make -C oracle ref` first")
+    which = sys.argv[1:] or ["rhs", "trace", "bench", "korc"]
+    if "rhs" in which:
+        rhs_cases()
+    if "trace" in which:
+        trace_cases()
+    if "bench" in which:
+        bench_case()
+    if "korc" in which:
+        korc_case()

