@@ -1,11 +1,13 @@
 # Builds libgfb200.so (C-ABI device layer + host front end bindings) for sm_100a, in tree.
 CUDA ?= /usr/local/cuda
 NVCC := $(CUDA)/bin/nvcc
-CXX ?= g++
+# The system compiler: its libstdc++ is the shared one every other module of the process uses.
+# (An environment CXX pointing at a toolchain with a static libstdc++ breaks iostreams inside a dlopen'ed library.)
+CXX := /usr/bin/g++
 PKG := graph_framework_b200
 SRC := $(PKG)/csrc
 LIB := $(PKG)/libgfb200.so
-CXXFLAGS := -std=c++20 -O2 -fPIC -Wall -Wno-unused-function -I$(CUDA)/include -Iinclude
+CXXFLAGS := -std=c++20 -O2 -g -fPIC -Wall -Wno-unused-function -I$(CUDA)/include -Iinclude
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
 
 all: $(LIB)

@@ -66,7 +66,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -78,8 +81,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 7:
+        t0 = getattr(self, "t0", 0.0)
+        for stamp, r in self.rows:
+            if len(r) < 7 or stamp < t0:
                 continue
             try:
                 sm.append(float(r[0]))
@@ -134,8 +138,8 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="efit_xmode", choices=sorted(WORKLOADS))
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
@@ -182,14 +186,15 @@ def main():
     fp64_peak = tracer.fp64_peak()
 
     # ---- kernel-resident measurement -------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         tracer.step(SUB_STEPS)
     tracer.wait()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()                                         # clocks are kept from here to the end of the e2e region
     launches0 = tracer.launch_count()
     kernel_ms = 0.0
     for _ in range(args.steps):
@@ -198,7 +203,7 @@ def main():
         tracer.step(SUB_STEPS)
         kernel_ms += tracer.timer_stop()
     tracer.wait()
-    launches = tracer.launch_count() - launches0 - args.steps      # minus the L2 flush fills
+    launches = tracer.launch_count() - launches0                    # solver_kernel launches (L2 fills not counted)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -207,7 +212,6 @@ def main():
         kernel_ms_max = float(t.item())
     else:
         kernel_ms_max = kernel_ms
-    clocks = sampler.stop()
 
     # ---- end to end through the public API with host buffers -------------------------
     host = {k: torch.empty(rays, dtype=torch.float64).pin_memory() for k in STATE + ("residual",)}
@@ -217,7 +221,7 @@ def main():
     for k in STATE:
         host_in[k].copy_(host[k])
     host_np = {k: host_in[k].numpy() for k in STATE}
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 10))
     for _ in range(2):
         tracer.put_state(host_np)
         tracer.step(SUB_STEPS)
@@ -237,6 +241,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     finite = bool(np.isfinite(out["x"]).all())
+    clocks = sampler.stop()
 
     total_rays = rays*world
     value = total_rays*SUB_STEPS*args.steps/(kernel_ms_max*1.0e-3)

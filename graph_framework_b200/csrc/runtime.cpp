@@ -19,8 +19,11 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 
+#include <csignal>
 #include <cstdio>
 #include <cstdlib>
+#include <execinfo.h>
+#include <unistd.h>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -43,6 +46,31 @@ const char *skeleton_text =
 ;
 
 thread_local std::string last_error;
+
+//  GFB_DEBUG=1: trace every device-layer call and print a raw backtrace on SIGSEGV
+//  (resolve the offsets with addr2line on libgfb200.so).
+bool debug_enabled() {
+    static const bool on = std::getenv("GFB_DEBUG") != nullptr;
+    return on;
+}
+void segv_handler(int sig) {
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "gfb200: fatal signal, backtrace:\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+struct debug_init {
+    debug_init() {
+        if (debug_enabled()) {
+            signal(SIGSEGV, segv_handler);
+            signal(SIGBUS, segv_handler);
+        }
+    }
+} debug_init_instance;
+#define GFB_TRACE(...) do { if (debug_enabled()) { std::fprintf(stderr, "[gfb] " __VA_ARGS__); std::fprintf(stderr, "\n"); std::fflush(stderr); } } while (0)
 
 int fail(const std::string &what) {
     last_error = what;
@@ -181,6 +209,7 @@ struct gfb_ctx {
 
 namespace {
 int launch_now(gfb_kernel *k, const unsigned steps) {
+    GFB_TRACE("launch %s steps=%u grid=%u block=%u smem=%zu", k->name.c_str(), steps, k->grid, k->block, k->smem);
     gfb_ctx *c = k->ctx;
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
     k->args.steps = k->can_repeat || k->kind == 2 ? steps : (steps ? 1u : 0u);
@@ -216,6 +245,7 @@ int gfb_device_count(void) {
 }
 
 gfb_ctx *gfb_ctx_create(int device) {
+    GFB_TRACE("ctx_create %d", device);
     int n = gfb_device_count();
     if (n <= 0) {
         fail("no CUDA device: the B200 back end has no CPU fallback");
@@ -243,6 +273,7 @@ gfb_ctx *gfb_ctx_create(int device) {
 }
 
 void gfb_ctx_destroy(gfb_ctx *c) {
+    GFB_TRACE("ctx_destroy %p", (void *)c);
     if (!c) return;
     cudaSetDevice(c->device);
     flush(c);
@@ -292,6 +323,7 @@ int gfb_compile_to_cubin(const char *source, const char *options, void **cubin, 
 void gfb_free(void *p) { std::free(p); }
 
 int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int num_names, const char *options) {
+    GFB_TRACE("compile %zu bytes", std::strlen(source));
     (void)names; (void)num_names;
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
     if (flush(c)) return 1;
@@ -313,6 +345,7 @@ const char *gfb_source(gfb_ctx *c) { return c->source.c_str(); }
 const char *gfb_compile_log(gfb_ctx *c) { return c->log.c_str(); }
 
 int gfb_buffer(gfb_ctx *c, uint64_t key, size_t bytes, const void *init, void **device_ptr) {
+    GFB_TRACE("buffer key=%llx bytes=%zu init=%p", (unsigned long long)key, bytes, init);
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
     auto it = c->buffers.find(key);
     if (it == c->buffers.end()) {
@@ -370,6 +403,7 @@ int gfb_buffer_lookup(gfb_ctx *c, uint64_t key, void **device_ptr, size_t *bytes
 int gfb_kernel_create(gfb_ctx *c, const char *name, const uint64_t *ptr_keys, int num_ptrs,
                       size_t num_rays, unsigned block_size, size_t dynamic_smem, int kind, int can_repeat,
                       gfb_kernel **kernel) {
+    GFB_TRACE("kernel_create %s ptrs=%d n=%zu block=%u smem=%zu kind=%d", name, num_ptrs, num_rays, block_size, dynamic_smem, kind);
     if (!c->module) return fail("gfb_kernel_create: nothing compiled");
     if (num_ptrs > max_ptrs) return fail("gfb_kernel_create: too many pointer arguments");
     auto k = std::make_unique<gfb_kernel> ();
@@ -399,6 +433,7 @@ int gfb_kernel_create(gfb_ctx *c, const char *name, const uint64_t *ptr_keys, in
 }
 
 int gfb_kernel_run(gfb_kernel *k) {
+    GFB_TRACE("kernel_run %s", k->name.c_str());
     gfb_ctx *c = k->ctx;
     if (c->pending == k && c->pending_steps < c->max_fused && (k->kind != 2)) {
         c->pending_steps++;
@@ -467,6 +502,7 @@ int gfb_wait(gfb_ctx *c) {
 }
 
 int gfb_copy_h2d(gfb_ctx *c, uint64_t key, const void *source, size_t bytes) {
+    GFB_TRACE("copy_h2d key=%llx", (unsigned long long)key);
     if (flush(c)) return 1;
     auto it = c->buffers.find(key);
     if (it == c->buffers.end()) return fail("gfb_copy_h2d: unknown key");
@@ -477,6 +513,7 @@ int gfb_copy_h2d(gfb_ctx *c, uint64_t key, const void *source, size_t bytes) {
 }
 
 int gfb_copy_d2h(gfb_ctx *c, uint64_t key, void *destination, size_t bytes) {
+    GFB_TRACE("copy_d2h key=%llx dst=%p bytes=%zu", (unsigned long long)key, destination, bytes);
     if (flush(c)) return 1;
     auto it = c->buffers.find(key);
     if (it == c->buffers.end()) return fail("gfb_copy_d2h: unknown key");

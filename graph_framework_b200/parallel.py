@@ -1,0 +1,60 @@
+"""Multi-GPU plumbing: one process per GPU, rays sharded with no data-path collective.
+
+The reference runs one std::thread per device, each with its own rays, and never exchanges
+data (graph_driver/xrays.cpp:419-527).  Here the unit is one process per GPU launched by
+torchrun; torch.distributed (NCCL over NVLink on the GPU box, gloo in CPU tests) is used for
+exactly one thing: summing the binned power-deposition profile across ranks.
+"""
+import os
+
+import numpy as np
+
+from .rays import shard_offsets, shard_sizes     # noqa: F401  (re-exported)
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def my_shard(total, rank=None, world=None):
+    """(offset, size) of this rank's contiguous slice, the reference's batch/extra split
+    (xrays.cpp:423-432, xrays_bench.cpp:38-51)."""
+    r, w = rank_world()
+    rank = r if rank is None else rank
+    world = w if world is None else world
+    offs = shard_offsets(total, world)
+    return offs[rank], offs[rank + 1] - offs[rank]
+
+
+def shard_state(state, rank=None, world=None):
+    n = len(next(iter(state.values())))
+    off, size = my_shard(n, rank, world)
+    return {k: np.ascontiguousarray(v[off:off + size]) for k, v in state.items()}
+
+
+def allreduce_profile(hist, total_rays=None):
+    """Sum a deposition histogram (torch tensor, FP64) over all ranks in place and, like
+    utilities/bin.py:96-106, normalise by the total number of rays when given.
+    One collective per output block; nothing else in the path communicates."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    if total_rays:
+        hist /= float(total_rays)
+    return hist
+
+
+def deposit(tracer, weight, hist, lo, hi):
+    """Bin per-ray weights at the rays' current positions into `hist` (a contiguous FP64 CUDA
+    tensor of shape bins) on the tracer's stream (kernels.cu deposit_kernel).
+    `weight` is a CUDA tensor or device pointer of num_rays doubles."""
+    import ctypes
+    from ._lib import lib, check
+    bins = (ctypes.c_int*3)(*hist.shape)
+    lo_a = (ctypes.c_double*3)(*lo)
+    hi_a = (ctypes.c_double*3)(*hi)
+    wptr = weight if isinstance(weight, int) else weight.data_ptr()
+    check(lib.gfb_deposit(tracer.ctx, tracer.device_ptr("x"), tracer.device_ptr("y"), tracer.device_ptr("z"),
+                          wptr, tracer.n, hist.data_ptr(), lo_a, hi_a, bins), "deposit")
+    check(lib.gfb_wait(tracer.ctx), "deposit wait")
+    return hist

@@ -78,10 +78,26 @@ def korc_case():
          b0=np.array(info["b0"]), larmor_radius=np.array(info["larmor_radius"]))
 
 
+def defect_case():
+    """Evidence for the reference's symbolic dD/dz defect (cold_plasma in a z-dependent field):
+    its own D at z +- h and w +- h next to its own symbolic dkz/dt."""
+    n = 16
+    s = workloads.interior_states(n, seed=7)
+    h = 1.0e-6
+    base = reference.rhs("cold_plasma", "efit", s)
+    out = {"state": workloads.pack(s), "rhs": base, "h": np.array(h)}
+    for var in ("z", "w", "x"):
+        for sign, tag in ((1.0, "p"), (-1.0, "m")):
+            p = dict(s)
+            p[var] = s[var] + sign*h
+            out["D_%s_%s" % (var, tag)] = reference.rhs("cold_plasma", "efit", p)[6]
+    save("ref_defect_cold_plasma_efit", **out)
+
+
 if __name__ == "__main__":
     if not reference.available():
         raise SystemExit("oracle/_ref/ref_driver missing: run `make -C oracle ref` first")
-    which = sys.argv[1:] or ["rhs", "trace", "bench", "korc"]
+    which = sys.argv[1:] or ["rhs", "trace", "bench", "korc", "defect"]
     if "rhs" in which:
         rhs_cases()
     if "trace" in which:
@@ -90,3 +106,5 @@ if __name__ == "__main__":
         bench_case()
     if "korc" in which:
         korc_case()
+    if "defect" in which:
+        defect_case()

@@ -73,10 +73,10 @@ class Efit:
     def __init__(self, tables):
         """tables: dict as read from the GFBT file (graph_framework_b200.tools.gfbt.read_gfbt)."""
         t = tables
-        self.rmin, self.dr = float(t["rmin"]), float(t["dr"])
-        self.zmin, self.dz = float(t["zmin"]), float(t["dz"])
-        self.psimin, self.dpsi = float(t["psimin"]), float(t["dpsi"])
-        self.ne_scale, self.te_scale, self.pres_scale = float(t["ne_scale"]), float(t["te_scale"]), float(t["pres_scale"])
+        self.rmin, self.dr = float(np.ravel(t["rmin"])[0]), float(np.ravel(t["dr"])[0])
+        self.zmin, self.dz = float(np.ravel(t["zmin"])[0]), float(np.ravel(t["dz"])[0])
+        self.psimin, self.dpsi = float(np.ravel(t["psimin"])[0]), float(np.ravel(t["dpsi"])[0])
+        self.ne_scale, self.te_scale, self.pres_scale = float(np.ravel(t["ne_scale"])[0]), float(np.ravel(t["te_scale"])[0]), float(np.ravel(t["pres_scale"])[0])
         self.numr, self.numz = t["psi_c00"].shape
         self.psi = [fold_spline([t["psi_c%d%d" % (i, j)].ravel() for j in range(4)], self.dz, self.zmin)
                     for i in range(4)]
