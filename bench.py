@@ -159,6 +159,7 @@ def main():
     import torch
     from graph_framework_b200 import workloads
     from graph_framework_b200.rays import RayTracer, STATE
+    from graph_framework_b200 import _lib
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 back end has no CPU fallback")
@@ -278,7 +279,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "ray-steps/s", "h2d_bytes_per_step": 8*8*rays,
                     "d2h_bytes_per_step": 9*8*rays, "steps": e2e_steps, "finite": finite},
             "gpu_launches": launches,
-            "kernel": dict(stats, block=128),
+            "kernel": dict(stats, block=128, min_blocks_per_sm=int(_lib.lib.gfb_compiled_min_blocks(tracer.ctx))),
             "clocks": clocks,
             "phases_s": {"setup": t_init - t_setup, "newton_init": t_compile - t_init, "jit": t_ready - t_compile},
         }

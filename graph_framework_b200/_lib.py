@@ -32,6 +32,7 @@ def _load():
         "gfb_ctx_destroy": (None, [P]),
         "gfb_ctx_device_info": (I, [P, ctypes.c_char_p, SZ, ctypes.POINTER(I), ctypes.POINTER(I), ctypes.POINTER(I)]),
         "gfb_compile": (I, [P, S, ctypes.POINTER(S), I, S]),
+        "gfb_compiled_min_blocks": (I, [P]),
         "gfb_compile_to_cubin": (I, [S, S, c_void_pp, ctypes.POINTER(SZ), ctypes.POINTER(ctypes.c_void_p)]),
         "gfb_free": (None, [P]),
         "gfb_source": (S, [P]),

@@ -201,7 +201,7 @@ equilibrium::shared<> make_equilibrium(const std::string &name, const std::strin
 
 struct run_options {
     jit::emit_options emit;
-    bool unroll_stages = false;
+    int unroll_stages = -1;         // -1: decided by body size (jit::context::compile)
     unsigned fused_steps = 0;
 };
 run_options parse_options(const char *options) {
@@ -218,7 +218,8 @@ run_options parse_options(const char *options) {
         else if (k == "minblocks") o.emit.min_blocks = static_cast<unsigned> (v);
         else if (k == "stage_tables") o.emit.stage_tables = v != 0;
         else if (k == "share_rcp") o.emit.share_reciprocals = v != 0;
-        else if (k == "unroll_stages") o.unroll_stages = v != 0;
+        else if (k == "fast_div") o.emit.fast_division = v != 0;
+        else if (k == "unroll_stages") o.unroll_stages = v != 0 ? 1 : 0;
         else if (k == "fused_steps") o.fused_steps = static_cast<unsigned> (v);
     }
     return o;
@@ -245,7 +246,9 @@ struct tracer final : public tracer_base {
            const run_options &o) :
     solve(s[GFB_W], s[GFB_KX], s[GFB_KY], s[GFB_KZ], s[GFB_X], s[GFB_Y], s[GFB_Z], s[GFB_T], dt, eq, "", n, device) {
         solve.get_work().get_context().options = o.emit;
-        if (o.unroll_stages) solve.get_work().get_context().set_nvrtc_options("-DGFB_UNROLL_STAGES=1");
+        if (o.unroll_stages >= 0) {
+            solve.get_work().get_context().set_nvrtc_options(o.unroll_stages ? "-DGFB_UNROLL_STAGES=1" : "-DGFB_UNROLL_STAGES=0");
+        }
         if (o.fused_steps) gfb_set_max_fused_steps(solve.get_work().get_context().device(), o.fused_steps);
     }
     std::vector<leaf_ptr> state() override { return solve.state(); }

@@ -70,8 +70,14 @@ namespace jit {
         size_t stage_total_bytes = 96*1024;
         bool share_reciprocals = true;
         bool stage_tables = true;
+///  Refined hardware reciprocal / rsqrt seeds instead of IEEE division and sqrt, and a
+///  multiplication by 1/scale in table indices (what -ffast-math does to the reference's kernels).
+        bool fast_division = true;
+        size_t unroll_stages_below = 640;       ///< unroll the RK stage loop for bodies up to this many statements
         unsigned block_size = 128;
-        unsigned min_blocks = 1;
+///  Resident blocks per SM promised to ptxas; 0 = let the device layer pick the highest
+///  value (4, 3, 2, 1) that compiles without register spills (-DGFB_MIN_BLOCKS).
+        unsigned min_blocks = 0;
     };
 
     inline std::string literal(const double d) {
@@ -180,8 +186,9 @@ namespace jit {
 
         std::string index_expr(const std::string &x, const double scale, const double offset, const size_t n) {
 //  The reference's contract: (uint)min(max((x - offset)/scale, 0), n - 1)  (piecewise.hpp:26-65).
-            return "static_cast<unsigned> (fmin(fmax((" + x + " - " + literal(offset) + ")/" + literal(scale) +
-                   ", 0.0), " + literal(static_cast<double> (n - 1)) + "))";
+            const std::string u = opt.fast_division ? "(" + x + " - " + literal(offset) + ")*" + literal(1.0/scale)
+                                                    : "(" + x + " - " + literal(offset) + ")/" + literal(scale);
+            return "static_cast<unsigned> (fmin(fmax(" + u + ", 0.0), " + literal(static_cast<double> (n - 1)) + "))";
         }
 
         const std::string &emit(const graph::leaf_node *n) {
@@ -239,16 +246,31 @@ namespace jit {
                 return reg.emplace(n, name).first->second;
             }
 
+            if (n->op == op_t::sqrt && opt.fast_division) {
+                const std::string arg = emit(n->args[0].get());
+                const std::string qname = "q" + std::to_string(n->id);
+                const std::string name = "t" + std::to_string(n->id);
+                out << "        const double " << qname << " = gfb::rsqrt(" << arg << ");" << std::endl;
+                out << "        const double " << name << " = gfb::sqrt_from_rsqrt(" << arg << ", " << qname << ");" << std::endl;
+                info.num_statements += 2;
+                inv_reg.emplace(n, qname);      // 1/sqrt(x) is free: divisions by this node multiply by q
+                return reg.emplace(n, name).first->second;
+            }
             std::vector<std::string> a;
             for (size_t i = 0, ie = n->num_args(); i < ie; i++) {
                 if (n->op == op_t::div && i == 1) {
                     const graph::leaf_node *d = strip(n->args[1].get());
-                    if (opt.share_reciprocals && denominators[d] > 1) {
+                    if ((opt.share_reciprocals && denominators[d] > 1) || opt.fast_division) {
                         auto inv = inv_reg.find(d);
                         if (inv == inv_reg.end()) {
                             const std::string dreg = emit(d);
+                            inv = inv_reg.find(d);      // a sqrt denominator registers its rsqrt while being emitted
+                        }
+                        if (inv == inv_reg.end()) {
+                            const std::string dreg = emit(d);
                             const std::string iname = "i" + std::to_string(d->id);
-                            out << "        const double " << iname << " = 1.0/" << dreg << ";" << std::endl;
+                            out << "        const double " << iname << " = "
+                                << (opt.fast_division ? "gfb::rcp(" + dreg + ")" : "1.0/" + dreg) << ";" << std::endl;
                             info.num_statements++;
                             info.num_reciprocals++;
                             inv = inv_reg.emplace(d, iname).first;
@@ -354,7 +376,8 @@ namespace jit {
             for (size_t j = 0; j < nr; j++) out << "        r[" << j << "] = " << regs[j] << ";" << std::endl;
             out << "    }" << std::endl << "};" << std::endl;
 
-            out << "extern \"C\" __global__ void __launch_bounds__(" << opt.block_size << ", " << opt.min_blocks << ") "
+            out << "extern \"C\" __global__ void __launch_bounds__(" << opt.block_size << ", "
+                << (opt.min_blocks ? std::to_string(opt.min_blocks) : std::string("GFB_MIN_BLOCKS")) << ") "
                 << info.name << "(const __grid_constant__ gfb_args a) {" << std::endl;
             switch (info.kind) {
                 case kernel_kind::generic: out << "    gfb::generic_item<" << k << "> (a);"; break;

@@ -132,8 +132,20 @@ namespace jit {
             std::vector<const char *> names;
             for (auto &n : kernel_names) names.push_back(n.c_str());
             const std::string s = source_buffer.str();
-            check(gfb_compile(gpu, s.c_str(), names.data(), static_cast<int> (names.size()),
-                              nvrtc_options.empty() ? nullptr : nvrtc_options.c_str()), "compile");
+//  Runge-Kutta stage loop: unrolling the four stages lets ptxas drop the unused residual of
+//  stages 2-4 and schedule across stages, but quadruples the body.  Measured on B200 (profiles/):
+//  it wins for the ~570 statement X-mode body and loses for the ~900 statement cold-plasma body.
+            std::string opts = nvrtc_options;
+            if (opts.find("GFB_UNROLL_STAGES") == std::string::npos) {
+                bool unroll = false;
+                for (auto &k : kernels) {
+                    if (k.kind == kernel_kind::rk2 || k.kind == kernel_kind::rk4) {
+                        unroll = k.num_statements <= options.unroll_stages_below;
+                    }
+                }
+                opts += unroll ? " -DGFB_UNROLL_STAGES=1" : " -DGFB_UNROLL_STAGES=0";
+            }
+            check(gfb_compile(gpu, s.c_str(), names.data(), static_cast<int> (names.size()), opts.c_str()), "compile");
             handles.clear();
         }
 

@@ -200,6 +200,7 @@ struct gfb_ctx {
     gfb_kernel *pending = nullptr;
     unsigned pending_steps = 0;
     unsigned max_fused = 1024;
+    int min_blocks = 0;
     uint64_t launches = 0;
     unsigned long long *scratch = nullptr;      // device scalar for reductions
     unsigned long long *scratch_host = nullptr; // pinned
@@ -328,19 +329,48 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
     if (flush(c)) return 1;
     c->source = std::string(skeleton_text) + source;
-    std::vector<char> image;
-    if (nvrtc_compile(c->source, options, image, c->log)) {
-        std::fprintf(stderr, "%s\n", last_error.c_str());
-        return 1;
-    }
     if (c->module) {
         cudaStreamSynchronize(c->stream);
         driver.ModuleUnload(c->module);
         c->module = nullptr;
         c->kernels.clear();
     }
-    return check_cu(driver.ModuleLoadData(&c->module, image.data()), "cuModuleLoadData");
+//  Occupancy choice: the emitted kernels carry __launch_bounds__(block, GFB_MIN_BLOCKS).  Unless the
+//  caller pinned it, take the largest promise (4, 3, 2, 1 blocks per SM) for which no kernel
+//  spills registers to local memory: FP64-bound bodies want warps to hide DFMA latency, but a
+//  spilling body pays for them in L1 traffic.
+    const std::string user = options ? options : "";
+    const bool pinned = user.find("-DGFB_MIN_BLOCKS") != std::string::npos;
+    const int candidates[] = {4, 3, 2, 1};
+    for (const int mb : candidates) {
+        const std::string opts = pinned ? user : user + " -DGFB_MIN_BLOCKS=" + std::to_string(mb);
+        std::vector<char> image;
+        if (nvrtc_compile(c->source, opts.c_str(), image, c->log)) {
+            std::fprintf(stderr, "%s\n", last_error.c_str());
+            return 1;
+        }
+        CUmodule module = nullptr;
+        if (check_cu(driver.ModuleLoadData(&module, image.data()), "cuModuleLoadData")) return 1;
+        int worst_local = 0;
+        for (int i = 0; i < num_names; i++) {
+            CUfunction f;
+            int local = 0;
+            if (driver.ModuleGetFunction(&f, module, names[i]) == CUDA_SUCCESS &&
+                driver.FuncGetAttribute(&local, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f) == CUDA_SUCCESS) {
+                worst_local = local > worst_local ? local : worst_local;
+            }
+        }
+        GFB_TRACE("compile min_blocks=%d local=%d", mb, worst_local);
+        if (pinned || worst_local == 0 || mb == 1) {
+            c->module = module;
+            c->min_blocks = pinned ? 0 : mb;
+            return 0;
+        }
+        driver.ModuleUnload(module);
+    }
+    return fail("gfb_compile: no variant loaded");
 }
+int gfb_compiled_min_blocks(gfb_ctx *c) { return c->min_blocks; }
 const char *gfb_source(gfb_ctx *c) { return c->source.c_str(); }
 const char *gfb_compile_log(gfb_ctx *c) { return c->log.c_str(); }
 

@@ -46,6 +46,9 @@ int gfb_ctx_device_info(gfb_ctx *ctx, char *name, size_t name_len, int *sm_count
  * `source` is the emitted bodies; the hand-written skeleton text is prepended by
  * the library.  `options` may be NULL or a space separated list of extra NVRTC flags. */
 int gfb_compile(gfb_ctx *ctx, const char *source, const char *const *names, int num_names, const char *options);
+/* Blocks per SM the last gfb_compile settled on (4..1: the largest without register spills;
+ * 0 when the caller pinned -DGFB_MIN_BLOCKS itself). */
+int gfb_compiled_min_blocks(gfb_ctx *ctx);
 /* NVRTC only, no device needed: used by the CPU test-suite and by tools.  On success
  * *cubin (malloc'ed, caller frees with gfb_free) holds the sm_100a cubin. */
 int gfb_compile_to_cubin(const char *source, const char *options, void **cubin, size_t *cubin_size, char **log);

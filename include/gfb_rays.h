@@ -32,7 +32,7 @@ enum { GFB_T = 0, GFB_W, GFB_X, GFB_Y, GFB_Z, GFB_KX, GFB_KY, GFB_KZ, GFB_NUM_ST
  * solver     : "rk4" | "rk2" (staged skeleton) | "rk4_graph" | "rk2_graph" (stages unrolled in the
  *              graph, the reference's construction)
  * options    : NULL or space separated key=value list:
- *              block=<threads> minblocks=<n> stage_tables=<0|1> share_rcp=<0|1> unroll_stages=<0|1>
+ *              block=<threads> minblocks=<n> stage_tables=<0|1> share_rcp=<0|1> fast_div=<0|1> unroll_stages=<0|1>
  *              fused_steps=<max steps per launch>
  * Mirrors the constructor sequence of xrays_bench.cpp:53-85. */
 gfb_rays *gfb_rays_create(const char *dispersion, const char *equilibrium, const char *table_file,

@@ -54,6 +54,7 @@ int main(int argc, char **argv) {
     jit::emit_options opt;
     if (const char *s = std::getenv("GFB_NO_STAGE")) opt.stage_tables = false;
     if (const char *s = std::getenv("GFB_NO_RCP")) opt.share_reciprocals = false;
+    if (const char *s = std::getenv("GFB_NO_FASTDIV")) opt.fast_division = false;
     if (const char *s = std::getenv("GFB_BLOCK")) opt.block_size = std::atoi(s);
     if (const char *s = std::getenv("GFB_MINB")) opt.min_blocks = std::atoi(s);
     std::ostringstream src;
