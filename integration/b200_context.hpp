@@ -172,7 +172,12 @@ namespace gpu {
 ///  the device layer; nothing else is needed for real double.
         void create_header(std::ostringstream &source_buffer) {
             source_buffer << "typedef unsigned int uint32_t;" << std::endl
-                          << "typedef unsigned short uint16_t;" << std::endl;
+                          << "typedef unsigned short uint16_t;" << std::endl
+//  The reference's index expressions call min<double>(max<double>(x, 0), n) (piecewise.hpp:26-65).
+//  NVRTC 12.9 has no such templates (the reference's own cuda_context fails to compile its EFIT
+//  kernels on this toolchain for that reason), so they are supplied here.
+                          << "template<typename T> __device__ __forceinline__ T min(const T a, const T b) { return a < b ? a : b; }" << std::endl
+                          << "template<typename T> __device__ __forceinline__ T max(const T a, const T b) { return a > b ? a : b; }" << std::endl;
         }
 
 ///  cuda_context.hpp:713-849.  Opens the kernel, loads every argument into a register and

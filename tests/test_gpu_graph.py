@@ -1,0 +1,156 @@
+"""Back-end contract tests through the C binding on the GPU, modelled on the reference's
+graph_tests/jit_test.cpp (kernel == host evaluate for every operator and derivative),
+workflow_test.cpp (setters, repeated items), piecewise_test.cpp (table kernels) and the
+converge item of c_binding_test.c."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def g(lib):
+    from graph_framework_b200.graph import Context
+    c = Context()
+    yield c
+    c.close()
+
+
+def test_every_operator_kernel_matches_host_evaluate(g):
+    """jit_test.cpp:49-70, 165-340: add_kernel -> compile -> run -> copy_to_host vs node->evaluate()."""
+    n = 257
+    rng = np.random.default_rng(0)
+    xs, ys, zs = rng.uniform(0.2, 3.0, n), rng.uniform(0.2, 3.0, n), rng.uniform(-2.0, 2.0, n)
+    x, y, z = g.variable(n, "x", xs), g.variable(n, "y", ys), g.variable(n, "z", zs)
+    exprs = {
+        "add": x + y, "sub": x - z, "mul": x*z, "div": z/y, "fma": g.fma(x, y, z),
+        "sqrt": g.sqrt(x), "exp": g.exp(z), "log": g.log(y), "pow": g.pow(x, y), "pow15": g.pow(x, 1.5),
+        "sin": g.sin(z), "cos": g.cos(z), "atan": g.atan(x, z), "chain": g.sqrt(x*x + y*y)/(1.0 + g.exp(-z)),
+    }
+    outs = []
+    for name, e in exprs.items():
+        outs += [e, e.df(x), e.df(y), e.df(z)]
+    outs = [o for o in outs if o.evaluate().size == n]          # constants are not kernel outputs
+    g.add_item([x, y, z], outs, [], "operators", n)
+    g.compile()
+    g.run()
+    for o in outs:
+        got = g.copy_to_host(o, n)
+        ref = o.evaluate()
+        # rcp/rsqrt seeds are refined to <= 1 ulp, libm calls differ by a few ulp
+        assert np.allclose(got, ref, rtol=4.0e-15, atol=1.0e-300), np.max(np.abs(got - ref)/np.abs(ref))
+
+
+def test_workflow_setters_and_repeated_items(g):
+    """workflow_test.cpp:19-70: several setters read the OLD values; ten runs fuse into one launch."""
+    n = 100
+    a = g.variable(n, "a", np.full(n, 2.0))
+    b = g.variable(n, "b", np.arange(n, dtype=float))
+    c = g.variable(n, "c", np.ones(n))
+    g.add_item([a, b, c], [a*b], [(a + 1.0, a), (b + a, b), (c*2.0, c)], "update", n)
+    g.compile()
+    for _ in range(10):
+        g.run()
+    av, bv, cv = g.copy_to_host(a, n), g.copy_to_host(b, n), g.copy_to_host(c, n)
+    ea, eb, ec = np.full(n, 2.0), np.arange(n, dtype=float), np.ones(n)
+    last = None
+    for _ in range(10):
+        last = ea*eb
+        ea, eb, ec = ea + 1.0, eb + ea, ec*2.0
+    assert np.array_equal(av, ea) and np.array_equal(bv, eb) and np.array_equal(cv, ec)
+    assert last is not None
+
+
+def test_output_holds_value_of_last_step(g):
+    n = 64
+    a = g.variable(n, "a", np.full(n, 3.0))
+    out = a*a
+    g.add_item([a], [out], [(a + 1.0, a)], "square", n)
+    g.compile()
+    for _ in range(5):
+        g.run()
+    assert np.array_equal(g.copy_to_host(a, n), np.full(n, 8.0))
+    assert np.array_equal(g.copy_to_host(out, n), np.full(n, 49.0))      # computed from a = 7 in the fifth step
+
+
+def test_converge_item_newton_sqrt(g):
+    """c_binding_test.c converge item: Newton for x^2 = s with the reference's stopping rule."""
+    n = 33
+    s = np.linspace(1.0, 50.0, n)
+    sv = g.variable(n, "s", s)
+    x = g.variable(n, "x", np.ones(n))
+    f = x*x - sv
+    g.add_converge_item([sv, x], [f*f], [(x - f/f.df(x), x)], "newton_sqrt", n, 1.0e-30, 1000)
+    g.compile()
+    g.run()
+    assert np.allclose(g.copy_to_host(x, n), np.sqrt(s), rtol=1.0e-15)
+
+
+def test_piecewise_kernels_match_host(g):
+    """piecewise_test.cpp:53-75: table kernels (global and TMA-staged groups) vs host evaluation,
+    including arguments outside the grid (clamped to the edge cells)."""
+    n = 500
+    rng = np.random.default_rng(1)
+    xs = rng.uniform(-0.3, 1.3, n)
+    ys = rng.uniform(-0.3, 1.3, n)
+    x, y = g.variable(n, "x", xs), g.variable(n, "y", ys)
+    t1a, t1b = rng.normal(size=40), rng.normal(size=40)
+    t2a, t2b = rng.normal(size=(30, 20)), rng.normal(size=(30, 20))
+    p1a = g.piecewise_1D(x, 1.0/40, 0.0, t1a)
+    p1b = g.piecewise_1D(x, 1.0/40, 0.0, t1b)
+    p2a = g.piecewise_2D(20, x, 1.0/30, 0.0, y, 1.0/20, 0.0, t2a.ravel())
+    p2b = g.piecewise_2D(20, x, 1.0/30, 0.0, y, 1.0/20, 0.0, t2b.ravel())
+    outs = [p1a*x + p1b, p2a + p2b*y, (p1a + p2a)*(p1b - p2b)]
+    g.add_item([x, y], outs, [], "tables", n)
+    g.compile()
+    g.run()
+    for o in outs:
+        assert np.allclose(g.copy_to_host(o, n), o.evaluate(), rtol=1.0e-15, atol=1.0e-300)
+    src = g.source()
+    assert "gfb::smem" in src and "__ldg" in src
+
+
+def test_max_reduction_handles_sign_and_size(lib):
+    """cuda_context.hpp:954-995 replacement: grid-wide maximum, any sign, ragged sizes."""
+    ctx = lib.gfb_ctx_create(0)
+    assert ctx
+    rng = np.random.default_rng(2)
+    for n in (1, 31, 1000, 1 << 20, (1 << 20) + 17):
+        for shift in (0.0, -10.0):
+            a = rng.normal(size=n) + shift
+            key = 1000 + n + int(shift)
+            assert lib.gfb_buffer(ctx, key, a.nbytes, a.ctypes.data_as(ctypes.c_void_p), None) == 0
+            out = ctypes.c_double(0)
+            assert lib.gfb_max(ctx, key, n, ctypes.byref(out)) == 0
+            assert out.value == a.max()
+    lib.gfb_ctx_destroy(ctx)
+
+
+def test_deposit_matches_oracle(lib):
+    """Deposition histogram kernel vs the numpy restatement of utilities/bin.py:53-106."""
+    import torch
+    from graph_framework_b200 import workloads, parallel
+    from graph_framework_b200.rays import RayTracer
+    from oracle import port
+    n = 20000
+    state = workloads.efit_ensemble(n, seed=9)
+    tr = RayTracer("ordinary_wave", "efit", n, 2.0e-5)
+    tr.set_state(state)
+    tr.init("kx")
+    tr.compile()
+    tr.step(50)
+    got = tr.get_state()
+    rng = np.random.default_rng(4)
+    w = rng.uniform(0.0, 1.0, n)
+    wt = torch.from_numpy(w).cuda()
+    bins = (16, 16, 32)
+    lo, hi = (2.3, -0.3, -0.3), (2.55, 0.3, 0.3)
+    hist = torch.zeros(bins, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    parallel.deposit(tr, wt, hist, lo, hi)
+    ref = port.deposit(got["x"], got["y"], got["z"], w, lo, hi, bins)
+    tr.close()
+    assert ref.sum() > 0.5*w.sum()
+    assert np.allclose(hist.cpu().numpy(), ref, rtol=1.0e-12, atol=1.0e-12)
