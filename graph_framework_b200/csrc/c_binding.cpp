@@ -191,6 +191,7 @@ const char *graph_get_source(graph_c_context *c) {
 namespace {
 equilibrium::shared<> make_equilibrium(const std::string &name, const std::string &table_file) {
     if (name == "efit") return equilibrium::make_efit<> (table_file);
+    if (name == "vmec") return equilibrium::make_vmec<> (table_file);
     if (name == "slab") return equilibrium::make_slab<> ();
     if (name == "slab_density") return equilibrium::make_slab_density<> ();
     if (name == "slab_field") return equilibrium::make_slab_field<> ();

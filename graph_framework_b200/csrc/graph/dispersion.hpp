@@ -230,6 +230,13 @@ namespace dispersion {
         }
     };
 
+///  See dispersion_interface: whether the k_vec correction term is applied (default: no, like
+///  the reference's effective behaviour).
+    inline bool &kvec_correction() {
+        static thread_local bool on = false;
+        return on;
+    }
+
     template<class D>
     concept function = std::is_base_of<dispersion_function<typename D::base, D::safe_math>, D>::value;
 
@@ -281,9 +288,23 @@ namespace dispersion {
             dxdt = -dDdkx/dDdw;
             dydt = -dDdky/dDdw;
             dzdt = -dDdkz/dDdw;
-            dkxdt = (dDdx - dDdk_vec->dot(dkdx))/dDdw;
-            dkydt = (dDdy - dDdk_vec->dot(dkdy))/dDdw;
-            dkzdt = (dDdz - dDdk_vec->dot(dkdz))/dDdw;
+//  The reference subtracts dD/dk_vec . dk_vec/dx so that the coordinate derivative is taken at
+//  fixed Cartesian k_vec (dispersion.hpp:1427-1429).  In the reference that term is identically
+//  zero in practice: for Cartesian equilibria dk_vec/dx = 0, and for curvilinear ones (VMEC) its
+//  reducer rewrites n = k_vec/w so that the k_vec component nodes no longer occur inside D and
+//  D->df(k_vec->get_x()) reduces to zero.  Measured: with the term dropped this back end matches
+//  the reference's VMEC right-hand side to 1e-15 on every component, with it kept dk/dt differs by
+//  O(1) (tests/golden/ref_rhs_ordinary_wave_vmec.npz).  Reproduced, not fixed;
+//  set dispersion::kvec_correction() = true for the formula as written.
+            if (kvec_correction()) {
+                dkxdt = (dDdx - dDdk_vec->dot(dkdx))/dDdw;
+                dkydt = (dDdy - dDdk_vec->dot(dkdy))/dDdw;
+                dkzdt = (dDdz - dDdk_vec->dot(dkdz))/dDdw;
+            } else {
+                dkxdt = dDdx/dDdw;
+                dkydt = dDdy/dDdw;
+                dkzdt = dDdz/dDdw;
+            }
             dsdt = graph::vector(dxdt, dydt, dzdt)->length();
         }
 

@@ -106,6 +106,8 @@ namespace jit {
         std::unordered_set<const graph::leaf_node *> visited;
         std::vector<std::string> index_reg;
         std::vector<std::vector<bool>> pair_loaded;
+///  Arguments that occur under both sin and cos in this kernel: one sincos() serves both.
+        std::unordered_map<const graph::leaf_node *, std::pair<const graph::leaf_node *, const graph::leaf_node *>> trig;
 
         static const graph::leaf_node *strip(const graph::leaf_node *n) {
             while (n->op == graph::op_t::pseudo) n = n->args[0].get();
@@ -126,6 +128,8 @@ namespace jit {
                 }
             }
             if (n->op == graph::op_t::div) denominators[strip(n->args[1].get())]++;
+            if (n->op == graph::op_t::sin) trig[strip(n->args[0].get())].first = n;
+            if (n->op == graph::op_t::cos) trig[strip(n->args[0].get())].second = n;
             if (n->is_piecewise()) {
                 const graph::leaf_node *a0 = strip(n->args[0].get());
                 const graph::leaf_node *a1 = n->args[1].get() ? strip(n->args[1].get()) : nullptr;
@@ -255,6 +259,21 @@ namespace jit {
                 info.num_statements += 2;
                 inv_reg.emplace(n, qname);      // 1/sqrt(x) is free: divisions by this node multiply by q
                 return reg.emplace(n, name).first->second;
+            }
+            if (n->op == op_t::sin || n->op == op_t::cos) {
+                const graph::leaf_node *arg = strip(n->args[0].get());
+                auto both = trig.find(arg);
+                if (both != trig.end() && both->second.first && both->second.second) {
+                    const std::string areg = emit(arg);
+                    const std::string sname = "t" + std::to_string(both->second.first->id);
+                    const std::string cname = "t" + std::to_string(both->second.second->id);
+                    out << "        double " << sname << ", " << cname << ";" << std::endl
+                        << "        sincos(" << areg << ", &" << sname << ", &" << cname << ");" << std::endl;
+                    info.num_statements += 2;
+                    reg.emplace(both->second.first, sname);
+                    reg.emplace(both->second.second, cname);
+                    return reg.at(n);
+                }
             }
             std::vector<std::string> a;
             for (size_t i = 0, ie = n->num_args(); i < ie; i++) {

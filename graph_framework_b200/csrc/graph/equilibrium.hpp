@@ -343,6 +343,136 @@ namespace equilibrium {
     shared<T, SAFE_MATH> make_efit(const efit<>::tables &t) {
         return std::make_shared<efit<T, SAFE_MATH>> (t);
     }
+//------------------------------------------------------------------------------
+///  VMEC stellarator equilibrium in flux coordinates (s, u, v)  (equilibrium.hpp:1868-2413).
+///  R, Z, lambda are Fourier series in (m u - n v) whose amplitudes are radial cubic splines;
+///  the contravariant basis, the Jacobian and B = (J B^u e_u + J B^v e_v)/J follow by df().
+///  Reference quirk kept: chi is evaluated with the NORMALISED s as spline argument
+///  (equilibrium.hpp:2138 vs :2045-2050).
+//------------------------------------------------------------------------------
+    template<typename T=double, bool SAFE_MATH=false>
+    class vmec final : public generic<T, SAFE_MATH> {
+    public:
+        struct tables {
+            double sminh, sminf, ds, dphi, signj;
+            std::array<std::vector<double>, 4> chi;
+            std::array<std::vector<std::vector<double>>, 4> rmnc, zmns, lmns;     // [coefficient][mode][radial cell]
+            std::vector<double> xm, xn;
+        };
+    private:
+        const tables tab;
+        leaf_ptr s_cache, u_cache, v_cache, x_cache, y_cache, z_cache;
+        vector_ptr esups_cache, esupu_cache, esupv_cache, bvec_cache;
+
+        leaf_ptr spline(const std::array<std::vector<std::vector<double>>, 4> &c, const size_t mode,
+                        leaf_ptr s, const double offset) {
+            return build_1D_spline({graph::piecewise_1D(c[0][mode], s, tab.ds, offset),
+                                    graph::piecewise_1D(c[1][mode], s, tab.ds, offset),
+                                    graph::piecewise_1D(c[2][mode], s, tab.ds, offset),
+                                    graph::piecewise_1D(c[3][mode], s, tab.ds, offset)}, s, tab.ds, offset);
+        }
+///  Cylindrical (dR, R dphi, dZ) components rotated to Cartesian (equilibrium.hpp:1948-2010).
+        vector_ptr rotate(leaf_ptr a, leaf_ptr b, leaf_ptr c) {
+            auto cosv = graph::cos(v_cache);
+            auto sinv = graph::sin(v_cache);
+            auto zero = graph::zero();
+            auto m = graph::matrix(graph::vector(cosv, -sinv, zero),
+                                   graph::vector(sinv, cosv, zero),
+                                   graph::vector(zero, zero, graph::one()));
+            return m->dot(graph::vector(a, b, c));
+        }
+        leaf_ptr get_chi(leaf_ptr s) {
+            return build_1D_spline({graph::piecewise_1D(tab.chi[0], s, tab.ds, tab.sminf),
+                                    graph::piecewise_1D(tab.chi[1], s, tab.ds, tab.sminf),
+                                    graph::piecewise_1D(tab.chi[2], s, tab.ds, tab.sminf),
+                                    graph::piecewise_1D(tab.chi[3], s, tab.ds, tab.sminf)}, s, tab.ds, tab.sminf);
+        }
+        void set_cache(leaf_ptr s, leaf_ptr u, leaf_ptr v) {
+            if (s->is_match(s_cache) && u->is_match(u_cache) && v->is_match(v_cache)) return;
+            s_cache = s;
+            u_cache = u;
+            v_cache = v;
+            auto s_norm_f = (s - tab.sminf)/tab.ds;
+            auto zero = graph::zero();
+            leaf_ptr r = zero, z = zero, l = zero;
+            for (size_t i = 0, ie = tab.xm.size(); i < ie; i++) {
+                auto rmnc = spline(tab.rmnc, i, s, tab.sminf);
+                auto zmns = spline(tab.zmns, i, s, tab.sminf);
+                auto lmns = spline(tab.lmns, i, s, tab.sminh);
+                auto angle = graph::constant(tab.xm[i])*u - graph::constant(tab.xn[i])*v;
+                auto sinmn = graph::sin(angle);
+                r = r + rmnc*graph::cos(angle);
+                z = z + zmns*sinmn;
+                l = l + lmns*sinmn;
+            }
+            x_cache = r*graph::cos(v);
+            y_cache = r*graph::sin(v);
+            z_cache = z;
+            auto esubs = rotate(r->df(s), zero, z->df(s));
+            auto esubu = rotate(r->df(u), zero, z->df(u));
+            auto esubv = rotate(r->df(v), r, z->df(v));
+            auto jacobian = esubs->dot(esubu->cross(esubv));
+            esups_cache = esubu->cross(esubv)/jacobian;
+            esupu_cache = esubv->cross(esubs)/jacobian;
+            esupv_cache = esubs->cross(esubu)/jacobian;
+            auto phip = (graph::constant(tab.signj)*graph::constant(tab.dphi)*s)->df(s);
+            auto jbsupu = get_chi(s_norm_f)->df(s) - phip*l->df(v);
+            auto jbsupv = phip*(1.0 + l->df(u));
+            bvec_cache = (jbsupu*esubu + jbsupv*esubv)/jacobian;
+        }
+///  (1 - |s|^1.5)^2  (equilibrium.hpp:2160-2163).
+        leaf_ptr get_profile(leaf_ptr s) {
+            return graph::pow(1.0 - graph::pow(graph::sqrt(s*s), 1.5), 2.0);
+        }
+    public:
+        vmec(const tables &t) : generic<T, SAFE_MATH> ({deuterium_mass}, {1}), tab(t) {
+            s_cache = u_cache = v_cache = graph::zero();
+        }
+        virtual vector_ptr get_esup1(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return esups_cache; }
+        virtual vector_ptr get_esup2(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return esupu_cache; }
+        virtual vector_ptr get_esup3(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return esupv_cache; }
+        virtual leaf_ptr get_electron_density(leaf_ptr s, leaf_ptr, leaf_ptr) { return graph::constant(1.0E19)*get_profile(s); }
+        virtual leaf_ptr get_ion_density(const size_t, leaf_ptr s, leaf_ptr u, leaf_ptr v) { return get_electron_density(s, u, v); }
+        virtual leaf_ptr get_electron_temperature(leaf_ptr s, leaf_ptr, leaf_ptr) { return graph::constant(1000.0)*get_profile(s); }
+        virtual leaf_ptr get_ion_temperature(const size_t, leaf_ptr s, leaf_ptr u, leaf_ptr v) { return get_electron_temperature(s, u, v); }
+        virtual vector_ptr get_magnetic_field(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return bvec_cache; }
+        virtual leaf_ptr get_characteristic_field(const size_t=0) final {
+            auto zero = graph::zero();
+            return get_magnetic_field(zero, zero, zero)->length();
+        }
+        virtual leaf_ptr get_x(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return x_cache; }
+        virtual leaf_ptr get_y(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return y_cache; }
+        virtual leaf_ptr get_z(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return z_cache; }
+    };
+
+///  Load VMEC tables (variable names of equilibrium.hpp:2424-2640) from a GFBT file.
+    inline vmec<>::tables load_vmec_tables(const std::string &spline_file) {
+        table_file f(spline_file);
+        vmec<>::tables t;
+        t.sminf = f.scalar("sminf"); t.sminh = f.scalar("sminh"); t.ds = f.scalar("ds");
+        t.dphi = f.scalar("dphi"); t.signj = f.scalar("signj");
+        t.xm = f.get("xm");
+        t.xn = f.get("xn");
+        const size_t modes = t.xm.size();
+        auto rows = [modes] (const std::vector<double> &flat) {
+            const size_t cols = flat.size()/modes;
+            std::vector<std::vector<double>> r(modes);
+            for (size_t i = 0; i < modes; i++) r[i].assign(flat.begin() + i*cols, flat.begin() + (i + 1)*cols);
+            return r;
+        };
+        for (size_t i = 0; i < 4; i++) {
+            const std::string n = std::to_string(i);
+            t.chi[i] = f.get("chi_c" + n);
+            t.rmnc[i] = rows(f.get("rmnc_c" + n));
+            t.zmns[i] = rows(f.get("zmns_c" + n));
+            t.lmns[i] = rows(f.get("lmns_c" + n));
+        }
+        return t;
+    }
+    template<typename T=double, bool SAFE_MATH=false>
+    shared<T, SAFE_MATH> make_vmec(const std::string &spline_file) {
+        return std::make_shared<vmec<T, SAFE_MATH>> (load_vmec_tables(spline_file));
+    }
 }
 
 #endif /* gfb_graph_equilibrium_hpp */

@@ -14,8 +14,9 @@ import numpy as np
 from ._lib import lib, check, c_double_p, GfbError
 
 STATE = ("t", "w", "x", "y", "z", "kx", "ky", "kz")
-_DEFAULT_EFIT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                             "tests", "golden", "efit.gfbt")
+_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+_DEFAULT_EFIT = os.path.join(_GOLDEN, "efit.gfbt")
+_DEFAULT_VMEC = os.path.join(_GOLDEN, "vmec.gfbt")
 
 
 def _ptr_array(arrays, n):
@@ -30,6 +31,8 @@ class RayTracer:
                  device=0, options=None):
         if equilibrium == "efit" and table_file is None:
             table_file = _DEFAULT_EFIT
+        if equilibrium == "vmec" and table_file is None:
+            table_file = _DEFAULT_VMEC
         self.n = int(num_rays)
         self.h = lib.gfb_rays_create(dispersion.encode(), equilibrium.encode(),
                                      (table_file or "").encode(), solver.encode(), self.n,

@@ -76,6 +76,20 @@ def interior_states(n, seed=1):
     return s
 
 
+def vmec_states(n, seed=0):
+    """C4: flux coordinates (s, u, v) stored in the x, y, z slots: s ~ U(0.2, 0.9), u, v ~ U(0, 2 pi),
+    w = 500, covariant wave numbers ~ N(0, 100) (no reference run exists)."""
+    rng = np.random.default_rng(seed)
+    s = {"t": np.zeros(n), "w": np.full(n, 500.0)}
+    s["x"] = rng.uniform(0.2, 0.9, n)
+    s["y"] = rng.uniform(0.0, 2.0*np.pi, n)
+    s["z"] = rng.uniform(0.0, 2.0*np.pi, n)
+    s["kx"] = rng.normal(0.0, 100.0, n)
+    s["ky"] = rng.normal(0.0, 100.0, n)
+    s["kz"] = rng.normal(0.0, 100.0, n)
+    return s
+
+
 def boris_ensemble(n, seed=0):
     """C5: xkorc start (xkorc.cpp:47-64) jittered so particles do not share one table cell."""
     rng = np.random.default_rng(seed)

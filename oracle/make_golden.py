@@ -78,6 +78,15 @@ def korc_case():
          b0=np.array(info["b0"]), larmor_radius=np.array(info["larmor_radius"]))
 
 
+def vmec_case():
+    """VMEC right-hand sides from the reference (graph build ~10 min, kernel compile minutes)."""
+    n = 16
+    s = workloads.vmec_states(n, seed=8)
+    for disp in ("ordinary_wave", "cold_plasma"):
+        out = reference.rhs(disp, "vmec", s)
+        save("ref_rhs_%s_vmec" % disp, state=workloads.pack(s), rhs=out)
+
+
 def defect_case():
     """Evidence for the reference's symbolic dD/dz defect (cold_plasma in a z-dependent field):
     its own D at z +- h and w +- h next to its own symbolic dkz/dt."""
@@ -108,3 +117,5 @@ if __name__ == "__main__":
         korc_case()
     if "defect" in which:
         defect_case()
+    if "vmec" in which:
+        vmec_case()

@@ -22,7 +22,7 @@ def available():
     return os.path.exists(DRIVER) and os.access(DRIVER, os.X_OK)
 
 
-def _run(args, timeout=1800, threads=None):
+def _run(args, timeout=7200, threads=None):
     env = dict(os.environ)
     env.setdefault("GFB_EFIT_FILE", os.path.join(ROOT, "tests", "golden", "efit.gfbt"))
     env.setdefault("GFB_VMEC_FILE", os.path.join(ROOT, "tests", "golden", "vmec.gfbt"))

@@ -9,6 +9,7 @@ using graph::leaf_ptr;
 
 static equilibrium::shared<> make_eq(const std::string &name, const std::string &efit) {
     if (name == "efit") return equilibrium::make_efit<> (efit);
+    if (name == "vmec") return equilibrium::make_vmec<> (std::getenv("GFB_VMEC_FILE") ? std::getenv("GFB_VMEC_FILE") : "tests/golden/vmec.gfbt");
     if (name == "slab") return equilibrium::make_slab<> ();
     if (name == "slab_density") return equilibrium::make_slab_density<> ();
     if (name == "slab_field") return equilibrium::make_slab_field<> ();

@@ -20,4 +20,5 @@ inline thread_local gfb_dim3 threadIdx, blockIdx, blockDim;
 inline void __syncthreads() {}
 using std::fma; using std::fmin; using std::fmax; using std::sqrt; using std::fabs;
 using std::exp; using std::log; using std::pow; using std::sin; using std::cos; using std::atan2;
+inline void sincos(const double x, double *s, double *c) { *s = std::sin(x); *c = std::cos(x); }
 #endif

@@ -57,7 +57,10 @@ def run_harness(cu, tab, kernel, arrays, n, steps, ni, no, tag, scalar=None):
 
 RHS_CASES = [("ordinary_wave", "efit"), ("extra_ordinary_wave", "efit"), ("cold_plasma", "efit"),
              ("cold_plasma", "slab"), ("cold_plasma", "slab_density"), ("ordinary_wave", "slab_density"),
-             ("bohm_gross", "no_magnetic_field"), ("simple", "slab")]
+             ("bohm_gross", "no_magnetic_field"), ("simple", "slab"), ("ordinary_wave", "vmec"), ("cold_plasma", "vmec")]
+#  cold_plasma in a field that depends on the coordinate: the reference's symbolic dD/dx_i is defective
+#  (tests/test_oracle.py::test_reference_dkz_defect); those components are not compared with it.
+REFERENCE_DEFECT = {("cold_plasma", "efit"): ("dkzdt",), ("cold_plasma", "vmec"): ("dkxdt", "dkydt", "dkzdt")}
 
 
 @pytest.mark.parametrize("disp,eq", RHS_CASES)
@@ -69,8 +72,8 @@ def test_emitted_rhs_matches_reference(emit_tool, disp, eq):
     assert info["divides"] == 0 or info["reciprocals"] >= 0
     out = run_harness(cu, tab, "rhs_kernel", g["state"], n, 1, 8, 7, tag)[8:]
     for i, k in enumerate(("dxdt", "dydt", "dzdt", "dkxdt", "dkydt", "dkzdt", "D")):
-        if (disp, eq) == ("cold_plasma", "efit") and k == "dkzdt":
-            continue        # reference defect, see tests/test_oracle.py::test_reference_dkz_defect
+        if k in REFERENCE_DEFECT.get((disp, eq), ()):
+            continue
         if np.max(np.abs(g["rhs"][i])) == 0.0:
             assert np.max(np.abs(out[i])) == 0.0
             continue
