@@ -77,16 +77,18 @@ def interior_states(n, seed=1):
 
 
 def vmec_states(n, seed=0):
-    """C4: flux coordinates (s, u, v) stored in the x, y, z slots: s ~ U(0.2, 0.9), u, v ~ U(0, 2 pi),
-    w = 500, covariant wave numbers ~ N(0, 100) (no reference run exists)."""
+    """C4: flux coordinates (s, u, v) stored in the x, y, z slots: s ~ U(0.2, 0.8), u, v ~ U(0, 2 pi),
+    w = 1000 (above the central plasma frequency of the 1e19 m^-3 profile), covariant wave numbers
+    k_u, k_v ~ N(0, 20) and a radial guess k_s = 100 for the Newton solve.  No reference run exists
+    for this configuration."""
     rng = np.random.default_rng(seed)
-    s = {"t": np.zeros(n), "w": np.full(n, 500.0)}
-    s["x"] = rng.uniform(0.2, 0.9, n)
+    s = {"t": np.zeros(n), "w": np.full(n, 1000.0)}
+    s["x"] = rng.uniform(0.2, 0.8, n)
     s["y"] = rng.uniform(0.0, 2.0*np.pi, n)
     s["z"] = rng.uniform(0.0, 2.0*np.pi, n)
-    s["kx"] = rng.normal(0.0, 100.0, n)
-    s["ky"] = rng.normal(0.0, 100.0, n)
-    s["kz"] = rng.normal(0.0, 100.0, n)
+    s["kx"] = np.full(n, 100.0)
+    s["ky"] = rng.normal(0.0, 20.0, n)
+    s["kz"] = rng.normal(0.0, 20.0, n)
     return s
 
 
