@@ -237,6 +237,13 @@ namespace dispersion {
         return on;
     }
 
+///  Whether dispersion_interface differentiates D with one reverse sweep (graph::gradient)
+///  instead of seven forward df() calls.
+    inline bool &reverse_mode() {
+        static thread_local bool on = std::getenv("GFB_FORWARD_MODE") == nullptr;
+        return on;
+    }
+
     template<class D>
     concept function = std::is_base_of<dispersion_function<typename D::base, D::safe_math>, D>::value;
 
@@ -263,13 +270,20 @@ namespace dispersion {
             auto dkdz = k_vec->df(z);
             auto dDdk_vec = graph::vector(D->df(k_vec->get_x()), D->df(k_vec->get_y()), D->df(k_vec->get_z()));
 
-            auto dDdw = D->df(w);
-            auto dDdkx = D->df(kx);
-            auto dDdky = D->df(ky);
-            auto dDdkz = D->df(kz);
-            auto dDdx = D->df(x);
-            auto dDdy = D->df(y);
-            auto dDdz = D->df(z);
+            leaf_ptr dDdw, dDdkx, dDdky, dDdkz, dDdx, dDdy, dDdz;
+            if (reverse_mode()) {
+//  One backward sweep for all seven derivatives (graph::gradient); same values as df().
+                auto g = graph::gradient(D, {w, kx, ky, kz, x, y, z});
+                dDdw = g[0]; dDdkx = g[1]; dDdky = g[2]; dDdkz = g[3]; dDdx = g[4]; dDdy = g[5]; dDdz = g[6];
+            } else {
+                dDdw = D->df(w);
+                dDdkx = D->df(kx);
+                dDdky = D->df(ky);
+                dDdkz = D->df(kz);
+                dDdx = D->df(x);
+                dDdy = D->df(y);
+                dDdz = D->df(z);
+            }
 
             if (graph::pseudo_variable_cast(x).get()) {
                 dkdx = dkdx->remove_pseudo();

@@ -785,6 +785,84 @@ namespace graph {
         return r;
     }
 
+//------------------------------------------------------------------------------
+///  Reverse-mode symbolic gradient: d f / d x_i for all requested leaves in ONE backward sweep
+///  over the DAG.  Mathematically identical to {f->df(x_i)}; the expression shape differs:
+///  every interior adjoint  df/dn  is formed once and shared by all x_i, where forward mode
+///  carries one tangent per x_i through every node.  For the ray Hamiltonian (7 derivatives of
+///  one scalar whose coordinate dependence funnels through psi(R, Z)) this is the cheaper form.
+///  Semantics match df(): coefficients of piecewise nodes and pseudo variables are leaves.
+//------------------------------------------------------------------------------
+    inline std::vector<leaf_ptr> gradient(leaf_ptr f, const std::vector<leaf_ptr> &xs) {
+        std::vector<leaf_node *> order;
+        std::unordered_map<const leaf_node *, bool> seen;
+        std::function<void(leaf_node *)> visit = [&] (leaf_node *n) {
+            if (seen[n]) return;
+            seen[n] = true;
+            if (n->op != op_t::pseudo && !n->is_piecewise()) {
+                for (size_t i = 0, ie = n->num_args(); i < ie; i++) visit(n->args[i].get());
+            }
+            order.push_back(n);
+        };
+        visit(f.get());
+        std::unordered_map<const leaf_node *, leaf_ptr> adj;
+        auto accumulate = [&adj] (const leaf_ptr &n, leaf_ptr v) {
+            if (n->is_constant()) return;
+            auto it = adj.find(n.get());
+            if (it == adj.end()) adj.emplace(n.get(), v);
+            else it->second = add(it->second, v);
+        };
+        adj.emplace(f.get(), one());
+        for (auto it = order.rbegin(); it != order.rend(); ++it) {
+            leaf_node *n = *it;
+            auto found = adj.find(n);
+            if (found == adj.end()) continue;
+            const leaf_ptr a = found->second;
+            if (a->is_constant(0.0)) continue;
+            const leaf_ptr self = n->shared_from_this();
+            const leaf_ptr &x = n->args[0];
+            const leaf_ptr &y = n->args[1];
+            switch (n->op) {
+                case op_t::add: accumulate(x, a); accumulate(y, a); break;
+                case op_t::sub: accumulate(x, a); accumulate(y, mul(none(), a)); break;
+                case op_t::mul: accumulate(x, mul(a, y)); accumulate(y, mul(a, x)); break;
+                case op_t::div: {
+                    auto q = div(a, y);
+                    accumulate(x, q);
+                    accumulate(y, mul(none(), mul(q, self)));
+                    break;
+                }
+                case op_t::fma: accumulate(x, mul(a, y)); accumulate(y, mul(a, x)); accumulate(n->args[2], a); break;
+                case op_t::sqrt: accumulate(x, div(a, mul(constant(2.0), self))); break;
+                case op_t::exp: accumulate(x, mul(a, self)); break;
+                case op_t::log: accumulate(x, div(a, x)); break;
+                case op_t::pow:
+                    if (y->is_constant()) {
+                        accumulate(x, mul(a, mul(y, pow(x, constant(y->value - 1.0)))));
+                    } else {
+                        accumulate(x, mul(a, mul(y, div(self, x))));
+                        accumulate(y, mul(a, mul(self, log(x))));
+                    }
+                    break;
+                case op_t::sin: accumulate(x, mul(a, cos(x))); break;
+                case op_t::cos: accumulate(x, mul(none(), mul(a, sin(x)))); break;
+                case op_t::atan: {
+                    auto q = div(a, add(mul(x, x), mul(y, y)));
+                    accumulate(x, mul(none(), mul(q, y)));
+                    accumulate(y, mul(q, x));
+                    break;
+                }
+                default: break;
+            }
+        }
+        std::vector<leaf_ptr> result;
+        for (auto &x : xs) {
+            auto it = adj.find(x.get());
+            result.push_back(it == adj.end() ? zero() : it->second);
+        }
+        return result;
+    }
+
     inline bool leaf_node::is_constant_like() {
         if (op == op_t::constant) return true;
         if (op == op_t::variable) return false;

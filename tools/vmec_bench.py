@@ -14,6 +14,9 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 1250000       # 10^7 rays / 8 GPU
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 opts = sys.argv[4] if len(sys.argv) > 4 else ""
 state = workloads.vmec_states(n, seed=0)
+if os.environ.get("GFB_SORT_RAYS"):
+    order = __import__("numpy").argsort(state["x"], kind="stable")      # radial cell locality experiment
+    state = {k: v[order] for k, v in state.items()}
 t0 = time.perf_counter()
 tr = RayTracer(disp, "vmec", n, 1.0e-4, options=("fused_steps=%d " % steps) + opts)
 tr.set_state(state)
