@@ -1,7 +1,7 @@
 #!/bin/bash
-# Sweep launch/emission options of the headline workload (run on the GPU box).
+# Sweep launch/emission options of a bench workload (run on the GPU box).
 WL=${1:-efit_xmode}
-for opt in "minblocks=1" "minblocks=3" "minblocks=4" "minblocks=5" "block=256 minblocks=2" "block=64 minblocks=8" "unroll_stages=1 minblocks=4" "fast_div=0 minblocks=4" "stage_tables=0 minblocks=4"; do
+for opt in "unroll_stages=0 minblocks=2" "unroll_stages=0 minblocks=3" "unroll_stages=0 minblocks=4" "unroll_stages=1 minblocks=2" "unroll_stages=1 minblocks=3" "unroll_stages=1 minblocks=4" "unroll_stages=0 minblocks=3 block=64" "unroll_stages=0 minblocks=2 block=256"; do
   echo "== $WL $opt"
   python bench.py --workload $WL --steps 3 --warmup 2 --no-cpu-baseline --options "$opt" 2>&1 | python -c "
 import sys,json
