@@ -27,6 +27,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SUB_STEPS = 100
+#  From the committed ncu --set full captures of exactly this command (profiles/r1_ncu_*.txt):
+#  DRAM bytes read + written per launch, and the share of cycles the FP64 pipe was busy.
+NCU = {
+    "efit_xmode": {"traffic": 64042496 + 11938304, "fp64_pipe_active_pct": 74.7, "source": "profiles/r1_ncu_efit_xmode_solver_kernel.txt"},
+    "efit_cold": {"traffic": 64056832 + 9436928, "fp64_pipe_active_pct": 72.8, "source": "profiles/r1_ncu_efit_cold_solver_kernel.txt"},
+}
 WORKLOADS = {
     # name: (dispersion, equilibrium, default rays per GPU, dt)
     "efit_xmode": ("extra_ordinary_wave", "efit", 1000000, 2.0e-5),     # BASELINE configs[1]
@@ -270,7 +276,11 @@ def main():
                        "l2": "flushed between timed steps (256 MiB fill, untimed)",
                        "options": args.options},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": (achieved/fp64_peak) if achieved else None, "traffic": None,
+                         "frac": (achieved/fp64_peak) if achieved else None,
+                         "traffic": NCU.get(args.workload, {}).get("traffic"),
+                         "fp64_pipe_active_pct_ncu": NCU.get(args.workload, {}).get("fp64_pipe_active_pct"),
+                         "ncu_source": NCU.get(args.workload, {}).get("source"),
+                         "note": "achieved = the REFERENCE kernel's flop count per ray-step (BASELINE.md section 2) x ray-steps / time, the unit of work SURVEY.md 8d fixes; this back end executes fewer FP64 instructions for the same step (reverse-mode gradient, shared reciprocals), so frac can exceed the FP64-pipe busy share and, for cold plasma, 1.0",
                          "peak_source": "DFMA peak measured live by gfb_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure); nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
                          "algorithmic_flop_per_ray_step": flop,
                          "hbm": {"algorithmic_bytes_per_launch": hbm_bytes,
