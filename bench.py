@@ -141,13 +141,71 @@ def reference_arm(args, rank, world):
     return 0
 
 
+def boris_arm(args, rank, local_rank, world):
+    """BASELINE configs[4]: the xkorc Boris push (graph_korc/xkorc.cpp:66-121) in the EFIT field.
+    Strong scaling: --rays is the TOTAL particle count, sharded over ranks."""
+    import numpy as np
+    import torch
+    from graph_framework_b200 import workloads, parallel
+    from graph_framework_b200.rays import BorisPusher
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    total = args.rays or 100000000
+    off, n = parallel.my_shard(total, rank, world)
+    x, y, z, ux, uy, uz = workloads.boris_ensemble(n, seed=rank)
+    push = BorisPusher("efit", n, dt=0.5, device=local_rank, options="fused_steps=%d %s" % (SUB_STEPS, args.options))
+    push.set_state(x, y, z, ux, uy, uz)
+    push.compile()
+    for _ in range(args.warmup):
+        push.step(SUB_STEPS)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    launches0 = push.launch_count()
+    ms = 0.0
+    for _ in range(args.steps):
+        push.timer_start()
+        push.step(SUB_STEPS)
+        ms += push.timer_stop()
+    launches = push.launch_count() - launches0
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st = push.get_state()
+    finite = bool(np.isfinite(st["gamma"]).all())
+    if rank == 0:
+        value = total*SUB_STEPS*args.steps/(ms*1.0e-3)
+        flop = workloads.FLOP_PER_PARTICLE_STEP_BORIS
+        print(json.dumps({
+            "metric": "particle-steps/sec (FP64 Boris)", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms/args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "boris: xkorc Boris push in the EFIT field, %d fused pushes per bench step" % SUB_STEPS,
+                       "particles_total": total, "dt": 0.5, "state_larger_than_L2": n*56 > 126e6, "options": args.options},
+            "roofline": {"bound": "fp64", "achieved": flop*value/world/1.0e12, "peak": None, "unit": "TFLOP/s", "frac": None,
+                         "traffic": None, "algorithmic_flop_per_particle_step": flop,
+                         "hbm": {"algorithmic_bytes_per_launch": 112*n, "achieved_gbs": 112*n/(ms/args.steps*1.0e-3)/1.0e9}},
+            "gpu_launches": launches, "finite": finite, "info": push.info()}))
+    push.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="efit_xmode", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="efit_xmode", choices=sorted(WORKLOADS) + ["boris"])
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
     ap.add_argument("--ref-rays", type=int, default=20000, help="rays of the bounded CPU sample")
     ap.add_argument("--options", default="", help="emit/launch options passed to gfb_rays_create")
@@ -158,6 +216,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.workload == "boris":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the Boris workload has no CPU arm in bench.py (see oracle/ref_driver korc mode)"}))
+            return 0
+        return boris_arm(args, rank, local_rank, world)
     if args.impl == "reference":
         return reference_arm(args, rank, world)
 
