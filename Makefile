@@ -32,3 +32,11 @@ $(LIB): build/kernels.o build/runtime.o build/c_binding.o
 
 clean:
 	rm -rf build $(LIB) $(SRC)/skeleton_text.inc
+
+# Reference-style C++ programs built against the header-only front end + libgfb200.so.
+TESTBIN := build/known_answers build/xrays_bench_b200
+tests: $(TESTBIN)
+build/known_answers: tests/cpp/known_answers.cpp $(wildcard $(SRC)/graph/*.hpp) $(LIB)
+	$(CXX) -std=c++20 -O1 -Iinclude -I$(CUDA)/include $< -o $@ -L$(PKG) -lgfb200 -Wl,-rpath,'$$ORIGIN/../$(PKG)'
+build/xrays_bench_b200: examples/xrays_bench.cpp $(wildcard $(SRC)/graph/*.hpp) $(LIB)
+	$(CXX) -std=c++20 -O1 -Iinclude -I$(CUDA)/include $< -o $@ -L$(PKG) -lgfb200 -Wl,-rpath,'$$ORIGIN/../$(PKG)' -lpthread

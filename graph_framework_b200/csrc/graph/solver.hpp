@@ -42,6 +42,7 @@ namespace solver {
 
     public:
         typedef DISPERSION_FUNCTION dispersion_function;
+        typedef typename DISPERSION_FUNCTION::base base;
 
         solver_interface(leaf_ptr w, leaf_ptr kx, leaf_ptr ky, leaf_ptr kz,
                          leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr t,
