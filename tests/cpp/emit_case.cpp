@@ -35,7 +35,12 @@ static jit::kernel_info build(const std::string &kind, equilibrium::shared<> eq,
                                      t, dt, D.get_residual(), n);
     } else if (kind == "newton" || kind == "loss") {
         auto f = D.get_d();
-        graph::map_nodes<> setters = {{kx - 1.0*f/f->df(kx), kx}};
+        leaf_ptr var = kx;
+        if (const char *v = std::getenv("GFB_NEWTON_VAR")) {
+            const std::string name = v;
+            var = name == "x" ? x : name == "y" ? y : name == "z" ? z : name == "ky" ? ky : name == "kz" ? kz : name == "w" ? w : kx;
+        }
+        graph::map_nodes<> setters = {{var - 1.0*f/f->df(var), var}};
         return jit::emit_item(src, opt, kind == "newton" ? jit::kernel_kind::newton : jit::kernel_kind::generic,
                               "loss_kernel", inputs, {f*f}, setters, n);
     } else if (kind == "rhs") {

@@ -43,6 +43,25 @@ def test_every_operator_kernel_matches_host_evaluate(g):
         assert np.allclose(got, ref, rtol=4.0e-15, atol=1.0e-300), np.max(np.abs(got - ref)/np.abs(ref))
 
 
+def test_division_and_sqrt_edge_values(g):
+    """The refined-seed reciprocal / rsqrt must keep IEEE results at the edges the ray path meets:
+    sqrt(0) = 0 (k = 0 cut-off searches, physics_test.cpp:380-470), x/inf = 0, x/0 = inf."""
+    vals = np.array([0.0, 1.0e-300, 1.0, 4.0, 1.0e300, np.inf])
+    n = vals.size
+    x = g.variable(n, "x", vals)
+    one = g.variable(n, "one", np.ones(n))
+    outs = [g.sqrt(x), one/x, g.sqrt(x)*g.sqrt(x), one/g.sqrt(x)]
+    g.add_item([x, one], outs, [], "edges", n)
+    g.compile()
+    g.run()
+    with np.errstate(all="ignore"):
+        ref = [np.sqrt(vals), 1.0/vals, vals, 1.0/np.sqrt(vals)]
+    for o, r in zip(outs, ref):
+        got = g.copy_to_host(o, n)
+        assert np.allclose(got[1:5], r[1:5], rtol=4.0e-16, atol=0.0), (got, r)
+        assert got[0] == r[0] or (np.isinf(got[0]) and np.isinf(r[0])), (got, r)
+
+
 def test_workflow_setters_and_repeated_items(g):
     """workflow_test.cpp:19-70: several setters read the OLD values; ten runs fuse into one launch."""
     n = 100
