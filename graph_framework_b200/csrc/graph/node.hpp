@@ -443,6 +443,17 @@ namespace graph {
         if (detail::caches().fold_tables && l->is_piecewise() && r->is_piecewise() &&
             detail::same_cells(l.get(), r.get()))
             return detail::zip_table(l.get(), r.get(), [] (double a, double b) { return a*b; });
+        if (l == r) {
+//  sqrt(u)*sqrt(u) -> u and (p*sqrt(u))*(p*sqrt(u)) -> (p*p)*u.  Besides saving the square root this
+//  keeps sqrt out of expressions that only need its square (n_perp^2 and (n_par n_perp)^2 in the
+//  cold-plasma determinant, dispersion.hpp:990-1007), whose derivative would otherwise be 0/0
+//  when k is parallel to B -- the state of the reference's cut-off searches (physics_test.cpp:472-530).
+            if (l->op == op_t::sqrt) return l->args[0];
+            if (l->op == op_t::mul && l->args[1]->op == op_t::sqrt)
+                return mul(mul(l->args[0], l->args[0]), l->args[1]->args[0]);
+            if (l->op == op_t::mul && l->args[0]->op == op_t::sqrt)
+                return mul(mul(l->args[1], l->args[1]), l->args[0]->args[0]);
+        }
         if (l->is_constant()) {
 //  c1*(c2*x) -> (c1*c2)*x
             if (r->op == op_t::mul && r->args[0]->is_constant())
