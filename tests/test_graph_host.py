@@ -61,14 +61,17 @@ def test_df_rules_numerically(g):
 
 
 def test_df_with_respect_to_subexpression(g):
-    """dispersion.hpp:1392-1396 differentiates with respect to k_vec components; efit uses psi->df(r)."""
+    """dispersion.hpp:1392-1396 differentiates with respect to k_vec components; efit uses psi->df(r).
+    df(x) matches x by node identity, so it sees exactly the occurrences of the node that survive
+    normalisation (sqrt(u)*sqrt(u) is reduced to u, as in the reference)."""
     x = g.variable(2, "x", [1.5, 2.5])
     y = g.variable(2, "y", [0.5, 0.1])
     r = g.sqrt(x*x + y*y)
-    f = r*r*r + 2.0*r
+    f = g.exp(r)*r + 2.0*r
     d = f.df(r).evaluate()
     rr = r.evaluate()
-    assert np.allclose(d, 3*rr**2 + 2, rtol=1e-14)
+    assert np.allclose(d, np.exp(rr)*(rr + 1.0) + 2.0, rtol=1e-14)
+    assert r*r == x*x + y*y
 
 
 def test_pseudo_variable_stops_df(g):
