@@ -213,6 +213,48 @@ namespace solver {
             }
         }
     };
+
+//------------------------------------------------------------------------------
+///  Second order symplectic split (position half step, momentum step, position half step) for
+///  separable Hamiltonians, solver.hpp:1016-1130.  Built in the graph like the reference does
+///  (stage arguments are pseudo variables) and run as a generic fused item.
+//------------------------------------------------------------------------------
+    template<dispersion::function DISPERSION_FUNCTION>
+    class split_simplextic : public solver_interface<DISPERSION_FUNCTION> {
+    protected:
+        typedef typename DISPERSION_FUNCTION::base T;
+        static constexpr bool SAFE_MATH = DISPERSION_FUNCTION::safe_math;
+    public:
+        split_simplextic(leaf_ptr w, leaf_ptr kx, leaf_ptr ky, leaf_ptr kz, leaf_ptr x, leaf_ptr y, leaf_ptr z,
+                         leaf_ptr t, leaf_ptr dt, equilibrium::shared<T, SAFE_MATH> &eq,
+                         const std::string &filename="", const size_t num_rays=0, const size_t index=0) :
+        solver_interface<DISPERSION_FUNCTION> (w, kx, ky, kz, x, y, z, t, eq, filename, num_rays, index) {
+            typedef dispersion::dispersion_interface<DISPERSION_FUNCTION> DI;
+//  Separable: dk/dt must not depend on k, dx/dt must not depend on x (solver.hpp:1060-1079).
+            bool separable = true;
+            for (auto rate : {this->D.get_dkxdt(), this->D.get_dkydt(), this->D.get_dkzdt()})
+                for (auto v : {kx, ky, kz}) separable = separable && rate->df(v)->is_constant(0.0);
+            for (auto rate : {this->D.get_dxdt(), this->D.get_dydt(), this->D.get_dzdt()})
+                for (auto v : {x, y, z}) separable = separable && rate->df(v)->is_constant(0.0);
+            if (!separable) {
+                std::cerr << "split_simplextic: Hamiltonian is not separable." << std::endl;
+                std::abort();
+            }
+            this->t_next = t + dt;
+            auto x1 = x + dt*this->D.get_dxdt()/2.0;
+            auto y1 = y + dt*this->D.get_dydt()/2.0;
+            auto z1 = z + dt*this->D.get_dzdt()/2.0;
+            auto pv = [] (leaf_ptr a) { return graph::pseudo_variable(a); };
+            DI D2(w, pv(kx), pv(ky), pv(kz), pv(x1), pv(y1), pv(z1), pv(t), eq);
+            this->kx_next = kx + dt*D2.get_dkxdt();
+            this->ky_next = ky + dt*D2.get_dkydt();
+            this->kz_next = kz + dt*D2.get_dkzdt();
+            DI D3(w, pv(this->kx_next), pv(this->ky_next), pv(this->kz_next), pv(x1), pv(y1), pv(z1), pv(t), eq);
+            this->x_next = x1 + dt*D3.get_dxdt()/2.0;
+            this->y_next = y1 + dt*D3.get_dydt()/2.0;
+            this->z_next = z1 + dt*D3.get_dzdt()/2.0;
+        }
+    };
 }
 
 #endif /* gfb_graph_solver_hpp */

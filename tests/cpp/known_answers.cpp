@@ -5,7 +5,7 @@
 // :380-470 cold-plasma cut-offs, :472-530 reflection, :583-618 EFIT reflection),
 // graph_tests/solver_test.cpp:28-60 (D^2 stays below tolerance for five steps) and
 // graph_tests/dispersion_test.cpp:25-64 (Newton solve for every wavenumber component and w).
-// Tolerances are the reference's CUDA-branch values.  split_simplextic variants are not built here.
+// Tolerances are the reference's CUDA-branch values.
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -57,13 +57,13 @@ static void invariant() {
 }
 
 // Linear density ramp, no field: x(t) is a parabola for Bohm-Gross and light waves.
-template<class DISPERSION>
-static void parabola(const double tolerance, const double k_guess, const bool thermal) {
+template<class SOLVER>
+static void parabola(const char *what, const double tolerance, const double k_guess, const bool thermal) {
     using namespace constants;
     ray r;
     r.set(600.0, k_guess, 0.0, 0.0, -1.0, 0.0, 0.0);
     auto eq = equilibrium::make_no_magnetic_field<> ();
-    auto solve = make<solver::rk4<DISPERSION>> (r, 0.1, eq);
+    auto solve = make<SOLVER> (r, 0.1, eq);
     solve.init(r.kx, tolerance);
     solve.compile();
     for (int i = 0; i < 20; i++) { solve.step(); solve.sync_host(); }
@@ -80,7 +80,7 @@ static void parabola(const double tolerance, const double k_guess, const bool th
         expected = -wp2_slope/(4.0*w0*w0)*time*time + k0/w0*time - 1.0;
     }
     const double d = r.x->evaluate().at(0) - expected;
-    EXPECT(d*d < tolerance, thermal ? "Bohm-Gross ray follows the analytic parabola" : "light wave follows the analytic parabola");
+    EXPECT(d*d < tolerance, what);
 }
 
 static void acoustic(const double tolerance) {
@@ -236,8 +236,10 @@ static void solves_every_unknown(const char *what, const double tolerance, const
 int main() {
     const double tolerance = 1.6E-21;       // physics_test.cpp:652, the reference's CUDA branch
     invariant();
-    parabola<dispersion::bohm_gross<>> (tolerance, 1000.0, true);
-    parabola<dispersion::light_wave<>> (tolerance, 100.0, false);
+    parabola<solver::rk4<dispersion::bohm_gross<>>> ("rk4: Bohm-Gross ray follows the analytic parabola", tolerance, 1000.0, true);
+    parabola<solver::split_simplextic<dispersion::bohm_gross<>>> ("split_simplextic: Bohm-Gross parabola", tolerance, 1000.0, true);
+    parabola<solver::rk4<dispersion::light_wave<>>> ("rk4: light wave follows the analytic parabola", tolerance, 100.0, false);
+    parabola<solver::split_simplextic<dispersion::light_wave<>>> ("split_simplextic: light-wave parabola", tolerance, 100.0, false);
     acoustic(tolerance);
     o_mode_cutoff();
     reflection(tolerance);
