@@ -54,6 +54,7 @@ def _load():
         "gfb_copy_d2h": (I, [P, U64, P, SZ]),
         "gfb_host_ptr": (I, [P, U64, c_void_pp]),
         "gfb_check_value": (I, [P, U64, SZ, c_double_p]),
+        "gfb_snapshot_async": (I, [P, ctypes.POINTER(U64), I, SZ, P]),
         "gfb_timer_start": (I, [P]),
         "gfb_timer_stop": (I, [P, ctypes.POINTER(ctypes.c_float)]),
         "gfb_stream": (P, [P]),
@@ -70,6 +71,7 @@ def _load():
         "gfb_rays_wait": (I, [P]),
         "gfb_rays_get_state": (I, [P, ctypes.POINTER(c_double_p), c_double_p]),
         "gfb_rays_put_state": (I, [P, ctypes.POINTER(c_double_p)]),
+        "gfb_rays_trace": (I, [P, SZ, SZ, c_double_p]),
         "gfb_rays_device_ptr": (I, [P, I, c_void_pp]),
         "gfb_rays_ctx": (P, [P]),
         "gfb_rays_source": (S, [P]),

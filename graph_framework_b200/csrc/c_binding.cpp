@@ -392,6 +392,19 @@ int gfb_rays_put_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]) {
     }
     return 0;
 }
+int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out) {
+    if (!r->compiled) return rays_fail("trace before compile");
+    std::vector<uint64_t> keys;
+    for (auto &v : r->vars) keys.push_back(reinterpret_cast<uint64_t> (v.get()));
+    keys.push_back(reinterpret_cast<uint64_t> (r->impl->residual().get()));
+    gfb_ctx *ctx = r->impl->context().device();
+    for (size_t b = 0; b < num_blocks; b++) {
+        r->impl->step(sub_steps);
+        if (gfb_snapshot_async(ctx, keys.data(), static_cast<int> (keys.size()), sizeof(double)*r->n,
+                               out + b*keys.size()*r->n)) return 1;
+    }
+    return gfb_wait(ctx);
+}
 int gfb_rays_device_ptr(gfb_rays *r, int which, void **device_ptr) {
     if (!r->compiled) return rays_fail("device_ptr before compile");
     if (which < 0 || which > GFB_NUM_STATE) return rays_fail("bad state index");

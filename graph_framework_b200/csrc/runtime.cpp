@@ -206,6 +206,13 @@ struct gfb_ctx {
     unsigned long long *scratch_host = nullptr; // pinned
     double *flush_buffer = nullptr;
     size_t flush_count = 0;
+//  Trajectory snapshots: two staging slots, a copy stream, events for the hand-over.
+    cudaStream_t copy_stream = nullptr;
+    void *stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    cudaEvent_t staged[2] = {nullptr, nullptr};     // slot filled (compute stream)
+    cudaEvent_t drained[2] = {nullptr, nullptr};    // slot copied out (copy stream)
+    unsigned next_slot = 0;
 };
 
 namespace {
@@ -287,6 +294,15 @@ void gfb_ctx_destroy(gfb_ctx *c) {
     if (c->scratch) cudaFree(c->scratch);
     if (c->scratch_host) cudaFreeHost(c->scratch_host);
     if (c->flush_buffer) cudaFree(c->flush_buffer);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+        for (int i = 0; i < 2; i++) {
+            if (c->stage[i]) cudaFree(c->stage[i]);
+            if (c->staged[i]) cudaEventDestroy(c->staged[i]);
+            if (c->drained[i]) cudaEventDestroy(c->drained[i]);
+        }
+    }
     cudaEventDestroy(c->ev_start);
     cudaEventDestroy(c->ev_stop);
     cudaStreamDestroy(c->stream);
@@ -530,7 +546,45 @@ int gfb_wait(gfb_ctx *c) {
             if (check(cudaMemcpyAsync(kv.second.host, kv.second.dev, kv.second.bytes, cudaMemcpyDeviceToHost, c->stream), "mirror")) return 1;
         }
     }
+    if (c->copy_stream && check(cudaStreamSynchronize(c->copy_stream), "copy stream sync")) return 1;
     return check(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+}
+
+int gfb_snapshot_async(gfb_ctx *c, const uint64_t *keys, int num_keys, size_t bytes_each, void *host_destination) {
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    const size_t total = bytes_each*static_cast<size_t> (num_keys);
+    if (!c->copy_stream) {
+        if (check(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "copy stream")) return 1;
+        for (int i = 0; i < 2; i++) {
+            cudaEventCreateWithFlags(&c->staged[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->drained[i], cudaEventDisableTiming);
+        }
+    }
+    if (c->stage_bytes < total) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        for (int i = 0; i < 2; i++) {
+            if (c->stage[i]) cudaFree(c->stage[i]);
+            if (check(cudaMalloc(&c->stage[i], total), "staging buffer")) return 1;
+        }
+        c->stage_bytes = total;
+    }
+    const unsigned slot = c->next_slot;
+    c->next_slot ^= 1u;
+//  The slot may still be draining from two snapshots ago.
+    if (check(cudaStreamWaitEvent(c->stream, c->drained[slot], 0), "wait drained")) return 1;
+    for (int i = 0; i < num_keys; i++) {
+        auto it = c->buffers.find(keys[i]);
+        if (it == c->buffers.end()) return fail("gfb_snapshot_async: unknown key");
+        if (it->second.bytes < bytes_each) return fail("gfb_snapshot_async: buffer smaller than bytes_each");
+        if (check(cudaMemcpyAsync(static_cast<char *> (c->stage[slot]) + bytes_each*i, it->second.dev, bytes_each,
+                                  cudaMemcpyDeviceToDevice, c->stream), "snapshot d2d")) return 1;
+    }
+    if (check(cudaEventRecord(c->staged[slot], c->stream), "record staged")) return 1;
+    if (check(cudaStreamWaitEvent(c->copy_stream, c->staged[slot], 0), "wait staged")) return 1;
+    if (check(cudaMemcpyAsync(host_destination, c->stage[slot], total, cudaMemcpyDeviceToHost, c->copy_stream), "snapshot d2h")) return 1;
+    return check(cudaEventRecord(c->drained[slot], c->copy_stream), "record drained");
 }
 
 int gfb_copy_h2d(gfb_ctx *c, uint64_t key, const void *source, size_t bytes) {

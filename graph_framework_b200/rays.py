@@ -99,6 +99,21 @@ class RayTracer:
             out["residual"] = res
         return out
 
+    def trace(self, num_blocks, sub_steps, out=None):
+        """The reference's output loop (xrays.cpp:246-259: sub_steps steps, then write_step):
+        returns an array [num_blocks, 9, num_rays] with rows t, w, x, y, z, kx, ky, kz, residual.
+        The copy of block b overlaps the stepping of block b + 1; `out` may be a preallocated
+        (pinned) array of that shape."""
+        if out is None:
+            try:
+                import torch
+                out = torch.empty((num_blocks, 9, self.n), dtype=torch.float64).pin_memory().numpy()
+            except Exception:       # torch is plumbing only; plain pageable memory works too
+                out = np.empty((num_blocks, 9, self.n), dtype=np.float64)
+        assert out.shape == (num_blocks, 9, self.n) and out.dtype == np.float64 and out.flags.c_contiguous
+        check(lib.gfb_rays_trace(self.h, int(num_blocks), int(sub_steps), out.ctypes.data_as(c_double_p)), "trace")
+        return out
+
     def rhs(self):
         """dx/dt, dy/dt, dz/dt, dkx/dt, dky/dt, dkz/dt, D at the current host state."""
         arrs = [np.empty(self.n, dtype=np.float64) for _ in range(7)]

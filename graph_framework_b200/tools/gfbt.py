@@ -69,3 +69,10 @@ def nc_to_gfbt(nc_path, out_path):
         arrays[name] = h.read(name)
     write_gfbt(out_path, arrays)
     return arrays
+
+
+def write_trajectory(path, records, names=("t", "w", "x", "y", "z", "kx", "ky", "kz", "residual")):
+    """Store RayTracer.trace output ([time, 9, rays]) with one (time, num_rays) variable per quantity,
+    the shape of the reference's result files (output.hpp:166: time-unlimited x num_rays)."""
+    records = np.asarray(records)
+    write_gfbt(path, {name: records[:, i, :] for i, name in enumerate(names)})

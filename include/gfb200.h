@@ -105,6 +105,14 @@ int gfb_host_ptr(gfb_ctx *ctx, uint64_t key, void **host_ptr);
 /* cuda_context::check_value  (cuda_context.hpp:613-617). */
 int gfb_check_value(gfb_ctx *ctx, uint64_t key, size_t index, double *value);
 
+/* Asynchronous snapshot of `num_keys` buffers to host memory (trajectory output; the reference's
+ * write_step, solver.hpp:418-424, hands the copy to a side thread).  Flushes pending steps, copies
+ * every buffer device->device into one of two staging slots on the compute stream, then moves
+ * the slot to `host_destination` (num_keys consecutive blocks of `bytes_each`; pinned memory
+ * recommended) on a second stream, so the next block of steps overlaps the transfer.
+ * gfb_wait() completes all outstanding snapshots. */
+int gfb_snapshot_async(gfb_ctx *ctx, const uint64_t *keys, int num_keys, size_t bytes_each, void *host_destination);
+
 /* Device timing on the context's stream (CUDA events). */
 int gfb_timer_start(gfb_ctx *ctx);
 int gfb_timer_stop(gfb_ctx *ctx, float *milliseconds);

@@ -55,6 +55,11 @@ int gfb_rays_wait(gfb_rays *r);
 int gfb_rays_get_state(gfb_rays *r, double *const state[GFB_NUM_STATE], double *residual);
 /* solver_interface::sync_device from caller memory  (solver.hpp:354-363). */
 int gfb_rays_put_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]);
+/* Trajectory output (solver_interface::write_step called every sub_steps, xrays.cpp:246-259):
+ * num_blocks times { sub_steps RK steps; snapshot of t, w, x, y, z, kx, ky, kz, residual }.
+ * `out` receives num_blocks records of 9 arrays of num_rays doubles ([block][9][ray]); the
+ * device->host transfer of block b overlaps the stepping of block b + 1.  Pinned memory recommended. */
+int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out);
 /* Device pointer of state array `which` (GFB_T..GFB_KZ) or of the residual (which = GFB_NUM_STATE). */
 int gfb_rays_device_ptr(gfb_rays *r, int which, void **device_ptr);
 /* The underlying device context (timers, launch counters, deposit, ...). */

@@ -270,3 +270,32 @@ def test_vmec_trajectory_properties(lib):
     for k in ("x", "y", "z", "kx", "ky", "kz"):
         scale = max(np.max(np.abs(b[k])), 1.0e-300)
         assert np.max(np.abs(a[k] - b[k]))/scale < 1.0e-6, k
+
+
+def test_trajectory_output_matches_blockwise_reads(lib, tmp_path):
+    """write_step analogue: overlapped snapshots equal stop-and-copy reads, and the file round-trips."""
+    from graph_framework_b200.rays import RayTracer
+    from graph_framework_b200.tools.gfbt import write_trajectory, read_gfbt
+    g = golden("ref_trace_extra_ordinary_wave_efit_rk4")
+    rec = g["long"]
+    start = unpack(rec[0][:8])
+    n = start["w"].size
+    tr = RayTracer("extra_ordinary_wave", "efit", n, float(g["dt"]))
+    tr.set_state(start)
+    tr.init("")
+    tr.compile()
+    out = tr.trace(4, 50)
+    tr.put_state(start)
+    for b in range(4):
+        tr.step(50)
+        st = tr.get_state()
+        for i, k in enumerate(ORDER + ("residual",)):
+            assert np.array_equal(out[b][i], st[k]), (b, k)
+    tr.close()
+    for block, ref_block in ((1, 1), (3, 2)):          # 100 and 200 steps vs the reference
+        for i, k in enumerate(ORDER):
+            assert rel_dev(out[block][i], rec[ref_block][i]) < 1.0e-9, (block, k)
+    path = str(tmp_path / "rays.gfbt")
+    write_trajectory(path, out)
+    back = read_gfbt(path)
+    assert back["x"].shape == (4, n) and np.array_equal(back["kz"], out[:, 7, :])
