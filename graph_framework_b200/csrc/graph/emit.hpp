@@ -45,7 +45,27 @@ namespace jit {
         bool staged;                    ///< copied to shared memory by TMA
         size_t smem_offset;             ///< byte offset in dynamic shared memory
         std::vector<double> packed;     ///< cells*stride doubles, cell major
+        bool raw = false;               ///< packed was filled by the emitter (Fourier tables), do not repack
         size_t bytes() const { return packed.size()*sizeof(double); }
+    };
+
+//------------------------------------------------------------------------------
+///  One device loop over Fourier modes: every graph::fourier_series node that shares the angles
+///  (u, v) and the mode numbers is a member; `sets` are the coefficient tables involved.
+//------------------------------------------------------------------------------
+    struct fourier_set {
+        graph::table_ptr table;
+        const graph::leaf_node *s;
+        double scale, offset;
+        size_t group;                                       ///< pointer slot of the coefficient buffer
+        std::vector<const graph::leaf_node *> members;
+    };
+    struct fourier_loop {
+        const graph::leaf_node *u, *v;
+        std::vector<double> xm, xn;
+        size_t mode_group;                                  ///< pointer slot of the [mode][2] table
+        std::vector<fourier_set> sets;
+        bool emitted = false;
     };
 
 //------------------------------------------------------------------------------
@@ -106,6 +126,8 @@ namespace jit {
         std::unordered_set<const graph::leaf_node *> visited;
         std::vector<std::string> index_reg;
         std::vector<std::vector<bool>> pair_loaded;
+        std::vector<fourier_loop> floops;
+        std::unordered_map<const graph::leaf_node *, size_t> floop_of;
 ///  Arguments that occur under both sin and cos in this kernel: one sincos() serves both.
         std::unordered_map<const graph::leaf_node *, std::pair<const graph::leaf_node *, const graph::leaf_node *>> trig;
 
@@ -130,6 +152,58 @@ namespace jit {
             if (n->op == graph::op_t::div) denominators[strip(n->args[1].get())]++;
             if (n->op == graph::op_t::sin) trig[strip(n->args[0].get())].first = n;
             if (n->op == graph::op_t::cos) trig[strip(n->args[0].get())].second = n;
+            if (n->op == graph::op_t::fourier) {
+                const graph::leaf_node *fs = strip(n->args[0].get());
+                const graph::leaf_node *fu = strip(n->args[1].get());
+                const graph::leaf_node *fv = strip(n->args[2].get());
+                size_t l = 0;
+                for (; l < floops.size(); l++)
+                    if (floops[l].u == fu && floops[l].v == fv && floops[l].xm == n->table->xm && floops[l].xn == n->table->xn) break;
+                if (l == floops.size()) {
+                    fourier_loop loop;
+                    loop.u = fu;
+                    loop.v = fv;
+                    loop.xm = n->table->xm;
+                    loop.xn = n->table->xn;
+                    table_group g;
+                    g.op = graph::op_t::fourier;
+                    g.num_cols = 0;
+                    g.cells = loop.xm.size();
+                    g.stride = 2;
+                    g.raw = true;
+                    for (size_t m = 0; m < loop.xm.size(); m++) {
+                        g.packed.push_back(loop.xm[m]);
+                        g.packed.push_back(loop.xn[m]);
+                    }
+                    loop.mode_group = info.groups.size();
+                    info.groups.push_back(g);
+                    floops.push_back(loop);
+                }
+                auto &sets = floops[l].sets;
+                size_t j = 0;
+                for (; j < sets.size(); j++)
+                    if (sets[j].table == n->table && sets[j].s == fs && sets[j].scale == n->scale[0] && sets[j].offset == n->offset[0]) break;
+                if (j == sets.size()) {
+                    fourier_set set;
+                    set.table = n->table;
+                    set.s = fs;
+                    set.scale = n->scale[0];
+                    set.offset = n->offset[0];
+                    table_group g;
+                    g.op = graph::op_t::fourier;
+                    g.num_cols = 0;
+                    g.cells = n->table->cells;
+                    g.stride = 4;
+                    g.raw = true;
+                    g.packed.assign(n->table->values.begin(),
+                                    n->table->values.begin() + n->table->xm.size()*n->table->cells*4);
+                    set.group = info.groups.size();
+                    info.groups.push_back(g);
+                    sets.push_back(set);
+                }
+                sets[j].members.push_back(n);
+                floop_of[n] = l;
+            }
             if (n->is_piecewise()) {
                 const graph::leaf_node *a0 = strip(n->args[0].get());
                 const graph::leaf_node *a1 = n->args[1].get() ? strip(n->args[1].get()) : nullptr;
@@ -164,6 +238,20 @@ namespace jit {
             size_t staged_total = 0;
             size_t offset = 16;     // mbarrier lives in the first 16 bytes
             for (auto &g : info.groups) {
+                if (g.raw) {
+//  Fourier tables keep their layout; the small [mode][2] mode-number table is staged.
+                    if (g.packed.size() & 1) g.packed.push_back(0.0);
+                    g.staged = opt.stage_tables && g.stride == 2 && g.bytes() <= opt.stage_limit_bytes &&
+                               staged_total + g.bytes() <= opt.stage_total_bytes;
+                    if (g.staged) {
+                        g.smem_offset = offset;
+                        offset += (g.bytes() + 127)/128*128;
+                        staged_total += g.bytes();
+                    } else {
+                        g.smem_offset = 0;
+                    }
+                    continue;
+                }
                 const size_t k = g.members.size();
                 const size_t bytes_even = g.cells*(k + (k & 1))*sizeof(double);
                 g.staged = opt.stage_tables && bytes_even <= opt.stage_limit_bytes &&
@@ -195,6 +283,89 @@ namespace jit {
             return "static_cast<unsigned> (fmin(fmax(" + u + ", 0.0), " + literal(static_cast<double> (n - 1)) + "))";
         }
 
+        std::string group_pointer(const size_t g) {
+            auto &grp = info.groups[g];
+            if (grp.staged) return "reinterpret_cast<const double *> (gfb::smem + " + std::to_string(grp.smem_offset) + ")";
+            return "tg[" + std::to_string(g) + "]";
+        }
+
+//  One loop over the modes computes every member of the loop group (see graph::fourier_series).
+        void emit_fourier_loop(fourier_loop &loop) {
+            if (loop.emitted) return;
+            loop.emitted = true;
+            using graph::fourier_order;
+            const std::string ureg = emit(loop.u), vreg = emit(loop.v);
+            std::vector<std::string> sreg;
+            for (auto &set : loop.sets) sreg.push_back(emit(set.s));
+            const size_t id = loop.mode_group;
+            for (auto &set : loop.sets) {
+                for (auto *m : set.members) {
+                    if (reg.count(m)) continue;
+                    const std::string name = "t" + std::to_string(m->id);
+                    out << "        double " << name << " = 0.0;" << std::endl;
+                    reg.emplace(m, name);
+                }
+            }
+            out << "        {" << std::endl
+                << "            const double *mn" << id << " = " << group_pointer(loop.mode_group) << ";" << std::endl;
+            for (size_t j = 0; j < loop.sets.size(); j++) {
+                auto &set = loop.sets[j];
+                out << "            const double *fc" << id << "_" << j << " = tg[" << set.group << "] + ("
+                    << index_expr(sreg[j], set.scale, set.offset, set.table->cells) << ")*4u;" << std::endl;
+            }
+//  Which polynomial orders, and which (b, c, trig phase) weights are needed.
+            std::set<std::pair<size_t, unsigned>> polys;
+            std::set<std::array<unsigned, 3>> weights;
+            for (size_t j = 0; j < loop.sets.size(); j++) {
+                for (auto *m : loop.sets[j].members) {
+                    const fourier_order o = fourier_order::unpack(m->num_cols);
+                    polys.insert({j, o.a});
+                    weights.insert({o.b, o.c, (o.b + o.c + (o.base ? 3u : 0u)) & 3u});
+                }
+            }
+            out << "#pragma unroll 2" << std::endl
+                << "            for (int m = 0; m < " << loop.xm.size() << "; m++) {" << std::endl
+                << "                const double xm = mn" << id << "[2*m], xn = mn" << id << "[2*m + 1];" << std::endl
+                << "                double sn, cs;" << std::endl
+                << "                sincos(xm*" << ureg << " - xn*" << vreg << ", &sn, &cs);" << std::endl;
+            for (size_t j = 0; j < loop.sets.size(); j++) {
+                const std::string c = "c" + std::to_string(j);
+                const std::string &x = sreg[j];
+                out << "                const double2 " << c << "lo = __ldg(reinterpret_cast<const double2 *> (fc" << id << "_" << j
+                    << " + m*" << loop.sets[j].table->cells*4 << ")), " << c << "hi = __ldg(reinterpret_cast<const double2 *> (fc"
+                    << id << "_" << j << " + m*" << loop.sets[j].table->cells*4 << ") + 1);" << std::endl;
+                for (auto &[jj, a] : polys) {
+                    if (jj != j) continue;
+                    out << "                const double p" << j << "_" << a << " = ";
+                    switch (a) {
+                        case 0: out << "fma(fma(fma(" << c << "hi.y, " << x << ", " << c << "hi.x), " << x << ", " << c << "lo.y), " << x << ", " << c << "lo.x)"; break;
+                        case 1: out << "fma(fma(3.0*" << c << "hi.y, " << x << ", 2.0*" << c << "hi.x), " << x << ", " << c << "lo.y)"; break;
+                        case 2: out << "fma(6.0*" << c << "hi.y, " << x << ", 2.0*" << c << "hi.x)"; break;
+                        default: out << "6.0*" << c << "hi.y"; break;
+                    }
+                    out << ";" << std::endl;
+                }
+            }
+            for (auto &w : weights) {
+                out << "                const double w" << w[0] << "_" << w[1] << "_" << w[2] << " = ";
+                std::string f;
+                for (unsigned i = 0; i < w[0]; i++) f += "xm*";
+                for (unsigned i = 0; i < w[1]; i++) f += "(-xn)*";
+                static const char *trig[4] = {"cs", "(-sn)", "(-cs)", "sn"};
+                out << f << trig[w[2]] << ";" << std::endl;
+            }
+            for (size_t j = 0; j < loop.sets.size(); j++) {
+                for (auto *m : loop.sets[j].members) {
+                    const fourier_order o = fourier_order::unpack(m->num_cols);
+                    const unsigned k = (o.b + o.c + (o.base ? 3u : 0u)) & 3u;
+                    out << "                " << reg.at(m) << " = fma(p" << j << "_" << o.a << ", w" << o.b << "_" << o.c << "_" << k
+                        << ", " << reg.at(m) << ");" << std::endl;
+                    info.num_statements++;
+                }
+            }
+            out << "            }" << std::endl << "        }" << std::endl;
+        }
+
         const std::string &emit(const graph::leaf_node *n) {
             n = strip(n);
             auto found = reg.find(n);
@@ -208,6 +379,10 @@ namespace jit {
                 for (size_t i = 0; i < info.inputs.size(); i++)
                     if (info.inputs[i].get() == n)
                         return reg.emplace(n, "v[" + std::to_string(i) + "]").first->second;
+            }
+            if (n->op == op_t::fourier) {
+                emit_fourier_loop(floops[floop_of.at(n)]);
+                return reg.at(n);
             }
             if (n->is_piecewise()) {
                 const auto [g, m] = slot.at(n);

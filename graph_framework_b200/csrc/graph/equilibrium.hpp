@@ -361,6 +361,7 @@ namespace equilibrium {
         };
     private:
         const tables tab;
+        graph::table_ptr rmnc_table, zmns_table, lmns_table;
         leaf_ptr s_cache, u_cache, v_cache, x_cache, y_cache, z_cache;
         vector_ptr esups_cache, esupu_cache, esupv_cache, bvec_cache;
 
@@ -395,15 +396,24 @@ namespace equilibrium {
             auto s_norm_f = (s - tab.sminf)/tab.ds;
             auto zero = graph::zero();
             leaf_ptr r = zero, z = zero, l = zero;
-            for (size_t i = 0, ie = tab.xm.size(); i < ie; i++) {
-                auto rmnc = spline(tab.rmnc, i, s, tab.sminf);
-                auto zmns = spline(tab.zmns, i, s, tab.sminf);
-                auto lmns = spline(tab.lmns, i, s, tab.sminh);
-                auto angle = graph::constant(tab.xm[i])*u - graph::constant(tab.xn[i])*v;
-                auto sinmn = graph::sin(angle);
-                r = r + rmnc*graph::cos(angle);
-                z = z + zmns*sinmn;
-                l = l + lmns*sinmn;
+            if (use_mode_loop()) {
+//  R, Z, lambda as Fourier-series nodes: their derivatives stay in the family and the emitter
+//  evaluates all of them in one device loop over the 86 modes (graph::fourier_series).
+                r = graph::fourier_series(rmnc_table, s, u, v, tab.ds, tab.sminf, {0, 0, 0, 0});
+                z = graph::fourier_series(zmns_table, s, u, v, tab.ds, tab.sminf, {0, 0, 0, 1});
+                l = graph::fourier_series(lmns_table, s, u, v, tab.ds, tab.sminh, {0, 0, 0, 1});
+            } else {
+//  The reference's construction: every mode unrolled in the graph (equilibrium.hpp:2120-2151).
+                for (size_t i = 0, ie = tab.xm.size(); i < ie; i++) {
+                    auto rmnc = spline(tab.rmnc, i, s, tab.sminf);
+                    auto zmns = spline(tab.zmns, i, s, tab.sminf);
+                    auto lmns = spline(tab.lmns, i, s, tab.sminh);
+                    auto angle = graph::constant(tab.xm[i])*u - graph::constant(tab.xn[i])*v;
+                    auto sinmn = graph::sin(angle);
+                    r = r + rmnc*graph::cos(angle);
+                    z = z + zmns*sinmn;
+                    l = l + lmns*sinmn;
+                }
             }
             x_cache = r*graph::cos(v);
             y_cache = r*graph::sin(v);
@@ -427,6 +437,15 @@ namespace equilibrium {
     public:
         vmec(const tables &t) : generic<T, SAFE_MATH> ({deuterium_mass}, {1}), tab(t) {
             s_cache = u_cache = v_cache = graph::zero();
+            rmnc_table = graph::fourier_table(tab.rmnc, tab.xm, tab.xn, tab.ds, tab.sminf);
+            zmns_table = graph::fourier_table(tab.zmns, tab.xm, tab.xn, tab.ds, tab.sminf);
+            lmns_table = graph::fourier_table(tab.lmns, tab.xm, tab.xn, tab.ds, tab.sminh);
+        }
+///  true (default): Fourier sums are device loops; false: the reference's fully unrolled graph
+///  (kept for cross-checks; 9 k statements per right-hand side).
+        static bool &use_mode_loop() {
+            static thread_local bool on = std::getenv("GFB_VMEC_UNROLLED") == nullptr;
+            return on;
         }
         virtual vector_ptr get_esup1(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return esups_cache; }
         virtual vector_ptr get_esup2(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return esupu_cache; }

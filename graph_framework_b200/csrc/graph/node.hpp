@@ -86,7 +86,8 @@ namespace graph {
         add, sub, mul, div, fma,
         sqrt, exp, log, pow,
         sin, cos, atan,
-        piecewise_1d, piecewise_2d
+        piecewise_1d, piecewise_2d,
+        fourier
     };
 
     class leaf_node;
@@ -118,6 +119,10 @@ namespace graph {
     struct table_data {
         std::vector<double> values;
         uint64_t hash;
+///  Fourier-series tables only (op_t::fourier): values = folded cubic coefficients
+///  [mode][cell][4], xm/xn = poloidal/toroidal mode numbers.
+        std::vector<double> xm, xn;
+        size_t cells = 0;
     };
     using table_ptr = std::shared_ptr<const table_data>;
 
@@ -153,7 +158,7 @@ namespace graph {
                 case op_t::constant: case op_t::variable: return 0;
                 case op_t::pseudo: case op_t::sqrt: case op_t::exp: case op_t::log:
                 case op_t::sin: case op_t::cos: case op_t::piecewise_1d: return 1;
-                case op_t::fma: return 3;
+                case op_t::fma: case op_t::fourier: return 3;
                 default: return 2;
             }
         }
@@ -587,6 +592,91 @@ namespace graph {
     }
 
 //------------------------------------------------------------------------------
+///  Fourier series with radial spline amplitudes -- the building block of the VMEC equilibrium
+///  (equilibrium.hpp:2120-2151 sums 86 modes of  spline_mn(s) * {cos, sin}(m u - n v)).
+///
+///      F[a, b, c](s, u, v) = sum_mn  d^a P_mn/ds^a (s) * d^(b+c)/du^b dv^c  trig(m u - n v)
+///
+///  P_mn is the cell's cubic in the physical s (coefficients folded like build_1D_spline,
+///  equilibrium.hpp:1121-1133; constant within a cell, so their derivative is zero like a
+///  piecewise node's).  The family is closed under differentiation, so df() and gradient() stay
+///  inside it, and the emitter evaluates every member that shares (u, v, mode numbers) in ONE
+///  device loop over the modes instead of unrolling ~10^4 statements.
+///  num_cols packs (a, b, c, base): base 0 = cos series, 1 = sin series.
+//------------------------------------------------------------------------------
+    inline size_t table_index(const double x, const double scale, const double offset, const size_t n);
+    struct fourier_order {
+        unsigned a, b, c, base;
+        size_t pack() const { return a | (b << 8) | (c << 16) | (base << 24); }
+        static fourier_order unpack(const size_t p) {
+            return {static_cast<unsigned> (p & 255), static_cast<unsigned> ((p >> 8) & 255),
+                    static_cast<unsigned> ((p >> 16) & 255), static_cast<unsigned> ((p >> 24) & 255)};
+        }
+    };
+
+///  Intern a coefficient set.  c[k][mode][cell] are the reference's raw spline tables c0..c3;
+///  they are folded to physical-s coefficients here, in build_1D_spline's operation order.
+    inline table_ptr fourier_table(const std::array<std::vector<std::vector<double>>, 4> &c,
+                                   const std::vector<double> &xm, const std::vector<double> &xn,
+                                   const double scale, const double offset) {
+        const size_t modes = xm.size(), cells = c[0].at(0).size();
+        std::vector<double> v(modes*cells*4);
+        const double s2 = scale*scale, s3 = scale*scale*scale;
+        for (size_t m = 0; m < modes; m++) {
+            for (size_t i = 0; i < cells; i++) {
+                const double c0 = c[0][m][i], c1 = c[1][m][i], c2 = c[2][m][i], c3 = c[3][m][i];
+                double *o = &v[(m*cells + i)*4];
+                o[3] = c3/s3;
+                o[2] = c2/s2 - (3.0*offset)*c3/s3;
+                o[1] = c1/scale - (2.0*offset)*c2/s2 + (3.0*offset*offset)*c3/s3;
+                o[0] = c0 - offset*c1/scale + (offset*offset)*c2/s2 - (offset*offset*offset)*c3/s3;
+            }
+        }
+        for (const double e : xm) v.push_back(e);      // mode numbers take part in the content hash
+        for (const double e : xn) v.push_back(e);
+        auto base = detail::intern_table(v);
+        if (base->cells == 0) {
+            auto t = std::const_pointer_cast<table_data> (base);
+            t->xm = xm;
+            t->xn = xn;
+            t->cells = cells;
+        }
+        return base;
+    }
+
+    inline leaf_ptr fourier_series(table_ptr table, leaf_ptr s, leaf_ptr u, leaf_ptr v,
+                                   const double scale, const double offset, const fourier_order order) {
+        if (order.a > 3) return zero();
+        return detail::intern(op_t::fourier, s, u, v, 0.0, table, order.pack(), {scale, 0.0}, {offset, 0.0});
+    }
+
+///  Host value of one member (also the oracle of the device loop in tests).
+    inline double fourier_value(const table_data &t, const fourier_order o, const double scale, const double offset,
+                                const double s, const double u, const double v) {
+        const size_t modes = t.xm.size();
+        const size_t cell = table_index(s, scale, offset, t.cells);
+        double sum = 0.0;
+        for (size_t m = 0; m < modes; m++) {
+            const double *c = &t.values[(m*t.cells + cell)*4];
+            double p;
+            switch (o.a) {
+                case 0: p = std::fma(std::fma(std::fma(c[3], s, c[2]), s, c[1]), s, c[0]); break;
+                case 1: p = std::fma(std::fma(3.0*c[3], s, 2.0*c[2]), s, c[1]); break;
+                case 2: p = std::fma(6.0*c[3], s, 2.0*c[2]); break;
+                default: p = 6.0*c[3]; break;
+            }
+            const double angle = t.xm[m]*u - t.xn[m]*v;
+            const unsigned k = (o.b + o.c + (o.base ? 3u : 0u)) & 3u;      // cos, -sin, -cos, sin; sin = cos shifted by 3
+            const double trig = k == 0 ? std::cos(angle) : k == 1 ? -std::sin(angle) : k == 2 ? -std::cos(angle) : std::sin(angle);
+            double factor = 1.0;
+            for (unsigned i = 0; i < o.b; i++) factor *= t.xm[m];
+            for (unsigned i = 0; i < o.c; i++) factor *= -t.xn[m];
+            sum += p*factor*trig;
+        }
+        return sum;
+    }
+
+//------------------------------------------------------------------------------
 //  Operators (double operands become constants).
 //------------------------------------------------------------------------------
     inline leaf_ptr operator+(leaf_ptr l, leaf_ptr r) { return add(l, r); }
@@ -669,6 +759,18 @@ namespace graph {
                     un([&] (double a) { return t[table_index(a, n->scale[0], n->offset[0], t.size())]; });
                     break;
                 }
+                case op_t::fourier: {
+                    const auto &a = eval(n->args[0].get(), memo);
+                    const auto &b = eval(n->args[1].get(), memo);
+                    const auto &c = eval(n->args[2].get(), memo);
+                    const size_t sz = std::max(a.size(), std::max(b.size(), c.size()));
+                    out.resize(sz);
+                    const fourier_order o = fourier_order::unpack(n->num_cols);
+                    for (size_t i = 0; i < sz; i++)
+                        out[i] = fourier_value(*n->table, o, n->scale[0], n->offset[0], a[a.size() == 1 ? 0 : i],
+                                               b[b.size() == 1 ? 0 : i], c[c.size() == 1 ? 0 : i]);
+                    break;
+                }
                 case op_t::piecewise_2d: {
                     const auto &t = n->table->values;
                     const size_t rows = t.size()/n->num_cols;
@@ -731,6 +833,13 @@ namespace graph {
                 r = div(sub(mul(a, b->df(x)), mul(b, a->df(x))), add(mul(a, a), mul(b, b)));
                 break;
             }
+            case op_t::fourier: {
+                const fourier_order o = fourier_order::unpack(num_cols);
+                r = add(add(mul(fourier_series(table, a, b, args[2], scale[0], offset[0], {o.a + 1, o.b, o.c, o.base}), a->df(x)),
+                            mul(fourier_series(table, a, b, args[2], scale[0], offset[0], {o.a, o.b + 1, o.c, o.base}), b->df(x))),
+                        mul(fourier_series(table, a, b, args[2], scale[0], offset[0], {o.a, o.b, o.c + 1, o.base}), args[2]->df(x)));
+                break;
+            }
             default: r = zero(); break;
         }
         memo.emplace(k, r);
@@ -758,6 +867,8 @@ namespace graph {
             case op_t::pseudo: return pseudo_variable(a);
             case op_t::piecewise_1d: case op_t::piecewise_2d:
                 return detail::intern(n->op, a, b, nullptr, 0.0, n->table, n->num_cols, n->scale, n->offset);
+            case op_t::fourier:
+                return detail::intern(n->op, a, b, c, 0.0, n->table, n->num_cols, n->scale, n->offset);
             default: return std::const_pointer_cast<leaf_node> (n->shared_from_this());
         }
     }
@@ -863,6 +974,14 @@ namespace graph {
                     accumulate(y, mul(q, x));
                     break;
                 }
+                case op_t::fourier: {
+                    const fourier_order o = fourier_order::unpack(n->num_cols);
+                    const leaf_ptr &v = n->args[2];
+                    accumulate(x, mul(a, fourier_series(n->table, x, y, v, n->scale[0], n->offset[0], {o.a + 1, o.b, o.c, o.base})));
+                    accumulate(y, mul(a, fourier_series(n->table, x, y, v, n->scale[0], n->offset[0], {o.a, o.b + 1, o.c, o.base})));
+                    accumulate(v, mul(a, fourier_series(n->table, x, y, v, n->scale[0], n->offset[0], {o.a, o.b, o.c + 1, o.base})));
+                    break;
+                }
                 default: break;
             }
         }
@@ -883,7 +1002,7 @@ namespace graph {
 
     inline std::string leaf_node::to_string() {
         static const char *names[] = {"const", "var", "pseudo", "+", "-", "*", "/", "fma", "sqrt", "exp", "log",
-                                      "pow", "sin", "cos", "atan", "pw1d", "pw2d"};
+                                      "pow", "sin", "cos", "atan", "pw1d", "pw2d", "fourier"};
         std::ostringstream s;
         s.precision(17);
         if (op == op_t::constant) { s << value; return s.str(); }
