@@ -39,7 +39,14 @@ WORKLOADS = {
     "efit_cold": ("cold_plasma", "efit", 1000000, 2.0e-5),              # north-star roofline kernel
     "efit_omode": ("ordinary_wave", "efit", 1000000, 2.0e-5),
     "slab_omode": ("ordinary_wave", "slab_density", 1000000, 1.0e-3),   # analytic variant of configs[0]
+    "vmec_omode": ("ordinary_wave", "vmec", 1250000, 1.0e-4),           # configs[3]: 10^7 rays / 8 GPUs
+    "vmec_cold": ("cold_plasma", "vmec", 1250000, 1.0e-4),
 }
+
+
+def generator(eq):
+    from graph_framework_b200 import workloads
+    return {"efit": workloads.efit_ensemble, "vmec": workloads.vmec_states}.get(eq, workloads.slab_ensemble)
 
 
 def nproc():
@@ -116,7 +123,7 @@ def reference_arm(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built"}))
         return 0
     rays = args.ref_rays
-    state = workloads.efit_ensemble(rays, seed=0) if eq == "efit" else workloads.slab_ensemble(rays, seed=0)
+    state = generator(eq)(rays, seed=0)
     times = []
     last = None
     for i in range(args.warmup + args.steps):
@@ -241,7 +248,7 @@ def main():
 
     disp, eq, default_rays, dt = WORKLOADS[args.workload]
     rays = args.rays or default_rays                      # per GPU: weak scaling
-    gen = workloads.efit_ensemble if eq == "efit" else workloads.slab_ensemble
+    gen = generator(eq)
     state0 = gen(rays, seed=rank)
 
     t_setup = time.perf_counter()

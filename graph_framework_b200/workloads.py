@@ -15,6 +15,7 @@ FLOP_PER_RAY_STEP = {
     ("cold_plasma", "slab"): 856.0,
     ("cold_plasma", "slab_density"): 612.0,
     ("ordinary_wave", "slab_density"): 96.0,
+    ("cold_plasma", "vmec"): 63165.0,
 }
 FLOP_PER_PARTICLE_STEP_BORIS = 216.0
 #  HBM bytes per ray-step when state makes one round trip per launch of S fused steps.
