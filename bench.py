@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
     ap.add_argument("--ref-rays", type=int, default=20000, help="rays of the bounded CPU sample")
     ap.add_argument("--options", default="", help="emit/launch options passed to gfb_rays_create")
+    ap.add_argument("--chunks", type=int, default=8, help="pieces of the ensemble pipelined by the e2e call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -301,17 +302,15 @@ def main():
     host_np = {k: host_in[k].numpy() for k in STATE}
     e2e_steps = max(2, min(args.steps, 10))
     for _ in range(2):
-        tracer.put_state(host_np)
-        tracer.step(SUB_STEPS)
-        out = tracer.get_state(out=host_out)
+        out = tracer.step_host(SUB_STEPS, host_np, host_out, chunks=args.chunks)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        tracer.put_state(host_np)                          # H2D: 8 arrays from pinned memory
-        tracer.step(SUB_STEPS)
-        out = tracer.get_state(out=host_out)               # D2H: 8 arrays + residual into pinned memory
+        # one public-API call: H2D of the 8 state arrays from pinned memory, SUB_STEPS fused steps,
+        # D2H of the 8 arrays + residual into pinned memory; pieces of the ensemble are pipelined
+        out = tracer.step_host(SUB_STEPS, host_np, host_out, chunks=args.chunks)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist:
@@ -358,7 +357,8 @@ def main():
                                  "achieved_gbs": hbm_bytes/(per_launch_ms*1.0e-3)/1.0e9,
                                  "peak_gbs": peaks.get("hbm_gbs")}},
             "e2e": {"value": e2e_value, "unit": "ray-steps/s", "h2d_bytes_per_step": 8*8*rays,
-                    "d2h_bytes_per_step": 9*8*rays, "steps": e2e_steps, "finite": finite},
+                    "d2h_bytes_per_step": 9*8*rays, "steps": e2e_steps, "finite": finite,
+                    "api": "RayTracer.step_host (gfb_rays_step_host): upload, %d fused steps, read-back; %d pipelined chunks" % (SUB_STEPS, args.chunks)},
             "gpu_launches": launches,
             "kernel": dict(stats, block=128, min_blocks_per_sm=int(_lib.lib.gfb_compiled_min_blocks(tracer.ctx))),
             "clocks": clocks,

@@ -43,6 +43,7 @@ def _load():
         "gfb_kernel_create": (I, [P, S, ctypes.POINTER(U64), I, SZ, U, SZ, I, I, c_void_pp]),
         "gfb_kernel_run": (I, [P]),
         "gfb_kernel_launch": (I, [P, U]),
+        "gfb_kernel_run_from_host": (I, [P, U, I, c_void_pp, c_void_pp, I]),
         "gfb_kernel_set_scalar": (I, [P, I, D]),
         "gfb_kernel_attributes": (I, [P, ctypes.POINTER(I), ctypes.POINTER(I), ctypes.POINTER(I), ctypes.POINTER(I)]),
         "gfb_launch_count": (U64, [P]),
@@ -71,6 +72,7 @@ def _load():
         "gfb_rays_wait": (I, [P]),
         "gfb_rays_get_state": (I, [P, ctypes.POINTER(c_double_p), c_double_p]),
         "gfb_rays_put_state": (I, [P, ctypes.POINTER(c_double_p)]),
+        "gfb_rays_step_host": (I, [P, SZ, ctypes.POINTER(c_double_p), ctypes.POINTER(c_double_p), c_double_p, I]),
         "gfb_rays_trace": (I, [P, SZ, SZ, c_double_p]),
         "gfb_rays_device_ptr": (I, [P, I, c_void_pp]),
         "gfb_rays_ctx": (P, [P]),

@@ -392,6 +392,21 @@ int gfb_rays_put_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]) {
     }
     return 0;
 }
+int gfb_rays_step_host(gfb_rays *r, size_t num_steps, const double *const state_in[GFB_NUM_STATE],
+                       double *const state_out[GFB_NUM_STATE], double *residual_out, int chunks) {
+    if (!r->compiled) return rays_fail("step_host before compile");
+//  Pointer slots of solver_kernel: the 8 inputs in solver order (= GFB_T..GFB_KZ), then the residual.
+    const void *src[GFB_NUM_STATE + 1];
+    void *dst[GFB_NUM_STATE + 1];
+    for (int i = 0; i < GFB_NUM_STATE; i++) {
+        src[i] = state_in ? state_in[i] : nullptr;
+        dst[i] = state_out ? state_out[i] : nullptr;
+    }
+    src[GFB_NUM_STATE] = nullptr;
+    dst[GFB_NUM_STATE] = residual_out;
+    gfb_kernel *k = r->impl->context().get_kernel("solver_kernel", r->n);
+    return gfb_kernel_run_from_host(k, static_cast<unsigned> (num_steps), GFB_NUM_STATE + 1, src, dst, chunks);
+}
 int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out) {
     if (!r->compiled) return rays_fail("trace before compile");
     std::vector<uint64_t> keys;

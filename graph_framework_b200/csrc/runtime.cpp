@@ -213,6 +213,7 @@ struct gfb_ctx {
     cudaEvent_t staged[2] = {nullptr, nullptr};     // slot filled (compute stream)
     cudaEvent_t drained[2] = {nullptr, nullptr};    // slot copied out (copy stream)
     unsigned next_slot = 0;
+    cudaStream_t upload_stream = nullptr;
 };
 
 namespace {
@@ -294,6 +295,10 @@ void gfb_ctx_destroy(gfb_ctx *c) {
     if (c->scratch) cudaFree(c->scratch);
     if (c->scratch_host) cudaFreeHost(c->scratch_host);
     if (c->flush_buffer) cudaFree(c->flush_buffer);
+    if (c->upload_stream) {
+        cudaStreamSynchronize(c->upload_stream);
+        cudaStreamDestroy(c->upload_stream);
+    }
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamDestroy(c->copy_stream);
@@ -499,6 +504,74 @@ int gfb_kernel_run(gfb_kernel *k) {
 int gfb_kernel_launch(gfb_kernel *k, unsigned steps) {
     if (flush(k->ctx)) return 1;
     return launch_now(k, steps);
+}
+
+int gfb_kernel_run_from_host(gfb_kernel *k, unsigned steps, int num_ray_slots,
+                             const void *const *host_src, void *const *host_dst, int chunks) {
+    gfb_ctx *c = k->ctx;
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    if (num_ray_slots > max_ptrs) return fail("gfb_kernel_run_from_host: too many slots");
+    if (!c->copy_stream) {
+        if (check(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "copy stream")) return 1;
+        for (int i = 0; i < 2; i++) {
+            cudaEventCreateWithFlags(&c->staged[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->drained[i], cudaEventDisableTiming);
+        }
+    }
+    if (!c->upload_stream) {
+        if (check(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking), "upload stream")) return 1;
+    }
+    const unsigned long long total = k->args.n;
+    if (chunks < 1) chunks = 1;
+//  Chunk boundaries on block multiples so every piece but the last fills whole blocks.
+    unsigned long long per = (total + chunks - 1)/chunks;
+    per = (per + k->block - 1)/k->block*k->block;
+    std::vector<cudaEvent_t> uploaded, computed;
+    int rc = 0;
+    for (unsigned long long off = 0; off < total && !rc; off += per) {
+        const unsigned long long cnt = total - off < per ? total - off : per;
+        cudaEvent_t up, done;
+        cudaEventCreateWithFlags(&up, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+        uploaded.push_back(up);
+        computed.push_back(done);
+        for (int s = 0; s < num_ray_slots && !rc; s++) {
+            if (host_src && host_src[s]) {
+                rc = check(cudaMemcpyAsync(static_cast<char *> (k->args.ptr[s]) + off*sizeof(double),
+                                           static_cast<const char *> (host_src[s]) + off*sizeof(double),
+                                           cnt*sizeof(double), cudaMemcpyHostToDevice, c->upload_stream), "chunk h2d");
+            }
+        }
+        if (rc) break;
+        cudaEventRecord(up, c->upload_stream);
+        cudaStreamWaitEvent(c->stream, up, 0);
+        device_args piece = k->args;
+        for (int s = 0; s < num_ray_slots; s++) piece.ptr[s] = static_cast<char *> (k->args.ptr[s]) + off*sizeof(double);
+        piece.n = cnt;
+        piece.steps = k->can_repeat ? steps : (steps ? 1u : 0u);
+        void *params[] = {&piece};
+        c->launches++;
+        rc = check_cu(driver.LaunchKernel(k->function, static_cast<unsigned> ((cnt + k->block - 1)/k->block), 1, 1, k->block, 1, 1,
+                                          static_cast<unsigned> (k->smem), reinterpret_cast<CUstream> (c->stream), params, nullptr),
+                      k->name.c_str());
+        if (rc) break;
+        cudaEventRecord(done, c->stream);
+        cudaStreamWaitEvent(c->copy_stream, done, 0);
+        for (int s = 0; s < num_ray_slots && !rc; s++) {
+            if (host_dst && host_dst[s]) {
+                rc = check(cudaMemcpyAsync(static_cast<char *> (host_dst[s]) + off*sizeof(double),
+                                           static_cast<const char *> (k->args.ptr[s]) + off*sizeof(double),
+                                           cnt*sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream), "chunk d2h");
+            }
+        }
+    }
+    const int sync_rc = check(cudaStreamSynchronize(c->copy_stream), "pipeline sync") |
+                        check(cudaStreamSynchronize(c->stream), "pipeline sync") |
+                        check(cudaStreamSynchronize(c->upload_stream), "pipeline sync");
+    for (auto e : uploaded) cudaEventDestroy(e);
+    for (auto e : computed) cudaEventDestroy(e);
+    return rc | sync_rc;
 }
 
 int gfb_kernel_set_scalar(gfb_kernel *k, int index, double value) {

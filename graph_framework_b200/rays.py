@@ -99,6 +99,18 @@ class RayTracer:
             out["residual"] = res
         return out
 
+    def step_host(self, num_steps, state_in, state_out, chunks=8):
+        """sync_device, num_steps steps and sync_host as one pipelined call (solver.hpp:354-384):
+        upload, stepping and read-back of `chunks` pieces of the ensemble overlap.  state_in: dict
+        of host arrays (pinned for full speed); state_out: dict of preallocated arrays, may
+        include 'residual'."""
+        ins = [state_in.get(k) for k in STATE]
+        outs = [state_out.get(k) for k in STATE]
+        res = state_out.get("residual")
+        check(lib.gfb_rays_step_host(self.h, int(num_steps), _ptr_array(ins, 8), _ptr_array(outs, 8),
+                                     res.ctypes.data_as(c_double_p) if res is not None else None, int(chunks)), "step_host")
+        return state_out
+
     def trace(self, num_blocks, sub_steps, out=None):
         """The reference's output loop (xrays.cpp:246-259: sub_steps steps, then write_step):
         returns an array [num_blocks, 9, num_rays] with rows t, w, x, y, z, kx, ky, kz, residual.

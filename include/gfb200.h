@@ -81,6 +81,15 @@ int gfb_kernel_create(gfb_ctx *ctx, const char *name, const uint64_t *ptr_keys, 
 int gfb_kernel_run(gfb_kernel *kernel);
 /* Immediate launch of `steps` fused steps (flushes anything pending first). */
 int gfb_kernel_launch(gfb_kernel *kernel, unsigned steps);
+/* Host-to-host pipelined run: the rays are cut into `chunks` contiguous pieces; for each piece the
+ * per-ray pointer slots that have a host source are uploaded, `steps` fused steps run on that
+ * piece, and the slots that have a host destination are read back -- upload, compute and
+ * read-back of different pieces overlap on three streams (two copy engines + SMs).
+ * host_src / host_dst: one pointer per per-ray slot (the first num_ray_slots pointer slots of the
+ * kernel: inputs then outputs), NULL = no transfer for that slot.  Pinned memory recommended.
+ * Returns after everything has completed. */
+int gfb_kernel_run_from_host(gfb_kernel *kernel, unsigned steps, int num_ray_slots,
+                             const void *const *host_src, void *const *host_dst, int chunks);
 /* Set scalar[index] passed to the kernel (Newton tolerance, ...). */
 int gfb_kernel_set_scalar(gfb_kernel *kernel, int index, double value);
 /* registers/thread, static smem, local (spill) bytes/thread, max threads/block. */

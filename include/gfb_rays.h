@@ -55,6 +55,12 @@ int gfb_rays_wait(gfb_rays *r);
 int gfb_rays_get_state(gfb_rays *r, double *const state[GFB_NUM_STATE], double *residual);
 /* solver_interface::sync_device from caller memory  (solver.hpp:354-363). */
 int gfb_rays_put_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]);
+/* sync_device + num_steps x step + sync_host as ONE pipelined call from and to host memory
+ * (solver.hpp:354-384): the ensemble is cut into `chunks` pieces whose upload, stepping and
+ * read-back overlap.  state_in / state_out: GFB_NUM_STATE host arrays (NULL entries are skipped);
+ * residual_out may be NULL.  Pinned memory recommended. */
+int gfb_rays_step_host(gfb_rays *r, size_t num_steps, const double *const state_in[GFB_NUM_STATE],
+                       double *const state_out[GFB_NUM_STATE], double *residual_out, int chunks);
 /* Trajectory output (solver_interface::write_step called every sub_steps, xrays.cpp:246-259):
  * num_blocks times { sub_steps RK steps; snapshot of t, w, x, y, z, kx, ky, kz, residual }.
  * `out` receives num_blocks records of 9 arrays of num_rays doubles ([block][9][ray]); the

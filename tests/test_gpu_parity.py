@@ -299,3 +299,25 @@ def test_trajectory_output_matches_blockwise_reads(lib, tmp_path):
     write_trajectory(path, out)
     back = read_gfbt(path)
     assert back["x"].shape == (4, n) and np.array_equal(back["kz"], out[:, 7, :])
+
+
+def test_pipelined_host_stepping_is_bit_identical(lib):
+    """gfb_rays_step_host (chunked upload / stepping / read-back overlap) == put_state + step + get_state."""
+    from graph_framework_b200.rays import RayTracer
+    g = golden("ref_trace_extra_ordinary_wave_efit_rk4")
+    base = unpack(g["per_step"][0][:8])
+    reps = 700                                  # ragged: 22400 rays, chunks do not divide evenly
+    start = {k: np.tile(v, reps) for k, v in base.items()}
+    n = start["w"].size
+    tr = RayTracer("extra_ordinary_wave", "efit", n, float(g["dt"]))
+    tr.set_state(start)
+    tr.init("")
+    tr.compile()
+    tr.step(25)
+    ref = tr.get_state()
+    for chunks in (1, 3, 8):
+        out = {k: np.empty(n) for k in ORDER + ("residual",)}
+        tr.step_host(25, start, out, chunks=chunks)
+        for k in ORDER + ("residual",):
+            assert np.array_equal(out[k], ref[k]), (chunks, k)
+    tr.close()
