@@ -524,9 +524,10 @@ int gfb_kernel_run_from_host(gfb_kernel *k, unsigned steps, int num_ray_slots,
     }
     const unsigned long long total = k->args.n;
     if (chunks < 1) chunks = 1;
-//  Chunk boundaries on block multiples so every piece but the last fills whole blocks.
+//  Chunk boundaries on whole waves (blocks/SM x SMs x block) so only the last piece has a tail.
     unsigned long long per = (total + chunks - 1)/chunks;
-    per = (per + k->block - 1)/k->block*k->block;
+    const unsigned long long wave = static_cast<unsigned long long> (k->block)*c->sms*(c->min_blocks > 0 ? c->min_blocks : 1);
+    per = (per + wave - 1)/wave*wave;
     std::vector<cudaEvent_t> uploaded, computed;
     int rc = 0;
     for (unsigned long long off = 0; off < total && !rc; off += per) {
