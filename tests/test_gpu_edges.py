@@ -1,0 +1,126 @@
+"""Edge cases of the device layer and the ray path (GPU): ragged and tiny ensembles, an empty one,
+error reporting, repeated compilation, step-count limits."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import golden, rel_dev
+
+pytestmark = pytest.mark.gpu
+ORDER = ("t", "w", "x", "y", "z", "kx", "ky", "kz")
+
+
+def unpack(a):
+    return {k: np.array(a[i]) for i, k in enumerate(ORDER)}
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 127, 129, 1000])
+def test_ragged_sizes_match_full_run(lib, n):
+    """Any ensemble size (not a multiple of the 128-thread block) gives the same per-ray results."""
+    from graph_framework_b200.rays import RayTracer
+    g = golden("ref_trace_ordinary_wave_efit_rk4")
+    rec = g["per_step"]
+    base = unpack(rec[0][:8])
+    idx = np.arange(n) % base["w"].size
+    start = {k: v[idx] for k, v in base.items()}
+    tr = RayTracer("ordinary_wave", "efit", n, float(g["dt"]))
+    tr.set_state(start)
+    tr.init("")
+    tr.compile()
+    tr.step(5)
+    got = tr.get_state()
+    tr.close()
+    for i, k in enumerate(ORDER):
+        assert rel_dev(got[k], rec[5][i][idx]) < 1.0e-11, (n, k)
+
+
+def test_empty_ensemble_is_a_no_op(lib):
+    from graph_framework_b200.rays import RayTracer
+    tr = RayTracer("simple", "slab", 0, 0.1)
+    tr.set_state({k: np.zeros(0) for k in ORDER})
+    tr.init("")
+    tr.compile()
+    tr.step(3)
+    got = tr.get_state()
+    tr.close()
+    assert all(got[k].size == 0 for k in ORDER)
+
+
+def test_step_counts_beyond_the_fusion_limit(lib):
+    """More steps than one launch may fuse (default 1024) are split into several launches."""
+    from graph_framework_b200.rays import RayTracer
+    n, dt = 16, 1.0e-3
+    s = {k: np.zeros(n) for k in ORDER}
+    s["w"][:] = 1.0
+    s["kx"][:] = 0.6
+    s["ky"][:] = 0.5
+    s["kz"][:] = 0.3
+    tr = RayTracer("simple", "slab", n, dt)
+    tr.set_state(s)
+    tr.init("kx")
+    tr.compile()
+    before = tr.launch_count()
+    tr.step(2500)
+    got = tr.get_state()
+    launches = tr.launch_count() - before
+    tr.close()
+    assert launches == 3                                   # 1024 + 1024 + 452
+    assert np.allclose(got["t"], 2500*dt, rtol=1e-12)
+    # D = k^2/w^2 - 1: dx/dt = k/w (|dx/dt| = 1), so |x| = t
+    r = np.sqrt(got["x"]**2 + got["y"]**2 + got["z"]**2)
+    assert np.allclose(r, 2500*dt, rtol=1e-10)
+
+
+def test_compile_error_is_reported_not_swallowed(lib):
+    """The reference prints the NVRTC log and carries on (cuda_context.hpp:256-267); here the call fails."""
+    ctx = lib.gfb_ctx_create(0)
+    assert ctx
+    names = (ctypes.c_char_p*1)(b"broken")
+    rc = lib.gfb_compile(ctx, b'extern "C" __global__ void broken(const gfb_args a) { this is not CUDA; }', names, 1, None)
+    assert rc != 0
+    assert b"error" in lib.gfb_last_error().lower()
+    k = ctypes.c_void_p()
+    keys = (ctypes.c_uint64*1)(1)
+    assert lib.gfb_kernel_create(ctx, b"broken", keys, 0, 4, 128, 0, 0, 0, ctypes.byref(k)) != 0
+    assert b"nothing compiled" in lib.gfb_last_error()
+    assert lib.gfb_copy_d2h(ctx, 12345, ctypes.c_void_p(), 8) != 0
+    assert b"unknown key" in lib.gfb_last_error()
+    lib.gfb_ctx_destroy(ctx)
+
+
+def test_device_info_is_a_b200(lib):
+    ctx = lib.gfb_ctx_create(0)
+    name = ctypes.create_string_buffer(128)
+    sms, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.gfb_ctx_device_info(ctx, name, 128, ctypes.byref(sms), ctypes.byref(major), ctypes.byref(minor)) == 0
+    assert major.value == 10 and sms.value >= 100
+    peak, ms = ctypes.c_double(), ctypes.c_float()
+    assert lib.gfb_measure_fp64_peak(ctx, ctypes.byref(peak), ctypes.byref(ms)) == 0
+    assert 20.0 < peak.value < 45.0                        # nominal 37.2 TFLOP/s
+    lib.gfb_ctx_destroy(ctx)
+
+
+def test_two_solvers_on_one_device_do_not_interfere(lib):
+    """Several managers per device are allowed (workflow.hpp:233-238); buffers are per context."""
+    from graph_framework_b200.rays import RayTracer
+    g = golden("ref_trace_extra_ordinary_wave_efit_rk4")
+    start = unpack(g["per_step"][0][:8])
+    n = start["w"].size
+    a = RayTracer("extra_ordinary_wave", "efit", n, float(g["dt"]))
+    b = RayTracer("ordinary_wave", "efit", n, float(g["dt"]))
+    for tr in (a, b):
+        tr.set_state(start)
+        tr.init("")
+        tr.compile()
+    a.step(3)
+    b.step(5)
+    a.step(2)
+    ga, gb = a.get_state(), b.get_state()
+    a.close()
+    b.close()
+    ref_a = g["per_step"][5]
+    ref_b = golden("ref_trace_ordinary_wave_efit_rk4")
+    assert rel_dev(ga["x"], ref_a[2]) < 1.0e-11 and rel_dev(ga["kz"], ref_a[7]) < 1.0e-11
+    assert np.isfinite(gb["x"]).all() and not np.array_equal(ga["kx"], gb["kx"])
+    assert ref_b["per_step"].shape[2] == n
