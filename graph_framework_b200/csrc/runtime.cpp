@@ -361,7 +361,9 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
 //  spills more than a few registers to local memory: FP64-bound bodies want warps to hide DFMA latency, but a
 //  spilling body pays for them in L1 traffic.
     const std::string user = options ? options : "";
-    const bool pinned = user.find("-DGFB_MIN_BLOCKS") != std::string::npos;
+//  Nothing to choose when the caller pinned the macro or no kernel uses it.
+    const bool pinned = user.find("-DGFB_MIN_BLOCKS") != std::string::npos ||
+                        std::string(source).find("GFB_MIN_BLOCKS)") == std::string::npos;
     const int candidates[] = {4, 3, 2, 1};
     for (const int mb : candidates) {
         const std::string opts = pinned ? user : user + " -DGFB_MIN_BLOCKS=" + std::to_string(mb);
@@ -382,9 +384,10 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
             }
         }
         GFB_TRACE("compile min_blocks=%d local=%d", mb, worst_local);
-//  A few spilled doubles are cheaper than a lost block per SM (measured: profiles/r1_sweep4_*.txt):
-//  accept up to 64 bytes of local memory per thread.
-        if (pinned || worst_local <= 64 || mb == 1) {
+//  A few spilled doubles are cheaper than a lost block per SM (measured: profiles/r1_sweep4_*.txt:
+//  X-mode wins with 48-72 B spilled at 3 blocks/SM, cold plasma loses with 344 B): accept up to
+//  128 bytes of local memory per thread.
+        if (pinned || worst_local <= 128 || mb == 1) {
             c->module = module;
             c->min_blocks = pinned ? 0 : mb;
             return 0;
