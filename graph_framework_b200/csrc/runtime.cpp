@@ -27,6 +27,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -112,8 +113,8 @@ bool entry(const char *name, F &f) {
     f = reinterpret_cast<F> (p);
     return true;
 }
-int load_driver() {
-    if (driver.loaded) return 0;
+std::once_flag driver_once;
+int load_driver_once() {
     if (!entry("cuModuleLoadData", driver.ModuleLoadData) ||
         !entry("cuModuleUnload", driver.ModuleUnload) ||
         !entry("cuModuleGetFunction", driver.ModuleGetFunction) ||
@@ -121,10 +122,16 @@ int load_driver() {
         !entry("cuFuncGetAttribute", driver.FuncGetAttribute) ||
         !entry("cuFuncSetAttribute", driver.FuncSetAttribute) ||
         !entry("cuGetErrorString", driver.GetErrorString)) {
-        return fail("CUDA driver entry points unavailable (no NVIDIA driver?)");
+        return 1;
     }
     driver.loaded = true;
     return 0;
+}
+//  One host thread per device is the reference's model (xrays.cpp:419-527): contexts may be created
+//  concurrently, so the entry points are resolved exactly once.
+int load_driver() {
+    std::call_once(driver_once, [] { load_driver_once(); });
+    return driver.loaded ? 0 : fail("CUDA driver entry points unavailable (no NVIDIA driver?)");
 }
 int check_cu(const CUresult r, const char *what) {
     if (r == CUDA_SUCCESS) return 0;
@@ -179,6 +186,7 @@ int nvrtc_compile(const std::string &full_source, const char *options, std::vect
 struct gfb_kernel {
     gfb_ctx *ctx;
     std::string name;
+    std::vector<uint64_t> slot_keys;     // buffer key behind every pointer slot
     CUfunction function;
     device_args args;
     unsigned block;
@@ -433,7 +441,16 @@ int gfb_buffer_import(gfb_ctx *c, uint64_t key, void *device_ptr, size_t bytes) 
         it->second.dev = device_ptr;
         it->second.bytes = bytes;
         it->second.owned = false;
-        for (auto &k : c->kernels) (void)k;
+        if (it->second.host) {
+            cudaFreeHost(it->second.host);
+            it->second.host = nullptr;
+        }
+//  Kernels created earlier must see the adopted memory.
+        for (auto &k : c->kernels) {
+            for (size_t i = 0; i < k->slot_keys.size(); i++) {
+                if (k->slot_keys[i] == key) k->args.ptr[i] = device_ptr;
+            }
+        }
         return 0;
     }
     buffer b;
@@ -471,6 +488,7 @@ int gfb_kernel_create(gfb_ctx *c, const char *name, const uint64_t *ptr_keys, in
         auto it = c->buffers.find(ptr_keys[i]);
         if (it == c->buffers.end()) return fail(std::string("gfb_kernel_create: missing buffer for ") + name);
         k->args.ptr[i] = it->second.dev;
+        k->slot_keys.push_back(ptr_keys[i]);
     }
     k->args.n = num_rays;
     k->block = block_size;

@@ -103,7 +103,6 @@ namespace gpu {
             }
             std::vector<uint64_t> keys;
             std::unordered_set<void *> seen;
-            bool written = false;
             for (auto &in : inputs) {
                 if (!seen.insert(in.get()).second) continue;
                 backend::buffer<T> b = in->evaluate();
@@ -115,7 +114,6 @@ namespace gpu {
                 check(gfb_buffer(ctx, key(out.get()), num_rays*sizeof(T), nullptr, nullptr), "output buffer");
                 keys.push_back(key(out.get()));
             }
-            (void)written;
             gfb_kernel *k = nullptr;
             check(gfb_kernel_create(ctx, kernel_name.c_str(), keys.data(), static_cast<int> (keys.size()),
                                     num_rays, 128, 0, 0, 1, &k), "kernel create");

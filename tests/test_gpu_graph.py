@@ -173,3 +173,50 @@ def test_deposit_matches_oracle(lib):
     tr.close()
     assert ref.sum() > 0.5*w.sum()
     assert np.allclose(hist.cpu().numpy(), ref, rtol=1.0e-12, atol=1.0e-12)
+
+
+
+ADD_ONE = b'''
+struct add_one_k {
+    static constexpr int NI = 1, NR = 1, NG = 0, NP = 1, NE = 1, TI = -1;
+    static constexpr unsigned SMEM_BYTES = 0, STAGED_BYTES = 0;
+    __device__ static constexpr bool group_staged(const int) { return false; }
+    __device__ static constexpr unsigned group_offset(const int) { return 0; }
+    __device__ static constexpr unsigned group_bytes(const int) { return 0; }
+    __device__ static constexpr int ev(const int) { return 0; }
+    __device__ static __forceinline__ void load(double (&v)[2], const gfb_args &a, const unsigned long long i) { v[0] = a.ptr[0][i]; }
+    __device__ static __forceinline__ void apply(double (&v)[2], const double (&r)[2]) { v[0] = r[0]; }
+    __device__ static __forceinline__ void store(const double (&v)[2], const double (&r)[2], const gfb_args &a, const unsigned long long i) { a.ptr[0][i] = v[0]; }
+    __device__ static __forceinline__ void body(const double (&v)[2], double (&r)[2], const double *(&tg)[1]) { r[0] = v[0] + 1.0; }
+};
+extern "C" __global__ void add_one(const __grid_constant__ gfb_args a) { gfb::generic_item<add_one_k> (a); }
+'''
+
+
+def test_raw_c_abi_with_adopted_torch_memory(lib):
+    """The device layer by hand: compile, buffer, kernel, deferred fused launches, and
+    gfb_buffer_import re-pointing an existing kernel at torch-owned memory."""
+    import torch
+    ctx = lib.gfb_ctx_create(0)
+    names = (ctypes.c_char_p*1)(b"add_one")
+    assert lib.gfb_compile(ctx, ADD_ONE, names, 1, None) == 0, lib.gfb_last_error()
+    n = 5000
+    host = np.arange(n, dtype=np.float64)
+    assert lib.gfb_buffer(ctx, 7, host.nbytes, host.ctypes.data_as(ctypes.c_void_p), None) == 0
+    k = ctypes.c_void_p()
+    keys = (ctypes.c_uint64*1)(7)
+    assert lib.gfb_kernel_create(ctx, b"add_one", keys, 1, n, 128, 0, 0, 1, ctypes.byref(k)) == 0
+    before = lib.gfb_launch_count(ctx)
+    for _ in range(5):
+        assert lib.gfb_kernel_run(k) == 0                   # deferred ...
+    out = np.empty(n)
+    assert lib.gfb_copy_d2h(ctx, 7, out.ctypes.data_as(ctypes.c_void_p), 0) == 0       # ... flushed here as one launch
+    assert lib.gfb_launch_count(ctx) - before == 1
+    assert np.array_equal(out, host + 5.0)
+    t = torch.full((n,), 100.0, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    assert lib.gfb_buffer_import(ctx, 7, ctypes.c_void_p(t.data_ptr()), t.numel()*8) == 0
+    assert lib.gfb_kernel_launch(k, 3) == 0
+    assert lib.gfb_wait(ctx) == 0
+    assert torch.equal(t.cpu(), torch.full((n,), 103.0, dtype=torch.float64))
+    lib.gfb_ctx_destroy(ctx)
