@@ -65,6 +65,26 @@ def test_division_and_sqrt_edge_values(g):
     assert g.copy_to_host(outs[0], n)[5] == np.inf
 
 
+def test_reciprocal_and_sqrt_accuracy(g):
+    """gfb::rcp / gfb::rsqrt / sqrt_from_rsqrt over 20 decades: within 1 ulp of the IEEE result."""
+    rng = np.random.default_rng(7)
+    n = 200000
+    vals = rng.uniform(1.0, 10.0, n)*10.0**rng.integers(-150, 150, n)*rng.choice([-1.0, 1.0], n)
+    x = g.variable(n, "x", vals)
+    a = g.variable(n, "a", np.abs(vals))
+    one = g.variable(n, "one", np.ones(n))
+    outs = [one/x, g.sqrt(a), one/g.sqrt(a)]
+    g.add_item([x, a, one], outs, [], "accuracy", n)
+    g.compile()
+    g.run()
+    ref = [1.0/vals, np.sqrt(np.abs(vals)), 1.0/np.sqrt(np.abs(vals))]
+    ulp = 2.0**-52
+    for o, r, bound in zip(outs, ref, (1.0, 1.0, 1.5)):
+        got = g.copy_to_host(o, n)
+        err = np.max(np.abs(got - r)/np.abs(r))
+        assert err <= bound*ulp, err/ulp
+
+
 def test_workflow_setters_and_repeated_items(g):
     """workflow_test.cpp:19-70: several setters read the OLD values; ten runs fuse into one launch."""
     n = 100
