@@ -93,6 +93,7 @@ namespace jit {
 ///  Refined hardware reciprocal / rsqrt seeds instead of IEEE division and sqrt, and a
 ///  multiplication by 1/scale in table indices (what -ffast-math does to the reference's kernels).
         bool fast_division = true;
+        unsigned mode_loop_unroll = 2;          ///< unroll factor of Fourier mode loops (graph::fourier_series)
         size_t unroll_stages_below = 640;       ///< unroll the RK stage loop for bodies up to this many statements
         unsigned block_size = 128;
 ///  Resident blocks per SM promised to ptxas; 0 = let the device layer pick the highest
@@ -323,7 +324,7 @@ namespace jit {
                     weights.insert({o.b, o.c, (o.b + o.c + (o.base ? 3u : 0u)) & 3u});
                 }
             }
-            out << "#pragma unroll 2" << std::endl
+            out << "#pragma unroll " << opt.mode_loop_unroll << std::endl
                 << "            for (int m = 0; m < " << loop.xm.size() << "; m++) {" << std::endl
                 << "                const double xm = mn" << id << "[2*m], xn = mn" << id << "[2*m + 1];" << std::endl
                 << "                double sn, cs;" << std::endl
