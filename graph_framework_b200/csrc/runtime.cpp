@@ -364,45 +364,57 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
         c->module = nullptr;
         c->kernels.clear();
     }
-//  Occupancy choice: the emitted kernels carry __launch_bounds__(block, GFB_MIN_BLOCKS).  Unless the
-//  caller pinned it, take the largest promise (4, 3, 2, 1 blocks per SM) for which no kernel
-//  spills more than a few registers to local memory: FP64-bound bodies want warps to hide DFMA latency, but a
-//  spilling body pays for them in L1 traffic.
+//  Occupancy choice.  The emitted kernels carry __launch_bounds__(128, GFB_MIN_BLOCKS).  Compile once
+//  without a promise to learn the natural register count R and the blocks/SM m0 that fit with it;
+//  then try to squeeze in one or two more blocks (m0 + 2, m0 + 1): FP64- and gather-latency-bound
+//  bodies want warps, but a body that spills pays for them in L1 traffic.  A few spilled doubles are
+//  cheaper than a lost block (measured, profiles/r1_sweep4_*.txt: X-mode wins with 48-104 B spilled
+//  at 3 blocks/SM, cold plasma loses with 344 B), so a candidate is accepted when it adds at most
+//  128 bytes of local memory per thread.
     const std::string user = options ? options : "";
 //  Nothing to choose when the caller pinned the macro or no kernel uses it.
     const bool pinned = user.find("-DGFB_MIN_BLOCKS") != std::string::npos ||
                         std::string(source).find("GFB_MIN_BLOCKS)") == std::string::npos;
-    const int candidates[] = {4, 3, 2, 1};
-    for (const int mb : candidates) {
-        const std::string opts = pinned ? user : user + " -DGFB_MIN_BLOCKS=" + std::to_string(mb);
+    struct variant { CUmodule module = nullptr; int regs = 0; int local = 0; };
+    auto build = [&] (const int mb, variant &v) -> int {
+        const std::string opts = (pinned || mb == 0) ? user : user + " -DGFB_MIN_BLOCKS=" + std::to_string(mb);
         std::vector<char> image;
         if (nvrtc_compile(c->source, opts.c_str(), image, c->log)) {
             std::fprintf(stderr, "%s\n", last_error.c_str());
             return 1;
         }
-        CUmodule module = nullptr;
-        if (check_cu(driver.ModuleLoadData(&module, image.data()), "cuModuleLoadData")) return 1;
-        int worst_local = 0;
+        if (check_cu(driver.ModuleLoadData(&v.module, image.data()), "cuModuleLoadData")) return 1;
         for (int i = 0; i < num_names; i++) {
             CUfunction f;
-            int local = 0;
-            if (driver.ModuleGetFunction(&f, module, names[i]) == CUDA_SUCCESS &&
-                driver.FuncGetAttribute(&local, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f) == CUDA_SUCCESS) {
-                worst_local = local > worst_local ? local : worst_local;
-            }
+            int value = 0;
+            if (driver.ModuleGetFunction(&f, v.module, names[i]) != CUDA_SUCCESS) continue;
+            if (driver.FuncGetAttribute(&value, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f) == CUDA_SUCCESS && value > v.local) v.local = value;
+            if (driver.FuncGetAttribute(&value, CU_FUNC_ATTRIBUTE_NUM_REGS, f) == CUDA_SUCCESS && value > v.regs) v.regs = value;
         }
-        GFB_TRACE("compile min_blocks=%d local=%d", mb, worst_local);
-//  A few spilled doubles are cheaper than a lost block per SM (measured: profiles/r1_sweep4_*.txt:
-//  X-mode wins with 48-72 B spilled at 3 blocks/SM, cold plasma loses with 344 B): accept up to
-//  128 bytes of local memory per thread.
-        if (pinned || worst_local <= 128 || mb == 1) {
-            c->module = module;
-            c->min_blocks = pinned ? 0 : mb;
+        GFB_TRACE("compile min_blocks=%d regs=%d local=%d", mb, v.regs, v.local);
+        return 0;
+    };
+    variant natural;
+    if (build(1, natural)) return 1;
+    c->module = natural.module;
+    c->min_blocks = 0;
+    if (pinned) return 0;
+    const int regs8 = (natural.regs + 7)/8*8;
+    int m0 = regs8 > 0 ? 65536/(128*regs8) : 1;
+    m0 = m0 < 1 ? 1 : (m0 > 8 ? 8 : m0);
+    c->min_blocks = m0;
+    for (int mb = (m0 + 2 > 8 ? 8 : m0 + 2); mb > m0; mb--) {
+        variant v;
+        if (build(mb, v)) return 1;
+        if (v.local - natural.local <= 128) {
+            driver.ModuleUnload(natural.module);
+            c->module = v.module;
+            c->min_blocks = mb;
             return 0;
         }
-        driver.ModuleUnload(module);
+        driver.ModuleUnload(v.module);
     }
-    return fail("gfb_compile: no variant loaded");
+    return 0;
 }
 int gfb_compiled_min_blocks(gfb_ctx *c) { return c->min_blocks; }
 const char *gfb_source(gfb_ctx *c) { return c->source.c_str(); }
