@@ -124,12 +124,9 @@ def reference_arm(args, rank, world):
         return 0
     rays = args.ref_rays
     state = generator(eq)(rays, seed=0)
-    times = []
-    last = None
-    for i in range(args.warmup + args.steps):
-        last = reference.bench(disp, eq, rays, dt, SUB_STEPS, cores, state)
-        if i >= args.warmup:
-            times.append(last["steps_s"])
+    # one process: graph build, Newton init and JIT once, then W + K timed blocks of SUB_STEPS steps
+    last = reference.bench(disp, eq, rays, dt, SUB_STEPS, cores, state, blocks=args.warmup + args.steps)
+    times = last["block_s"][args.warmup:]
     total = sum(times)
     value = rays*SUB_STEPS*len(times)/total
     line = {

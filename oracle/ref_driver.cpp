@@ -16,8 +16,10 @@
 //                the pre-step state of the last step, solver.hpp:316-319).
 //   ref_driver rhs <dispersion> <equilibrium> <N> <in.bin> <out.bin>
 //       out.bin: 7 arrays dxdt,dydt,dzdt,dkxdt,dkydt,dkzdt,D  (dispersion.hpp:1387-1433)
-//   ref_driver bench <dispersion> <equilibrium> <N> <dt> <nsteps> <threads> <in.bin|->
-//       prints one JSON line; rays are split batch/extra like xrays_bench.cpp:38-51.
+//   ref_driver bench <dispersion> <equilibrium> <N> <dt> <nsteps> <threads> <in.bin|-> [blocks]
+//       prints one JSON line; rays are split batch/extra like xrays_bench.cpp:38-51.  With
+//       [blocks] > 1 the stepping phase is repeated that many times after one setup/init/compile
+//       and every block is timed separately ("block_s").
 //   ref_driver korc <equilibrium> <N> <nsteps> <in.bin> <out.bin>
 //       in.bin: 6 arrays x,y,z,ux,uy,uz (physical u/c, as xkorc.cpp:47-64); out: 7 arrays x,y,z,ux,uy,uz,gamma
 //   ref_driver source <dispersion> <equilibrium> <solver>     (dump kernel text; set GFB_ORACLE_KEEP_SOURCE=1)
@@ -169,10 +171,12 @@ static int bench_impl(int argc, char **argv) {
     const size_t nsteps = std::stoul(argv[6]);
     const size_t nthreads = std::max<size_t> (1, std::min<size_t> (std::stoul(argv[7]), n));
     const std::string inpath = argv[8];
+    const size_t blocks = argc > 9 ? std::max<size_t> (1, std::stoul(argv[9])) : 1;
     std::vector<std::vector<double>> in;
     if (inpath != "-") in = read_arrays(inpath, 8, n);
     const size_t batch = n/nthreads, extra = n%nthreads;   // xrays_bench.cpp:38-51
     std::vector<double> t_setup(nthreads), t_init(nthreads), t_compile(nthreads), t_steps(nthreads);
+    std::vector<std::vector<double>> t_block(nthreads, std::vector<double> (blocks, 0.0));
     std::vector<std::thread> threads(nthreads);
     std::vector<size_t> offsets(nthreads + 1, 0);
     for (size_t i = 0; i < nthreads; i++) offsets[i + 1] = offsets[i] + batch + (extra > i ? 1 : 0);
@@ -192,19 +196,29 @@ static int bench_impl(int argc, char **argv) {
             auto t2 = now();
             solve.compile();
             auto t3 = now();
-            for (size_t j = 0; j < nsteps; j++) solve.step();
-            solve.sync_host();
+            for (size_t b = 0; b < blocks; b++) {
+                auto b0 = now();
+                for (size_t j = 0; j < nsteps; j++) solve.step();
+                solve.sync_host();
+                t_block[i][b] = secs(b0, now());
+            }
             auto t4 = now();
             t_setup[i] = secs(t0, t1); t_init[i] = secs(t1, t2); t_compile[i] = secs(t2, t3); t_steps[i] = secs(t3, t4);
         });
     }
     for (auto &t : threads) t.join();
     auto mx = [] (const std::vector<double> &v) { double m = 0; for (double x : v) m = std::max(m, x); return m; };
-    const double steps_s = mx(t_steps);
+    const double steps_s = mx(t_steps)/static_cast<double> (blocks);
     std::printf("{\"impl\": \"reference\", \"rays\": %zu, \"steps\": %zu, \"threads\": %zu, \"setup_s\": %.4f, \"init_s\": %.4f, "
-                "\"compile_s\": %.4f, \"steps_s\": %.6f, \"ray_steps_per_s\": %.6e}\n",
+                "\"compile_s\": %.4f, \"steps_s\": %.6f, \"ray_steps_per_s\": %.6e, \"block_s\": [",
                 n, nsteps, nthreads, mx(t_setup), mx(t_init), mx(t_compile), steps_s,
                 static_cast<double> (n)*static_cast<double> (nsteps)/steps_s);
+    for (size_t b = 0; b < blocks; b++) {
+        double worst = 0.0;
+        for (size_t i = 0; i < nthreads; i++) worst = std::max(worst, t_block[i][b]);
+        std::printf("%s%.6f", b ? ", " : "", worst);
+    }
+    std::printf("]}\n");
     return 0;
 }
 
@@ -304,7 +318,7 @@ int main(int argc, char **argv) {
     if (mode == "trace" && argc == 12) {
         const std::string d = argv[2], s = argv[4];
         DISPATCH_SOLVER(trace_impl, d, s)
-    } else if (mode == "bench" && argc == 9) {
+    } else if (mode == "bench" && (argc == 9 || argc == 10)) {
         const std::string d = argv[2], s = "rk4";
         DISPATCH_SOLVER(bench_impl, d, s)
     } else if (mode == "rhs" && argc == 7) {

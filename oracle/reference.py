@@ -61,14 +61,15 @@ def rhs(dispersion, equilibrium, state):
         return np.fromfile(fout).reshape(7, n)
 
 
-def bench(dispersion, equilibrium, n, dt, nsteps, threads, state=None):
-    """Times the reference stepping loop (xrays_bench.cpp:88-102) on `threads` host threads."""
+def bench(dispersion, equilibrium, n, dt, nsteps, threads, state=None, blocks=1):
+    """Times the reference stepping loop (xrays_bench.cpp:88-102) on `threads` host threads;
+    `blocks` repetitions of nsteps after one setup are timed separately (result["block_s"])."""
     with tempfile.TemporaryDirectory() as d:
         fin = "-"
         if state is not None:
             fin = os.path.join(d, "in.bin")
             _pack(state).tofile(fin)
-        out = _run(["bench", dispersion, equilibrium, n, repr(float(dt)), nsteps, threads, fin])
+        out = _run(["bench", dispersion, equilibrium, n, repr(float(dt)), nsteps, threads, fin, blocks])
     return json.loads(out.strip().splitlines()[-1])
 
 
