@@ -22,6 +22,7 @@ def lib():
     so = os.path.join(ROOT, "graph_framework_b200", "libgfb200.so")
     if not os.path.exists(so):
         subprocess.run(["make", "-j4"], cwd=ROOT, check=True)
+        subprocess.run(["make", "-j2", "tests"], cwd=ROOT, check=True)
     from graph_framework_b200 import _lib
     return _lib.lib
 

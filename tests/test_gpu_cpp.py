@@ -11,8 +11,12 @@ pytestmark = pytest.mark.gpu
 
 
 def build(target):
-    subprocess.run(["make", "build/" + target], cwd=ROOT, check=True, capture_output=True)
-    return os.path.join(ROOT, "build", target)
+    """Prebuilt by __graft_entry__.build() (`make tests`); only built here when missing, so that a
+    loaded libgfb200.so is never relinked under a running test session."""
+    exe = os.path.join(ROOT, "build", target)
+    if not os.path.exists(exe):
+        subprocess.run(["make", "build/" + target], cwd=ROOT, check=True, capture_output=True)
+    return exe
 
 
 def test_known_answers():
