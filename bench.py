@@ -361,7 +361,7 @@ def main():
             "clocks": clocks,
             "phases_s": {"setup": t_init - t_setup, "newton_init": t_compile - t_init, "jit": t_ready - t_compile},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # reported baseline, rank 0 at N = 1 only
             try:
                 from oracle import reference
                 if reference.available():
