@@ -241,6 +241,19 @@ def test_million_ray_properties(lib):
     tr.close()
     for k in ORDER:
         assert np.array_equal(got2[k], got[k][perm]), k
+    # ... and an oracle check at full size: 512 of the 10^6 rays against the independent numpy
+    # restatement (Newton + 100 RK4 steps), 1e-9 relative at the end of the block.
+    from oracle import port
+    from graph_framework_b200.tools.gfbt import read_gfbt
+    import os
+    from conftest import GOLDEN
+    sel = perm[:512]
+    eq = port.Efit(read_gfbt(os.path.join(GOLDEN, "efit.gfbt")))
+    with np.errstate(all="ignore"):
+        s0 = port.newton("extra_ordinary_wave", eq, {k: state[k][sel] for k in ORDER}, "kx", per_ray=True)
+        ref, res = port.trace("extra_ordinary_wave", eq, s0, dt, 100)
+    for k in ORDER:
+        assert rel_dev(got[k][sel], ref[k]) < 1.0e-9, (k, rel_dev(got[k][sel], ref[k]))
 
 
 def test_vmec_trajectory_properties(lib):
