@@ -279,6 +279,13 @@ tracer_base *make_tracer(const std::string &solver_name, std::vector<leaf_ptr> &
     if (solver_name == "rk2") return new tracer<solver::rk2<DF, true>> (s, dt, eq, n, device, o);
     if (solver_name == "rk4_graph") return new tracer<solver::rk4<DF, false>> (s, dt, eq, n, device, o);
     if (solver_name == "rk2_graph") return new tracer<solver::rk2<DF, false>> (s, dt, eq, n, device, o);
+    if (solver_name == "split_simplextic") {
+//  Only separable Hamiltonians (the constructor aborts otherwise, like the reference's assert).
+        if constexpr (std::is_same<DF, dispersion::bohm_gross<>>::value || std::is_same<DF, dispersion::light_wave<>>::value ||
+                      std::is_same<DF, dispersion::simple<>>::value || std::is_same<DF, dispersion::acoustic_wave<>>::value) {
+            return new tracer<solver::split_simplextic<DF>> (s, dt, eq, n, device, o);
+        }
+    }
     return nullptr;
 }
 }  // namespace

@@ -30,7 +30,7 @@ enum { GFB_T = 0, GFB_W, GFB_X, GFB_Y, GFB_Z, GFB_KX, GFB_KY, GFB_KZ, GFB_NUM_ST
  * equilibrium: "efit" (table_file = GFBT path) | "slab" | "slab_density" | "slab_field" |
  *              "no_magnetic_field" | "gaussian_density"
  * solver     : "rk4" | "rk2" (staged skeleton) | "rk4_graph" | "rk2_graph" (stages unrolled in the
- *              graph, the reference's construction)
+ *              graph, the reference's construction) | "split_simplextic" (separable dispersions only)
  * options    : NULL or space separated key=value list:
  *              block=<threads> minblocks=<n> stage_tables=<0|1> share_rcp=<0|1> fast_div=<0|1> unroll_stages=<0|1>
  *              fused_steps=<max steps per launch>

@@ -122,3 +122,25 @@ def test_two_solvers_on_one_device_do_not_interfere(lib):
     for i, k in enumerate(ORDER):
         assert rel_dev(ga[k], g["per_step"][5][i]) < 1.0e-11, ("x-mode", k)
         assert rel_dev(gb[k], go["per_step"][5][i]) < 1.0e-11, ("o-mode", k)
+
+
+def test_xrays_driver_efit_example(lib, tmp_path):
+    """The reference's efit_example.sh command line (graph_driver/efit_example.sh) at reduced size
+    through graph_framework_b200.xrays: per-shard result files with (time, num_rays) variables."""
+    from graph_framework_b200 import xrays
+    from graph_framework_b200.tools.gfbt import read_gfbt
+    prefix = str(tmp_path / "result")
+    rc = xrays.main(["--dispersion=ordinary_wave", "--endtime=0.02", "--equilibrium=efit", "--init_kx",
+                     "--init_kx_mean=-700.0", "--init_ky_dist=normal", "--init_ky_mean=-100.0", "--init_ky_sigma=10.0",
+                     "--init_kz_dist=normal", "--init_kz_mean=0.0", "--init_kz_sigma=10.0", "--init_w_dist=normal",
+                     "--init_w_mean=700", "--init_w_sigma=10.0", "--init_x_mean=2.5", "--init_y_dist=normal",
+                     "--init_y_mean=0.0", "--init_y_sigma=0.05", "--init_z_dist=normal", "--init_z_mean=0.0",
+                     "--init_z_sigma=0.05", "--num_rays=5000", "--num_times=1000", "--solver=rk4", "--sub_steps=100",
+                     "--use_cyl_xy", "--seed", "--devices=1", "--output=" + prefix])
+    assert rc == 0
+    out = read_gfbt(prefix + "0.gfbt")
+    assert out["x"].shape == (10, 5000)
+    assert np.allclose(out["t"][:, 0], 2.0e-5*100*np.arange(1, 11), rtol=1e-12)
+    assert np.isfinite(out["kx"]).all() and np.max(out["residual"][-1]) < 1.0e-18
+    r = np.sqrt(out["x"]**2 + out["y"]**2)
+    assert np.all(r[-1] < r[0])                    # launched inward from R = 2.5
