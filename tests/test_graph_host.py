@@ -116,3 +116,26 @@ def test_trig_of_atan_is_algebraic(g):
 def test_unsupported_context_types_are_refused(lib):
     assert not lib.graph_construct_context(0, False)     # FLOAT
     assert not lib.graph_construct_context(1, True)      # DOUBLE with safe math
+
+
+def test_xrays_driver_options_and_sampling():
+    """graph_framework_b200.xrays keeps the reference driver's option names (xrays.cpp:955-1037) and
+    its sampling rules (xrays.cpp:56-130): uniform = the mean for every ray, normal = N(mean, sigma),
+    --use_cyl_xy reads x as radius and y as angle, --seed makes shards reproducible and distinct."""
+    from graph_framework_b200 import xrays
+    argv = ["--num_rays=1000", "--num_times=1000", "--sub_steps=100", "--endtime=0.02", "--init_kx",
+            "--init_kx_mean=-700", "--init_w_dist=normal", "--init_w_mean=700", "--init_w_sigma=10",
+            "--init_x_mean=2.5", "--init_y_dist=normal", "--init_y_sigma=0.05", "--use_cyl_xy", "--seed"]
+    args = xrays.parser().parse_args(argv)
+    assert args.init_kx and not args.init_ky and args.solver == "rk4" and args.equilibrium == "efit"
+    a = xrays.initial_conditions(args, 0, 1000)
+    b = xrays.initial_conditions(args, 0, 1000)
+    c = xrays.initial_conditions(args, 1, 1000)
+    assert set(a) == {"t", "w", "kx", "ky", "kz", "x", "y", "z"}
+    assert np.array_equal(a["w"], b["w"]) and not np.array_equal(a["w"], c["w"])
+    assert np.all(a["kx"] == -700.0) and np.all(a["z"] == 0.0)
+    assert np.allclose(np.hypot(a["x"], a["y"]), 2.5, rtol=1e-15)
+    assert abs(a["w"].mean() - 700.0) < 1.5 and 8.0 < a["w"].std() < 12.0
+    assert np.abs(np.arctan2(a["y"], a["x"])).max() < 0.3
+    with pytest.raises(SystemExit):
+        xrays.parser().parse_args(["--solver=euler"])
