@@ -15,15 +15,19 @@ all: $(LIB)
 $(SRC)/skeleton_text.inc: $(SRC)/skeleton.cuh
 	( printf 'R"GFBSKEL(' ; cat $< ; printf ')GFBSKEL"\n' ) > $@
 
+# special.cuh with its coefficient table spliced in: NVRTC sees one self-contained text.
+$(SRC)/special_text.inc: $(SRC)/special.cuh $(SRC)/wim_table.inc
+	( printf 'R"GFBSPEC(' ; sed -e '/#include "wim_table.inc"/{r $(SRC)/wim_table.inc' -e 'd}' $< ; printf ')GFBSPEC"\n' ) > $@
+
 build/kernels.o: $(SRC)/kernels.cu
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
-build/runtime.o: $(SRC)/runtime.cpp $(SRC)/skeleton_text.inc include/gfb200.h
+build/runtime.o: $(SRC)/runtime.cpp $(SRC)/skeleton_text.inc $(SRC)/special_text.inc include/gfb200.h
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-build/c_binding.o: $(SRC)/c_binding.cpp $(wildcard $(SRC)/graph/*.hpp) include/gfb200.h include/graph_c_binding.h include/gfb_rays.h
+build/c_binding.o: $(SRC)/c_binding.cpp $(wildcard $(SRC)/graph/*.hpp) $(SRC)/special.cuh $(SRC)/wim_table.inc include/gfb200.h include/graph_c_binding.h include/gfb_rays.h
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
@@ -31,7 +35,7 @@ $(LIB): build/kernels.o build/runtime.o build/c_binding.o
 	$(CXX) -shared -o $@ $^ -L$(CUDA)/lib64 -lcudart_static -lnvrtc -ldl -lrt -lpthread
 
 clean:
-	rm -rf build $(LIB) $(SRC)/skeleton_text.inc
+	rm -rf build $(LIB) $(SRC)/skeleton_text.inc $(SRC)/special_text.inc
 
 # Reference-style C++ programs built against the header-only front end + libgfb200.so.
 TESTBIN := build/known_answers build/xrays_bench_b200

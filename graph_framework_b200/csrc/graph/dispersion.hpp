@@ -230,6 +230,119 @@ namespace dispersion {
         }
     };
 
+//------------------------------------------------------------------------------
+//  Absorption path (dispersion.hpp:245-305, 1010-1098, 1209-1290 of the reference).
+//
+//  The reference runs this stage in std::complex<T>.  Ray state is real, so every quantity is real
+//  except the plasma dispersion function Z(zeta); a complex value is therefore carried as a pair of
+//  real graphs and the few complex operations (Z, 1/Z, scaling by a real) are written out.  The real
+//  arithmetic below is what the complex arithmetic of the reference reduces to for zero imaginary
+//  parts, up to rounding in complex division.
+//------------------------------------------------------------------------------
+    struct complex_leaf {
+        leaf_ptr re, im;
+    };
+
+///  Z(zeta) = -sqrt(pi) exp(-zeta^2) (erfi(zeta) - i)  (z_erfi, dispersion.hpp:289-305).
+    template<typename T=double, bool SAFE_MATH=false>
+    class z_erfi {
+    public:
+        complex_leaf Z(leaf_ptr zeta) {
+            auto scale = -std::sqrt(M_PI)*graph::exp(-1.0*(zeta*zeta));
+            return {scale*graph::erfi(zeta), -1.0*scale};
+        }
+    };
+
+///  Cold plasma dispersion function in the form the hot plasma expansion reduces to for
+///  v_th -> 0 (dispersion.hpp:1010-1098); real, usable as an ordinary dispersion function.
+    template<typename T=double, bool SAFE_MATH=false>
+    class cold_plasma_expansion : public physics<T, SAFE_MATH> {
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            auto b_vec = eq->get_magnetic_field(x, y, z);
+            auto b_len = b_vec->length();
+            auto b_hat = b_vec/b_len;
+            auto ec = build_cyclotron_frequency(this->q, b_len, this->me, this->c);
+            auto wpe2 = build_plasma_frequency(eq->get_electron_density(x, y, z), this->q, this->me, this->c, this->epsilon0);
+
+            auto P = wpe2/(w*w);
+            auto q = P/(2.0*(1.0 + ec/w));
+
+            auto n = k_vec/w;
+            auto n2 = n->dot(n);
+            auto npara = n->dot(b_hat);
+            auto npara2 = npara*npara;
+            auto nperp = b_hat->cross(n);
+            auto nperp2 = nperp->dot(nperp);
+
+            auto q_func = 1.0 - 2.0*q;
+            auto n_func = n2 + npara2;
+            auto p_func = 1.0 - P;
+
+            auto gamma1 = (1.0 - q)*(n2*nperp2) + p_func*(n2*npara2 - (1.0 - q)*n_func) + q_func*(p_func - nperp2);
+            auto gamma0 = nperp2*(n2 - 2.0*q_func) + p_func*(2.0*q_func - n_func);
+            return -1.0*P/2.0*(1.0 + ec/w)*gamma0 + (1.0 - ec*ec/(w*w))*gamma1;
+        }
+    };
+
+///  Weakly relativistic / warm correction near the electron cyclotron fundamental
+///  (hot_plasma_expansion, dispersion.hpp:1209-1290).  Complex through Z only.
+    template<typename T=double, class Z=z_erfi<T, false>, bool SAFE_MATH=false>
+    class hot_plasma_expansion : public physics<T, SAFE_MATH> {
+    private:
+        Z z_function;
+    public:
+///  Not a ray-tracing Hamiltonian: the real part alone is returned through the common interface.
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr t,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            return D_complex(w, k_vec, x, y, z, t, eq).re;
+        }
+        complex_leaf D_complex(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                               equilibrium::shared<T, SAFE_MATH> &eq) {
+            auto b_vec = eq->get_magnetic_field(x, y, z);
+            auto b_hat = b_vec->unit();
+            auto b_len = b_vec->length();
+            auto te = eq->get_electron_temperature(x, y, z);
+            auto ve = graph::sqrt(static_cast<T> (2.0)*this->q*te/this->me);
+            auto ec = build_cyclotron_frequency(this->q, b_len, this->me, this->c);
+            auto wpe2 = build_plasma_frequency(eq->get_electron_density(x, y, z), this->q, this->me, this->c, this->epsilon0);
+
+            auto P = wpe2/(w*w);
+            auto q = P/(2.0*(1.0 + ec/w));
+
+            auto n = k_vec/w;
+            auto n2 = n->dot(n);
+            auto npara = b_hat->dot(n);
+            auto npara2 = npara*npara;
+            auto nperp = b_hat->cross(n);
+            auto nperp2 = nperp->dot(nperp);
+            auto vtnorm = ve/this->c;
+
+            auto zeta = (1.0 - ec/w)/(npara*vtnorm);
+            auto Zf = z_function.Z(zeta);
+
+            auto q_func = 1.0 - 2.0*q;
+            auto n_func = n2 + npara2;
+            auto p_func = 1.0 - P;
+
+            auto gamma5 = P*(n2*npara2 - (1.0 - q)*n_func + q_func);
+            auto gamma2 = P*w/ec*nperp2*(n2 - q_func) + P*P*w*w/(4.0*ec*ec)*(n_func - 2.0*q_func)*nperp2/npara2;
+            auto gamma1 = (1.0 - q)*(n2*nperp2) + p_func*(n2*npara2 - (1.0 - q)*n_func) + q_func*(p_func - nperp2);
+
+            auto amplitude = -1.0*(1.0 + ec/w)*npara*vtnorm*
+                             (gamma1 + gamma2 + nperp2/(2.0*npara)*(w*w/(ec*ec))*vtnorm*zeta*gamma5);
+//  1/Z = conj(Z)/|Z|^2.  Far from the resonance (|zeta| > 27.2) exp(-zeta^2) underflows, Z = 0 and
+//  1/Z is 0/0.  The reference leaves that to its SAFE_MATH rules (products with an exact zero are
+//  zero, NaN is stored as 0: cpu_context.hpp:533-544) and to the fast-math of its JIT compiler; what
+//  its kernels deliver there is D = 0, i.e. no damping, which is also the analytic limit
+//  (Z -> -1/zeta).  Stated explicitly here.
+            auto norm = Zf.re*Zf.re + Zf.im*Zf.im;
+            return {graph::nan_to_zero(amplitude*(Zf.re/norm + zeta)),
+                    graph::nan_to_zero(amplitude*(-1.0*Zf.im/norm))};
+        }
+    };
+
 ///  See dispersion_interface: whether the k_vec correction term is applied (default: no, like
 ///  the reference's effective behaviour).
     inline bool &kvec_correction() {

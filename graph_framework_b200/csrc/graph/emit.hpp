@@ -492,6 +492,8 @@ namespace jit {
                 case op_t::sqrt: rhs = "sqrt(" + a[0] + ")"; break;
                 case op_t::exp: rhs = "exp(" + a[0] + ")"; break;
                 case op_t::log: rhs = "log(" + a[0] + ")"; break;
+                case op_t::erfi: rhs = "gfb::erfi(" + a[0] + ")"; break;
+                case op_t::nan_to_zero: rhs = "(" + a[0] + " == " + a[0] + " ? " + a[0] + " : 0.0)"; break;
                 case op_t::pow: rhs = "pow(" + a[0] + ", " + a[1] + ")"; break;
                 case op_t::sin: rhs = "sin(" + a[0] + ")"; break;
                 case op_t::cos: rhs = "cos(" + a[0] + ")"; break;

@@ -10,4 +10,5 @@
 #include "equilibrium.hpp"
 #include "dispersion.hpp"
 #include "solver.hpp"
+#include "absorption.hpp"
 #endif

@@ -40,6 +40,8 @@
 #include <utility>
 #include <vector>
 
+#include "../special.cuh"
+
 namespace backend {
 //------------------------------------------------------------------------------
 ///  Host value buffer (reference: backend.hpp:28-786, a std::vector wrapper).
@@ -87,7 +89,8 @@ namespace graph {
         sqrt, exp, log, pow,
         sin, cos, atan,
         piecewise_1d, piecewise_2d,
-        fourier
+        fourier,
+        erfi, nan_to_zero
     };
 
     class leaf_node;
@@ -157,7 +160,8 @@ namespace graph {
             switch (op) {
                 case op_t::constant: case op_t::variable: return 0;
                 case op_t::pseudo: case op_t::sqrt: case op_t::exp: case op_t::log:
-                case op_t::sin: case op_t::cos: case op_t::piecewise_1d: return 1;
+                case op_t::sin: case op_t::cos: case op_t::piecewise_1d: case op_t::erfi:
+                case op_t::nan_to_zero: return 1;
                 case op_t::fma: case op_t::fourier: return 3;
                 default: return 2;
             }
@@ -398,6 +402,8 @@ namespace graph {
     inline leaf_ptr sqrt(leaf_ptr a);
     inline leaf_ptr exp(leaf_ptr a);
     inline leaf_ptr log(leaf_ptr a);
+    inline leaf_ptr erfi(leaf_ptr a);
+    inline leaf_ptr nan_to_zero(leaf_ptr a);
     inline leaf_ptr pow(leaf_ptr a, leaf_ptr b);
     inline leaf_ptr sin(leaf_ptr a);
     inline leaf_ptr cos(leaf_ptr a);
@@ -514,6 +520,18 @@ namespace graph {
     inline leaf_ptr log(leaf_ptr a) {
         if (a->is_constant()) return constant(std::log(a->value));
         return detail::intern(op_t::log, a, nullptr, nullptr);
+    }
+///  erfi of a real argument (reference: graph::erfi, math.hpp; evaluation special_functions.hpp:1583).
+    inline leaf_ptr erfi(leaf_ptr a) {
+        if (a->is_constant()) return constant(gfb::erfi(a->value));
+        return detail::intern(op_t::erfi, a, nullptr, nullptr);
+    }
+///  x if x == x, else 0: the store rule of the reference's SAFE_MATH kernels
+///  (cpu_context.hpp:533-544, cuda_context.hpp:905-930) made available as a node.
+    inline leaf_ptr nan_to_zero(leaf_ptr a) {
+        if (a->is_constant()) return constant(a->value == a->value ? a->value : 0.0);
+        if (a->op == op_t::nan_to_zero) return a;
+        return detail::intern(op_t::nan_to_zero, a, nullptr, nullptr);
     }
     inline leaf_ptr pow(leaf_ptr a, leaf_ptr b) {
         if (a->is_constant() && b->is_constant()) return constant(std::pow(a->value, b->value));
@@ -742,6 +760,8 @@ namespace graph {
                 case op_t::sqrt: un([] (double a) { return std::sqrt(a); }); break;
                 case op_t::exp: un([] (double a) { return std::exp(a); }); break;
                 case op_t::log: un([] (double a) { return std::log(a); }); break;
+                case op_t::erfi: un([] (double a) { return gfb::erfi(a); }); break;
+                case op_t::nan_to_zero: un([] (double a) { return a == a ? a : 0.0; }); break;
                 case op_t::sin: un([] (double a) { return std::sin(a); }); break;
                 case op_t::cos: un([] (double a) { return std::cos(a); }); break;
                 case op_t::fma: {
@@ -818,6 +838,8 @@ namespace graph {
             case op_t::sqrt: r = div(a->df(x), mul(constant(2.0), self)); break;
             case op_t::exp: r = mul(self, a->df(x)); break;
             case op_t::log: r = div(a->df(x), a); break;
+            case op_t::erfi: r = mul(mul(constant(2.0/std::sqrt(M_PI)), exp(mul(a, a))), a->df(x)); break;
+            case op_t::nan_to_zero: r = nan_to_zero(a->df(x)); break;
             case op_t::pow: {
                 if (b->is_constant()) {
                     r = mul(mul(b, pow(a, constant(b->value - 1.0))), a->df(x));
@@ -860,6 +882,8 @@ namespace graph {
             case op_t::sqrt: return sqrt(a);
             case op_t::exp: return exp(a);
             case op_t::log: return log(a);
+            case op_t::erfi: return erfi(a);
+            case op_t::nan_to_zero: return nan_to_zero(a);
             case op_t::pow: return pow(a, b);
             case op_t::sin: return sin(a);
             case op_t::cos: return cos(a);
@@ -958,6 +982,8 @@ namespace graph {
                 case op_t::sqrt: accumulate(x, div(a, mul(constant(2.0), self))); break;
                 case op_t::exp: accumulate(x, mul(a, self)); break;
                 case op_t::log: accumulate(x, div(a, x)); break;
+                case op_t::erfi: accumulate(x, mul(a, mul(constant(2.0/std::sqrt(M_PI)), exp(mul(x, x))))); break;
+                case op_t::nan_to_zero: accumulate(x, a); break;
                 case op_t::pow:
                     if (y->is_constant()) {
                         accumulate(x, mul(a, mul(y, pow(x, constant(y->value - 1.0)))));
@@ -1002,7 +1028,7 @@ namespace graph {
 
     inline std::string leaf_node::to_string() {
         static const char *names[] = {"const", "var", "pseudo", "+", "-", "*", "/", "fma", "sqrt", "exp", "log",
-                                      "pow", "sin", "cos", "atan", "pw1d", "pw2d", "fourier"};
+                                      "pow", "sin", "cos", "atan", "pw1d", "pw2d", "fourier", "erfi", "nan0"};
         std::ostringstream s;
         s.precision(17);
         if (op == op_t::constant) { s << value; return s.str(); }

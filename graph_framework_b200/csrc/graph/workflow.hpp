@@ -160,6 +160,7 @@ namespace workflow {
         jit::context<T, SAFE_MATH> context;
         std::vector<std::unique_ptr<work_item<T, SAFE_MATH>>> preitems;
         std::vector<std::unique_ptr<work_item<T, SAFE_MATH>>> items;
+        std::vector<std::unique_ptr<work_item<T, SAFE_MATH>>> side_items;
         bool add_reduction;
     public:
         manager(const size_t index) : context(index), add_reduction(false) {}
@@ -200,10 +201,22 @@ namespace workflow {
                                                                               residual, name, size, context));
         }
 
+///  Extension: an item that shares this manager's device buffers but is NOT part of run(); it is
+///  launched on request with run_side(id).  Used for kernels that act between blocks of steps
+///  (absorption, diagnostics) on state that stays in HBM.
+        size_t add_side_item(graph::input_nodes<T, SAFE_MATH> in, graph::output_nodes<T, SAFE_MATH> out,
+                             graph::map_nodes<T, SAFE_MATH> maps, graph::shared_random_state<T, SAFE_MATH> state,
+                             const std::string name, const size_t size) {
+            side_items.push_back(std::make_unique<work_item<T, SAFE_MATH>> (in, out, maps, state, name, size, context));
+            return side_items.size() - 1;
+        }
+        void run_side(const size_t id) { side_items.at(id)->run(); }
+
         void compile() {
             context.compile(add_reduction);
             for (auto &item : preitems) item->create_kernel_call(context);
             for (auto &item : items) item->create_kernel_call(context);
+            for (auto &item : side_items) item->create_kernel_call(context);
         }
         void pre_run() { for (auto &item : preitems) item->run(); }
         void run() { for (auto &item : items) item->run(); }

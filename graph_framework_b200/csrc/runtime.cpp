@@ -45,8 +45,18 @@ namespace {
 const char *skeleton_text =
 #include "skeleton_text.inc"
 ;
+//  Special functions (erfi) are only compiled into modules that call them.
+const char *special_text =
+#include "special_text.inc"
+;
 
 thread_local std::string last_error;
+
+std::string full_source(const char *source) {
+    std::string text(skeleton_text);
+    if (std::strstr(source, "gfb::erfi(")) text += special_text;
+    return text + source;
+}
 
 //  GFB_DEBUG=1: trace every device-layer call and print a raw backtrace on SIGSEGV
 //  (resolve the offsets with addr2line on libgfb200.so).
@@ -338,7 +348,7 @@ int gfb_ctx_device_info(gfb_ctx *c, char *name, size_t name_len, int *sm_count, 
 int gfb_compile_to_cubin(const char *source, const char *options, void **cubin, size_t *cubin_size, char **log) {
     std::vector<char> image;
     std::string text;
-    const int r = nvrtc_compile(std::string(skeleton_text) + source, options, image, text);
+    const int r = nvrtc_compile(full_source(source), options, image, text);
     if (log) {
         const std::string &msg = r ? last_error : text;
         *log = static_cast<char *> (std::malloc(msg.size() + 1));
@@ -357,7 +367,7 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
     (void)names; (void)num_names;
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
     if (flush(c)) return 1;
-    c->source = std::string(skeleton_text) + source;
+    c->source = full_source(source);
     if (c->module) {
         cudaStreamSynchronize(c->stream);
         driver.ModuleUnload(c->module);

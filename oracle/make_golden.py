@@ -103,6 +103,22 @@ def defect_case():
     save("ref_defect_cold_plasma_efit", **out)
 
 
+def absorb_case():
+    """The absorption stages of xrays on an O-mode trajectory that crosses the electron cyclotron
+    fundamental of the EFIT case (w = 700: resonance near R = 2.06), and erfi on a grid."""
+    n = 32
+    s = workloads.efit_ensemble(n, seed=0)
+    records = reference.trace("ordinary_wave", "efit", s, 1.0e-3, 600, save_every=20, init="kx", solver="rk4")
+    out = reference.absorb("efit", records[:, :8])
+    save("ref_absorb_ordinary_wave_efit", state=workloads.pack(s), dt=np.array(1.0e-3), sub_steps=np.array(20),
+         records=records, **out)
+    rng = np.random.default_rng(11)
+    x = np.concatenate([[0.0, 1e-300, 1e-8, 0.01, 0.0308, 0.0309, 0.031, 0.5, 1.0, 26.6, 26.8, 26.9, 44.9, 45.0, 45.1,
+                         100.0, 1e6, 6e7, -1.3, -30.0], rng.uniform(-46, 46, 600), rng.uniform(-3, 3, 400)])
+    w_im, erfi = reference.erfi(x)
+    save("ref_erfi", x=x, w_im=w_im, erfi=erfi)
+
+
 if __name__ == "__main__":
     if not reference.available():
         raise SystemExit("oracle/_ref/ref_driver missing: run `make -C oracle ref` first")
@@ -119,3 +135,5 @@ if __name__ == "__main__":
         defect_case()
     if "vmec" in which:
         vmec_case()
+    if "absorb" in which:
+        absorb_case()

@@ -16,6 +16,9 @@ What it restates, with the reference lines it follows:
   * Newton initial solve                newton.hpp:42-50 + workflow.hpp:179-205
   * Boris push                          graph_korc/xkorc.cpp:66-103
   * deposition histogram                utilities/bin.py:53-106
+  * weak damping k_amp                  absorption.hpp:395-412 with dispersion.hpp:1010-1098 (cold expansion),
+                                        :1209-1290 (hot expansion), :289-305 (Z through erfi)
+  * power stage                         graph_driver/xrays.cpp:693-736
 
 The reference differentiates D symbolically; this restatement differentiates the SAME function D by
 the complex-step method (f(x + ih).imag/h, h = 1e-30), which is exact to rounding for the analytic
@@ -354,3 +357,96 @@ def deposit(x, y, z, weight, lo, hi, bins):
     ok = (fx >= 0) & (fx < bins[0]) & (fy >= 0) & (fy < bins[1]) & (fz >= 0) & (fz < bins[2])
     np.add.at(hist, (fx[ok].astype(int), fy[ok].astype(int), fz[ok].astype(int)), weight[ok])
     return hist
+
+
+def _expansion_terms(eq, w, k, x, y, z):
+    f = eq.fields(x, y, z)
+    b = f["b"]
+    bl = np.sqrt(_dot(b, b))
+    bh = (b[0]/bl, b[1]/bl, b[2]/bl)
+    ec = Q*bl/(ME*C)
+    wpe2 = f["ne"]*Q*Q/(EPSILON0*ME*C*C)
+    P = wpe2/(w*w)
+    q = P/(2.0*(1.0 + ec/w))
+    n = (k[0]/w, k[1]/w, k[2]/w)
+    n2 = _dot(n, n)
+    npara = _dot(n, bh)
+    npara2 = npara*npara
+    cr = _cross(bh, n)
+    nperp2 = _dot(cr, cr)
+    q_func = 1.0 - 2.0*q
+    n_func = n2 + npara2
+    p_func = 1.0 - P
+    gamma1 = (1.0 - q)*n2*nperp2 + p_func*(n2*npara2 - (1.0 - q)*n_func) + q_func*(p_func - nperp2)
+    return dict(f=f, ec=ec, P=P, q=q, n2=n2, npara=npara, npara2=npara2, nperp2=nperp2, q_func=q_func,
+                n_func=n_func, p_func=p_func, gamma1=gamma1)
+
+
+def cold_plasma_expansion(eq, w, kx, ky, kz, x, y, z):
+    """dispersion.hpp:1010-1098."""
+    e = _expansion_terms(eq, w, (kx, ky, kz), x, y, z)
+    gamma0 = e["nperp2"]*(e["n2"] - 2.0*e["q_func"]) + e["p_func"]*(2.0*e["q_func"] - e["n_func"])
+    return -e["P"]/2.0*(1.0 + e["ec"]/w)*gamma0 + (1.0 - e["ec"]*e["ec"]/(w*w))*e["gamma1"]
+
+
+def erfi_real(x):
+    """erfi for real x as the reference evaluates it (special_functions.hpp:1504-1512): overflow is
+    replaced by +-DBL_MAX above x^2 = 720.  scipy's erfi (an independent Faddeeva build) supplies the
+    values."""
+    from scipy.special import erfi
+    x = np.asarray(x, dtype=np.float64)
+    with np.errstate(over="ignore"):
+        return np.where(x*x > 720.0, np.copysign(np.finfo(np.float64).max, x), erfi(x))
+
+
+def hot_plasma_expansion(eq, w, kx, ky, kz, x, y, z):
+    """dispersion.hpp:1209-1290 with Z from z_erfi (:289-305); real arguments, complex result."""
+    e = _expansion_terms(eq, w, (kx, ky, kz), x, y, z)
+    ve = np.sqrt(2.0*Q*e["f"]["te"]/ME)
+    vtnorm = ve/C
+    ec, P, npara = e["ec"], e["P"], e["npara"]
+    with np.errstate(all="ignore"):
+        zeta = (1.0 - ec/w)/(npara*vtnorm)
+        Z = -np.sqrt(np.pi)*np.exp(-zeta*zeta)*(erfi_real(zeta) - 1j)
+        gamma5 = P*(e["n2"]*e["npara2"] - (1.0 - e["q"])*e["n_func"] + e["q_func"])
+        gamma2 = P*w/ec*e["nperp2"]*(e["n2"] - e["q_func"]) + \
+                 P*P*w*w/(4.0*ec*ec)*(e["n_func"] - 2.0*e["q_func"])*e["nperp2"]/e["npara2"]
+        D = -(1.0 + ec/w)*npara*vtnorm*(e["gamma1"] + gamma2 +
+                                         e["nperp2"]/(2.0*npara)*(w*w/(ec*ec))*vtnorm*zeta*gamma5)*(1.0/Z + zeta)
+    # Z underflows to 0 for |zeta| > 27.2 and 1/Z is 0/0; the reference's SAFE_MATH kernels deliver
+    # D = 0 there (cpu_context.hpp:533-544 stores NaN as 0; measured with oracle/_ref).
+    return np.where(np.isnan(D.real), 0.0, D.real) + 1j*np.where(np.isnan(D.imag), 0.0, D.imag)
+
+
+def weak_damping(eq, s):
+    """absorption.hpp:395-412 for Cartesian equilibria: complex k_amp per ray."""
+    base = {k: np.asarray(s[k], dtype=np.complex128) for k in ORDER}
+
+    def d(var):
+        p = dict(base)
+        p[var] = base[var] + 1j*H
+        return cold_plasma_expansion(eq, p["w"], p["kx"], p["ky"], p["kz"], p["x"], p["y"], p["z"]).imag/H
+
+    r = {k: np.asarray(s[k], dtype=np.float64) for k in ORDER}
+    klen = np.sqrt(r["kx"]**2 + r["ky"]**2 + r["kz"]**2)
+    with np.errstate(all="ignore"):
+        slope = (r["kx"]*d("kx") + r["ky"]*d("ky") + r["kz"]*d("kz"))/klen
+        Dw = hot_plasma_expansion(eq, r["w"], r["kx"], r["ky"], r["kz"], r["x"], r["y"], r["z"])
+        return klen - Dw/slope
+
+
+def power_stage(records_xyz, kamp_im):
+    """xrays.cpp:693-776: records_xyz [nrec, 3, n], kamp_im [nrec, n] -> power, d_power [nrec, n].
+    p_next uses k_sum before the current segment is added; record 0 is the initial state."""
+    nrec, _, n = records_xyz.shape
+    power = np.ones((nrec, n))
+    d_power = np.zeros((nrec, n))
+    k_sum = np.zeros(n)
+    with np.errstate(all="ignore"):
+        for j in range(1, nrec):
+            dl = np.sqrt(((records_xyz[j] - records_xyz[j - 1])**2).sum(axis=0))
+            p_next = np.exp(-2.0*k_sum)
+            d_power[j] = np.sqrt((p_next - power[j - 1])**2)
+            k_sum = kamp_im[j]*dl + k_sum
+            power[j] = p_next
+    return power, d_power

@@ -23,6 +23,16 @@
 //   ref_driver korc <equilibrium> <N> <nsteps> <in.bin> <out.bin>
 //       in.bin: 6 arrays x,y,z,ux,uy,uz (physical u/c, as xkorc.cpp:47-64); out: 7 arrays x,y,z,ux,uy,uz,gamma
 //   ref_driver source <dispersion> <equilibrium> <solver>     (dump kernel text; set GFB_ORACLE_KEEP_SOURCE=1)
+//   ref_driver absorb <equilibrium> <N> <nrec> <in.bin> <out.bin>
+//       in.bin : nrec records of 8 arrays t,w,x,y,z,kx,ky,kz (a trajectory as written by trace)
+//       out.bin: nrec records of 4 arrays  Re kamp, Im kamp, power, d_power.  kamp is the setter of
+//                absorption::weak_damping (absorption.hpp:395-412) evaluated through the reference's
+//                own JIT path with T = std::complex<double>, SAFE_MATH = true as xrays.cpp:1099-1104
+//                does; power/d_power follow the bin_power stage (xrays.cpp:674-793, T = double) fed
+//                with Im kamp (reference_imag_variable, xrays.cpp:743).  Record 0 holds power = 1,
+//                d_power = 0 (the state before the first bin_power kernel).
+//   ref_driver erfi <N> <in.bin> <out.bin>
+//       in: N doubles x; out: 2 arrays special::w_im(x), Re special::erfi(x + 0i) (special_functions.hpp)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -33,6 +43,7 @@
 #include <vector>
 
 #include "solver.hpp"
+#include "special_functions.hpp"
 #include "timing.hpp"
 
 #ifndef GFB_EFIT_FILE
@@ -303,6 +314,140 @@ static int korc(int argc, char **argv) {
     return 0;
 }
 
+//  The weak damping stage followed by the power stage, as xrays.cpp main() chains them.
+static int absorb(int argc, char **argv) {
+    typedef std::complex<double> C;
+    constexpr bool SAFE = true;
+    const std::string eqn = argv[2];
+    const size_t n = std::stoul(argv[3]);
+    const size_t nrec = std::stoul(argv[4]);
+    auto in = read_arrays(argv[5], 8*nrec, n);
+    std::ofstream out(argv[6], std::ios::binary);
+
+    std::vector<std::vector<double>> kre(nrec, std::vector<double> (n)), kim(nrec, std::vector<double> (n));
+    {
+        auto t = graph::variable<C, SAFE> (n, "t");
+        auto w = graph::variable<C, SAFE> (n, "\\omega");
+        auto x = graph::variable<C, SAFE> (n, "x");
+        auto y = graph::variable<C, SAFE> (n, "y");
+        auto z = graph::variable<C, SAFE> (n, "z");
+        auto kx = graph::variable<C, SAFE> (n, "k_{x}");
+        auto ky = graph::variable<C, SAFE> (n, "k_{y}");
+        auto kz = graph::variable<C, SAFE> (n, "k_{z}");
+        auto kamp = graph::variable<C, SAFE> (n, "kamp");
+        equilibrium::shared<C, SAFE> eq;
+        if (eqn == "efit") eq = equilibrium::make_efit<C, SAFE> (efit_path());
+        else if (eqn == "slab_density") eq = equilibrium::make_slab_density<C, SAFE> ();
+        else if (eqn == "slab") eq = equilibrium::make_slab<C, SAFE> ();
+        else { std::cerr << "absorb: unsupported equilibrium " << eqn << std::endl; return 2; }
+
+//  absorption.hpp:395-412, the weak_damping constructor body.
+        auto k_vec = kx*eq->get_esup1(x, y, z) + ky*eq->get_esup2(x, y, z) + kz*eq->get_esup3(x, y, z);
+        auto k_unit = k_vec->unit();
+        auto Dc = dispersion::cold_plasma_expansion<C, SAFE> ().D(w, k_vec, x, y, z, t, eq);
+        auto Dw = dispersion::hot_plasma_expansion<C, dispersion::z_erfi<C, SAFE>, SAFE> ().D(w, k_vec, x, y, z, t, eq);
+        auto kamp1 = k_vec->length() - Dw/k_unit->dot(Dc->df(kx)*eq->get_esup1(x, y, z) +
+                                                      Dc->df(ky)*eq->get_esup2(x, y, z) +
+                                                      Dc->df(kz)*eq->get_esup3(x, y, z));
+        graph::input_nodes<C, SAFE> inputs = {
+            graph::variable_cast(kamp), graph::variable_cast(kx), graph::variable_cast(ky), graph::variable_cast(kz),
+            graph::variable_cast(x), graph::variable_cast(y), graph::variable_cast(z), graph::variable_cast(t),
+            graph::variable_cast(w)
+        };
+        graph::map_nodes<C, SAFE> setters = {{kamp1, graph::variable_cast(kamp)}};
+        workflow::manager<C, SAFE> work(0);
+        work.add_item(inputs, {}, setters, graph::shared_random_state<C, SAFE> (), "weak_damping_kimg_kernel", n);
+        work.compile();
+
+        std::vector<graph::shared_leaf<C, SAFE>> order = {t, w, x, y, z, kx, ky, kz};
+        std::vector<C> buffer(n);
+        for (size_t j = 0; j < nrec; j++) {
+            for (size_t k = 0; k < 8; k++) {
+                for (size_t i = 0; i < n; i++) buffer[i] = C(in[8*j + k][i], 0.0);
+                graph::variable_cast(order[k])->set(buffer);
+                work.copy_to_device(order[k], graph::variable_cast(order[k])->data());
+            }
+            work.run();
+            work.wait();
+            work.copy_to_host(kamp, buffer.data());
+            for (size_t i = 0; i < n; i++) { kre[j][i] = std::real(buffer[i]); kim[j][i] = std::imag(buffer[i]); }
+        }
+    }
+
+//  xrays.cpp:693-776, the bin_power stage.
+    std::vector<std::vector<double>> power(nrec, std::vector<double> (n, 1.0)), d_power_rec(nrec, std::vector<double> (n, 0.0));
+    {
+        auto x = graph::variable<T> (n, "x");
+        auto y = graph::variable<T> (n, "y");
+        auto z = graph::variable<T> (n, "z");
+        auto x_last = graph::variable<T> (n, "x_last");
+        auto y_last = graph::variable<T> (n, "y_last");
+        auto z_last = graph::variable<T> (n, "z_last");
+        auto kamp = graph::variable<T> (n, "kamp");
+        auto pw = graph::variable<T> (n, static_cast<T> (1.0), "power");
+        auto k_sum = graph::variable<T> (n, static_cast<T> (0.0), "k_sum");
+        auto eq = make_eq(eqn);
+        auto dlvec = graph::vector(eq->get_x(x, y, z) - eq->get_x(x_last, y_last, z_last),
+                                   eq->get_y(x, y, z) - eq->get_y(x_last, y_last, z_last),
+                                   eq->get_z(x, y, z) - eq->get_z(x_last, y_last, z_last));
+        auto dl = dlvec->length();
+        auto kdl = kamp*dl;
+        auto k_next = kdl + k_sum;
+        auto p_next = graph::exp(-2.0*k_sum);
+        auto d_power = p_next - pw;
+        d_power = graph::sqrt(d_power*d_power);
+        workflow::manager<T> work(0);
+        work.add_item({graph::variable_cast(x), graph::variable_cast(y), graph::variable_cast(z),
+                       graph::variable_cast(x_last), graph::variable_cast(y_last), graph::variable_cast(z_last),
+                       graph::variable_cast(kamp), graph::variable_cast(pw), graph::variable_cast(k_sum)},
+                      {d_power},
+                      {{x, graph::variable_cast(x_last)}, {y, graph::variable_cast(y_last)}, {z, graph::variable_cast(z_last)},
+                       {p_next, graph::variable_cast(pw)}, {k_next, graph::variable_cast(k_sum)}},
+                      graph::shared_random_state<T> (), "power", n);
+        work.compile();
+        graph::variable_cast(x_last)->set(in[2]);
+        graph::variable_cast(y_last)->set(in[3]);
+        graph::variable_cast(z_last)->set(in[4]);
+        work.copy_to_device(x_last, graph::variable_cast(x_last)->data());
+        work.copy_to_device(y_last, graph::variable_cast(y_last)->data());
+        work.copy_to_device(z_last, graph::variable_cast(z_last)->data());
+        for (size_t j = 1; j < nrec; j++) {
+            graph::variable_cast(x)->set(in[8*j + 2]);
+            graph::variable_cast(y)->set(in[8*j + 3]);
+            graph::variable_cast(z)->set(in[8*j + 4]);
+            graph::variable_cast(kamp)->set(kim[j]);
+            work.copy_to_device(x, graph::variable_cast(x)->data());
+            work.copy_to_device(y, graph::variable_cast(y)->data());
+            work.copy_to_device(z, graph::variable_cast(z)->data());
+            work.copy_to_device(kamp, graph::variable_cast(kamp)->data());
+            work.run();
+            work.wait();
+            work.copy_to_host(pw, power[j].data());
+            work.copy_to_host(d_power, d_power_rec[j].data());
+        }
+    }
+    for (size_t j = 0; j < nrec; j++) {
+        for (auto *v : {&kre[j], &kim[j], &power[j], &d_power_rec[j]}) {
+            out.write(reinterpret_cast<const char *> (v->data()), sizeof(double)*n);
+        }
+    }
+    return 0;
+}
+
+static int erfi_values(int argc, char **argv) {
+    const size_t n = std::stoul(argv[2]);
+    auto in = read_arrays(argv[3], 1, n);
+    std::ofstream out(argv[4], std::ios::binary);
+    std::vector<double> a(n), b(n);
+    for (size_t i = 0; i < n; i++) {
+        a[i] = special::w_im<double> (in[0][i]);
+        b[i] = std::real(special::erfi<double> (std::complex<double> (in[0][i], 0.0)));
+    }
+    out.write(reinterpret_cast<const char *> (a.data()), sizeof(double)*n);
+    out.write(reinterpret_cast<const char *> (b.data()), sizeof(double)*n);
+    return 0;
+}
+
 #define DISPATCH_SOLVER(FN, DNAME, SNAME)                                                         \
     if (DNAME == "cold_plasma" && SNAME == "rk4") return FN<solver::rk4<dispersion::cold_plasma<T>>> (argc, argv);          \
     if (DNAME == "ordinary_wave" && SNAME == "rk4") return FN<solver::rk4<dispersion::ordinary_wave<T>>> (argc, argv);      \
@@ -330,6 +475,10 @@ int main(int argc, char **argv) {
         if (d == "simple") return rhs_impl<dispersion::simple<T>> (argc, argv);
     } else if (mode == "korc" && argc == 7) {
         return korc(argc, argv);
+    } else if (mode == "absorb" && argc == 7) {
+        return absorb(argc, argv);
+    } else if (mode == "erfi" && argc == 5) {
+        return erfi_values(argc, argv);
     }
     std::cerr << "bad arguments; see header of oracle/ref_driver.cpp" << std::endl;
     return 2;

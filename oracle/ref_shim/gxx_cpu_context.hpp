@@ -182,7 +182,7 @@ public:
                               const jit::register_usage &,
                               jit::texture1d_list &,
                               jit::texture2d_list &) {
-        const std::string type = jit::type_to_string<T> ();
+        const std::string type = jit::get_type_string<T> ();
         s << std::endl << "extern \"C\" void " << name << "(" << std::endl
           << "    map<size_t, " << type << " *> &args";
         if (state.get()) s << "," << std::endl << "    mt_state *" << jit::to_string('s', state.get());

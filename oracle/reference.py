@@ -28,6 +28,9 @@ def _run(args, timeout=7200, threads=None):
     env.setdefault("GFB_VMEC_FILE", os.path.join(ROOT, "tests", "golden", "vmec.gfbt"))
     if threads:
         env["GFB_ORACLE_THREADS"] = str(threads)
+#  Complex kernels (absorb) include the reference's special_functions.hpp: only where it exists.
+    if os.path.isdir("/root/reference/graph_framework"):
+        env.setdefault("GFB_REFERENCE_INCLUDE", "/root/reference/graph_framework")
     return subprocess.run([DRIVER] + [str(a) for a in args], cwd=ROOT, env=env, timeout=timeout,
                           check=True, capture_output=True, text=True).stdout
 
@@ -81,3 +84,27 @@ def korc(equilibrium, x, y, z, ux, uy, uz, nsteps):
         arr.tofile(fin)
         out = _run(["korc", equilibrium, n, nsteps, fin, fout])
         return np.fromfile(fout).reshape(7, n), json.loads(out.strip().splitlines()[-1])
+
+
+def absorb(equilibrium, records):
+    """records [nrec, 8, n] in the order t,w,x,y,z,kx,ky,kz -> dict of [nrec, n] arrays
+    kamp_re, kamp_im, power, d_power (ref_driver absorb: weak_damping then bin_power)."""
+    arr = np.ascontiguousarray(records, dtype=np.float64)
+    nrec, _, n = arr.shape
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        arr.tofile(fin)
+        _run(["absorb", equilibrium, n, nrec, fin, fout])
+        out = np.fromfile(fout).reshape(nrec, 4, n)
+    return {"kamp_re": out[:, 0], "kamp_im": out[:, 1], "power": out[:, 2], "d_power": out[:, 3]}
+
+
+def erfi(x):
+    """special::w_im(x), Re special::erfi(x + 0i) of the reference's special_functions.hpp."""
+    arr = np.ascontiguousarray(x, dtype=np.float64)
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        arr.tofile(fin)
+        _run(["erfi", arr.size, fin, fout])
+        out = np.fromfile(fout).reshape(2, arr.size)
+    return out[0], out[1]

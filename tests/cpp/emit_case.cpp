@@ -52,6 +52,38 @@ static jit::kernel_info build(const std::string &kind, equilibrium::shared<> eq,
     std::exit(2);
 }
 
+//  The two absorption kernels (absorption.hpp): emitted through a manager-less path so that no
+//  device is needed.  Argument orders match absorption::weak_damping / absorption::power_item.
+static jit::kernel_info build_absorption(const std::string &kind, equilibrium::shared<> eq, std::ostringstream &src,
+                                         const jit::emit_options &opt) {
+    const size_t n = 1;
+    auto w = graph::variable(n, "w"), kx = graph::variable(n, "kx"), ky = graph::variable(n, "ky"), kz = graph::variable(n, "kz");
+    auto x = graph::variable(n, "x"), y = graph::variable(n, "y"), z = graph::variable(n, "z"), t = graph::variable(n, "t");
+    if (kind == "kamp") {
+        auto kamp_re = graph::variable(n, "kamp_re"), kamp_im = graph::variable(n, "kamp_im");
+        auto k_vec = kx*eq->get_esup1(x, y, z) + ky*eq->get_esup2(x, y, z) + kz*eq->get_esup3(x, y, z);
+        auto Dc = dispersion::cold_plasma_expansion<> ().D(w, k_vec, x, y, z, t, eq);
+        auto Dw = dispersion::hot_plasma_expansion<> ().D_complex(w, k_vec, x, y, z, t, eq);
+        auto grad = graph::gradient(Dc, {kx, ky, kz});
+        auto slope = k_vec->unit()->dot(grad[0]*eq->get_esup1(x, y, z) + grad[1]*eq->get_esup2(x, y, z) +
+                                        grad[2]*eq->get_esup3(x, y, z));
+        graph::map_nodes<> setters = {{k_vec->length() - Dw.re/slope, kamp_re}, {-1.0*(Dw.im/slope), kamp_im}};
+        return jit::emit_item(src, opt, jit::kernel_kind::generic, "weak_damping_kimg_kernel",
+                              {kamp_re, kamp_im, kx, ky, kz, x, y, z, t, w}, {}, setters, n);
+    }
+    auto x_last = graph::variable(n, "x_last"), y_last = graph::variable(n, "y_last"), z_last = graph::variable(n, "z_last");
+    auto kamp = graph::variable(n, "kamp"), power = graph::variable(n, "power"), k_sum = graph::variable(n, "k_sum");
+    auto dl = graph::vector(eq->get_x(x, y, z) - eq->get_x(x_last, y_last, z_last),
+                            eq->get_y(x, y, z) - eq->get_y(x_last, y_last, z_last),
+                            eq->get_z(x, y, z) - eq->get_z(x_last, y_last, z_last))->length();
+    auto p_next = graph::exp(-2.0*k_sum);
+    auto difference = p_next - power;
+    graph::map_nodes<> setters = {{x, x_last}, {y, y_last}, {z, z_last}, {p_next, power}, {kamp*dl + k_sum, k_sum}};
+    return jit::emit_item(src, opt, jit::kernel_kind::generic, "power",
+                          {x, y, z, x_last, y_last, z_last, kamp, power, k_sum},
+                          {graph::sqrt(difference*difference)}, setters, n);
+}
+
 int main(int argc, char **argv) {
     if (argc < 5) { std::cerr << "usage: emit_case <dispersion> <equilibrium> <kind> <out.cu> [tables.bin] [efit.gfbt]" << std::endl; return 2; }
     const std::string d = argv[1], e = argv[2], kind = argv[3];
@@ -65,7 +97,8 @@ int main(int argc, char **argv) {
     if (const char *s = std::getenv("GFB_MINB")) opt.min_blocks = std::atoi(s);
     std::ostringstream src;
     jit::kernel_info info;
-    if (d == "cold_plasma") info = build<dispersion::cold_plasma<>> (kind, eq, src, opt);
+    if (kind == "kamp" || kind == "power") info = build_absorption(kind, eq, src, opt);
+    else if (d == "cold_plasma") info = build<dispersion::cold_plasma<>> (kind, eq, src, opt);
     else if (d == "ordinary_wave") info = build<dispersion::ordinary_wave<>> (kind, eq, src, opt);
     else if (d == "extra_ordinary_wave") info = build<dispersion::extra_ordinary_wave<>> (kind, eq, src, opt);
     else if (d == "bohm_gross") info = build<dispersion::bohm_gross<>> (kind, eq, src, opt);

@@ -7,6 +7,7 @@
 #include <vector>
 #include "cuda_stub.hpp"
 #include "../../graph_framework_b200/csrc/skeleton.cuh"
+#include "../../graph_framework_b200/csrc/special.cuh"
 namespace gfb { __attribute__((aligned(128))) unsigned char smem[256*1024]; }
 #ifndef GFB_UNROLL_STAGES
 #define GFB_UNROLL_STAGES 0

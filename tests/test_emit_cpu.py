@@ -43,9 +43,12 @@ def emit(tool, disp, eq, kind, tag, dt=None):
 
 def run_harness(cu, tab, kernel, arrays, n, steps, ni, no, tag, scalar=None):
     exe = os.path.join(BUILD, "harness_%s" % tag)
-    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", '-DGFB_KERNEL_FILE="%s"' % cu,
-                    "-DGFB_KERNEL_NAME=%s" % kernel, os.path.join(ROOT, "tests", "cpu_harness", "harness.cpp"),
-                    "-o", exe], check=True)
+    deps = [cu, os.path.join(ROOT, "tests", "cpu_harness", "harness.cpp"),
+            os.path.join(ROOT, "graph_framework_b200", "csrc", "skeleton.cuh"),
+            os.path.join(ROOT, "graph_framework_b200", "csrc", "special.cuh")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", '-DGFB_KERNEL_FILE="%s"' % cu,
+                        "-DGFB_KERNEL_NAME=%s" % kernel, deps[1], "-o", exe], check=True)
     fin, fout = os.path.join(BUILD, tag + "_in.bin"), os.path.join(BUILD, tag + "_out.bin")
     np.ascontiguousarray(arrays, dtype=np.float64).tofile(fin)
     cmd = [exe, tab, fin, fout, str(n), str(steps), str(ni), str(no)]
@@ -145,6 +148,76 @@ def test_nvrtc_compiles_for_sm_100a(lib, emit_tool, disp, eq, kind):
     assert rc == 0, msg
     image = ctypes.string_at(cubin, size.value)
     assert image[:4] == b"\x7fELF" and size.value > 4096
+    lib.gfb_free(cubin)
+    if log.value:
+        lib.gfb_free(log)
+
+
+#  Absorption.  Tolerances: Im k_amp carries exp(-zeta^2) with zeta^2 up to ~740 and
+#  zeta = (1 - w_ce/w)/(n_par v_t/c) is itself a cancellation, so its relative precision is
+#  ~zeta^2 * 1e-13; the absolute floor 1e-11 is 1e-14 of |k|.  Re k_amp is only compared where the
+#  reference's own value is defined (|zeta| < 26.6: above that erfi overflows, special_functions.hpp:1508).
+def absorption_zeta(records):
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import port
+    from graph_framework_b200.tools.gfbt import read_gfbt
+    eq = port.make_equilibrium("efit", read_gfbt(os.path.join(ROOT, "tests", "golden", "efit.gfbt")))
+    z = []
+    with np.errstate(all="ignore"):
+        for r in records:
+            s = dict(zip(port.ORDER, r[:8]))
+            e = port._expansion_terms(eq, s["w"], (s["kx"], s["ky"], s["kz"]), s["x"], s["y"], s["z"])
+            z.append((1.0 - e["ec"]/s["w"])/(e["npara"]*np.sqrt(2.0*port.Q*e["f"]["te"]/port.ME)/port.C))
+    return np.array(z)
+
+
+def assert_kamp_close(re, im, g, zeta, what=""):
+    assert np.isfinite(im).all() and np.isfinite(re).all(), what
+    assert np.max(np.abs(im - g["kamp_im"]) - 1.0e-8*np.abs(g["kamp_im"])) < 1.0e-11, what
+    ok = np.abs(zeta) < 26.6
+    assert ok.sum() > 0.4*ok.size
+    assert np.max(np.abs(re[ok] - g["kamp_re"][ok])/np.abs(g["kamp_re"][ok])) < 1.0e-10, what
+
+
+def test_emitted_absorption_kernels_match_reference(emit_tool):
+    """weak_damping_kimg_kernel and power (absorption.hpp / xrays.cpp bin_power) on the CPU harness
+    against the reference's own JIT kernels (complex<double>, SAFE_MATH) record by record."""
+    g = golden("ref_absorb_ordinary_wave_efit")
+    rec = g["records"]
+    nrec, _, n = rec.shape
+    zeta = absorption_zeta(rec)
+    cu, tab, info = emit(emit_tool, "none", "efit", "kamp", "kamp_efit")
+    assert "gfb::erfi(" in open(cu).read()
+    re, im = np.zeros((nrec, n)), np.zeros((nrec, n))
+    for j in range(nrec):
+        t, w, x, y, z, kx, ky, kz = rec[j][:8]
+        out = run_harness(cu, tab, "weak_damping_kimg_kernel", [np.zeros(n), np.zeros(n), kx, ky, kz, x, y, z, t, w],
+                          n, 1, 10, 0, "kamp_efit")
+        re[j], im[j] = out[0], out[1]
+    assert_kamp_close(re, im, g, zeta)
+    assert np.max(im) > 5.0                       # the case does cross the resonance
+
+    cu, tab, info = emit(emit_tool, "none", "efit", "power", "power_efit")
+    last, power, k_sum = rec[0][2:5].copy(), np.ones(n), np.zeros(n)
+    for j in range(1, nrec):
+        x, y, z = rec[j][2:5]
+        out = run_harness(cu, tab, "power", [x, y, z, last[0], last[1], last[2], g["kamp_im"][j], power, k_sum],
+                          n, 1, 9, 1, "power_efit")
+        last, power, k_sum = out[3:6].copy(), out[7], out[8]
+        assert np.array_equal(last, rec[j][2:5])
+        assert np.max(np.abs(power - g["power"][j])) < 1.0e-13
+        assert np.max(np.abs(out[9] - g["d_power"][j])) < 1.0e-13
+    assert 0.05 < power.min() < 0.6               # most of the power is absorbed by the last record
+
+
+@pytest.mark.parametrize("kind", ["kamp", "power"])
+def test_nvrtc_compiles_absorption_kernels(lib, emit_tool, kind):
+    cu, tab, info = emit(emit_tool, "none", "efit", kind, "nvrtc_" + kind)
+    cubin, size, log = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_void_p()
+    rc = lib.gfb_compile_to_cubin(open(cu).read().encode(), None, ctypes.byref(cubin), ctypes.byref(size), ctypes.byref(log))
+    assert rc == 0, ctypes.string_at(log).decode() if log.value else ""
+    assert ctypes.string_at(cubin, 4) == b"\x7fELF"
     lib.gfb_free(cubin)
     if log.value:
         lib.gfb_free(log)
