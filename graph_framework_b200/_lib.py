@@ -74,6 +74,9 @@ def _load():
         "gfb_rays_put_state": (I, [P, ctypes.POINTER(c_double_p)]),
         "gfb_rays_step_host": (I, [P, SZ, ctypes.POINTER(c_double_p), ctypes.POINTER(c_double_p), c_double_p, I]),
         "gfb_rays_trace": (I, [P, SZ, SZ, c_double_p]),
+        "gfb_rays_trace_absorb": (I, [P, SZ, SZ, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                      ctypes.POINTER(ctypes.c_int)]),
+        "gfb_rays_absorption_reset": (I, [P]),
         "gfb_rays_device_ptr": (I, [P, I, c_void_pp]),
         "gfb_rays_ctx": (P, [P]),
         "gfb_rays_source": (S, [P]),

@@ -204,6 +204,7 @@ struct run_options {
     jit::emit_options emit;
     int unroll_stages = -1;         // -1: decided by body size (jit::context::compile)
     unsigned fused_steps = 0;
+    bool absorption = false;
 };
 run_options parse_options(const char *options) {
     run_options o;
@@ -223,6 +224,7 @@ run_options parse_options(const char *options) {
         else if (k == "mode_unroll") o.emit.mode_loop_unroll = static_cast<unsigned> (v);
         else if (k == "unroll_stages") o.unroll_stages = v != 0 ? 1 : 0;
         else if (k == "fused_steps") o.fused_steps = static_cast<unsigned> (v);
+        else if (k == "absorption") o.absorption = v != 0;
     }
     return o;
 }
@@ -239,6 +241,33 @@ struct tracer_base {
     virtual leaf_ptr residual() = 0;
     virtual jit::context<> &context() = 0;
     virtual std::vector<leaf_ptr> rhs() = 0;
+    virtual workflow::manager<> &work() = 0;
+
+//  Absorption attached to the solver's device context (absorption.hpp): state that the
+//  Runge-Kutta kernel leaves in HBM is read in place.
+    leaf_ptr kamp_re, kamp_im, x_last, y_last, z_last, power, k_sum;
+    std::unique_ptr<absorption::weak_damping<>> damping;
+    std::unique_ptr<absorption::power_item<>> deposition;
+    size_t reset_item = 0;
+    void attach_absorption(equilibrium::shared<> &eq, const size_t n) {
+        auto s = state();
+        kamp_re = graph::variable(n, 0.0, "kamp_re");
+        kamp_im = graph::variable(n, 0.0, "kamp_im");
+        x_last = graph::variable(n, 0.0, "x_last");
+        y_last = graph::variable(n, 0.0, "y_last");
+        z_last = graph::variable(n, 0.0, "z_last");
+        power = graph::variable(n, 1.0, "power");
+        k_sum = graph::variable(n, 0.0, "k_sum");
+        damping = std::make_unique<absorption::weak_damping<>> (work(), kamp_re, kamp_im, s[GFB_W], s[GFB_KX], s[GFB_KY],
+                                                                 s[GFB_KZ], s[GFB_X], s[GFB_Y], s[GFB_Z], s[GFB_T], eq);
+        deposition = std::make_unique<absorption::power_item<>> (work(), s[GFB_X], s[GFB_Y], s[GFB_Z], x_last, y_last, z_last,
+                                                                  kamp_im, power, k_sum, eq);
+//  Start of a power calculation (xrays.cpp:745-755): X_last = X, power = 1, k_sum = 0.
+        reset_item = work().add_side_item({s[GFB_X], s[GFB_Y], s[GFB_Z], x_last, y_last, z_last, power, k_sum}, {},
+                                          {{s[GFB_X], x_last}, {s[GFB_Y], y_last}, {s[GFB_Z], z_last},
+                                           {graph::one(), power}, {graph::zero(), k_sum}},
+                                          graph::shared_random_state<> (), "power_reset", n);
+    }
 };
 
 template<class SOLVER>
@@ -266,6 +295,7 @@ struct tracer final : public tracer_base {
     void sync_device() override { solve.sync_device(); }
     leaf_ptr residual() override { return solve.get_residual(); }
     jit::context<> &context() override { return solve.get_work().get_context(); }
+    workflow::manager<> &work() override { return solve.get_work(); }
     std::vector<leaf_ptr> rhs() override {
         auto &D = solve.get_dispersion();
         return {D.get_dxdt(), D.get_dydt(), D.get_dzdt(), D.get_dkxdt(), D.get_dkydt(), D.get_dkzdt(), D.get_d()};
@@ -296,6 +326,8 @@ struct gfb_rays {
     std::vector<leaf_ptr> vars;       // t, w, x, y, z, kx, ky, kz
     std::unique_ptr<tracer_base> impl;
     bool compiled = false;
+    bool absorption_started = false;
+    char profile_tag = 0;             // its address keys the deposition profile buffer
     std::string source;
 };
 
@@ -343,6 +375,7 @@ gfb_rays *gfb_rays_create(const char *dispersion_name, const char *equilibrium_n
         return nullptr;
     }
     r->impl.reset(t);
+    if (o.absorption) t->attach_absorption(eq, num_rays);
     return r.release();
 }
 void gfb_rays_destroy(gfb_rays *r) { delete r; }
@@ -426,6 +459,55 @@ int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out
         if (gfb_snapshot_async(ctx, keys.data(), static_cast<int> (keys.size()), sizeof(double)*r->n,
                                out + b*keys.size()*r->n)) return 1;
     }
+    return gfb_wait(ctx);
+}
+int gfb_rays_absorption_reset(gfb_rays *r) {
+    if (!r->compiled) return rays_fail("absorption_reset before compile");
+    if (!r->impl->damping) return rays_fail("created without absorption=1");
+    r->impl->work().run_side(r->impl->reset_item);
+    r->absorption_started = true;
+    return 0;
+}
+int gfb_rays_trace_absorb(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *records, double *absorbed,
+                          double *profile, const double *lo, const double *hi, const int *bins) {
+    if (!r->compiled) return rays_fail("trace before compile");
+    if (!r->impl->damping) return rays_fail("created without absorption=1");
+    tracer_base &t = *r->impl;
+    gfb_ctx *ctx = t.context().device();
+    if (!r->absorption_started && gfb_rays_absorption_reset(r)) return 1;
+    std::vector<uint64_t> state_keys, absorb_keys;
+    for (auto &v : r->vars) state_keys.push_back(reinterpret_cast<uint64_t> (v.get()));
+    state_keys.push_back(reinterpret_cast<uint64_t> (t.residual().get()));
+    auto d_power = t.deposition->get_d_power();
+    for (auto v : {t.kamp_im, t.power, d_power}) absorb_keys.push_back(reinterpret_cast<uint64_t> (v.get()));
+
+    double *profile_device = nullptr;
+    const uint64_t profile_key = reinterpret_cast<uint64_t> (&r->profile_tag);
+    size_t cells = 0;
+    if (profile) {
+        if (!lo || !hi || !bins) return rays_fail("profile requested without lo/hi/bins");
+        cells = static_cast<size_t> (bins[0])*bins[1]*bins[2];
+        void *p = nullptr;
+        if (gfb_buffer(ctx, profile_key, sizeof(double)*cells, nullptr, &p)) return 1;
+        profile_device = static_cast<double *> (p);
+        if (gfb_copy_h2d(ctx, profile_key, profile, sizeof(double)*cells)) return 1;      // accumulate onto the caller's array
+    }
+    const double *xd = static_cast<const double *> (t.context().device_pointer(r->vars[GFB_X]));
+    const double *yd = static_cast<const double *> (t.context().device_pointer(r->vars[GFB_Y]));
+    const double *zd = static_cast<const double *> (t.context().device_pointer(r->vars[GFB_Z]));
+    const double *wd = static_cast<const double *> (t.context().device_pointer(d_power));
+    for (size_t b = 0; b < num_blocks; b++) {
+        t.step(sub_steps);
+        t.damping->run();
+        t.deposition->run();
+        if (profile && gfb_deposit(ctx, xd, yd, zd, wd, r->n, profile_device, lo, hi, bins)) return 1;
+        if (records && gfb_snapshot_async(ctx, state_keys.data(), static_cast<int> (state_keys.size()),
+                                          sizeof(double)*r->n, records + b*state_keys.size()*r->n)) return 1;
+        if (absorbed && gfb_snapshot_async(ctx, absorb_keys.data(), static_cast<int> (absorb_keys.size()),
+                                           sizeof(double)*r->n, absorbed + b*absorb_keys.size()*r->n)) return 1;
+    }
+    if (gfb_wait(ctx)) return 1;
+    if (profile && gfb_copy_d2h(ctx, profile_key, profile, sizeof(double)*cells)) return 1;
     return gfb_wait(ctx);
 }
 int gfb_rays_device_ptr(gfb_rays *r, int which, void **device_ptr) {

@@ -126,6 +126,33 @@ class RayTracer:
         check(lib.gfb_rays_trace(self.h, int(num_blocks), int(sub_steps), out.ctypes.data_as(c_double_p)), "trace")
         return out
 
+    def trace_absorb(self, num_blocks, sub_steps, bins=None, lo=None, hi=None, profile=None, records=True):
+        """Trace with power absorption (tracer created with options "absorption=1"): after every
+        block of sub_steps steps the weak-damping and power kernels of the reference driver's
+        second and third stage (absorption.hpp:395-412, xrays.cpp:693-736) run on the state in
+        device memory.  Returns (records [blocks, 9, n] or None, absorbed [blocks, 3, n] with rows
+        Im k_amp, power, d_power, profile [bins] or None).  `profile` continues an earlier one."""
+        rec = np.empty((num_blocks, 9, self.n), dtype=np.float64) if records else None
+        absorbed = np.empty((num_blocks, 3, self.n), dtype=np.float64)
+        args = [None, None, None, None]
+        if bins is not None:
+            bins = tuple(int(b) for b in bins)
+            profile = np.zeros(bins, dtype=np.float64) if profile is None else np.ascontiguousarray(profile, dtype=np.float64)
+            assert profile.shape == bins
+            lo_a, hi_a = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+            bins_a = (ctypes.c_int*3)(*bins)
+            args = [profile.ctypes.data_as(c_double_p), lo_a.ctypes.data_as(c_double_p),
+                    hi_a.ctypes.data_as(c_double_p), bins_a]
+        else:
+            profile = None
+        check(lib.gfb_rays_trace_absorb(self.h, int(num_blocks), int(sub_steps),
+                                        rec.ctypes.data_as(c_double_p) if records else None,
+                                        absorbed.ctypes.data_as(c_double_p), *args), "trace_absorb")
+        return rec, absorbed, profile
+
+    def absorption_reset(self):
+        check(lib.gfb_rays_absorption_reset(self.h), "absorption_reset")
+
     def rhs(self):
         """dx/dt, dy/dt, dz/dt, dkx/dt, dky/dt, dkz/dt, D at the current host state."""
         arrs = [np.empty(self.n, dtype=np.float64) for _ in range(7)]

@@ -8,20 +8,27 @@ Option names and meaning follow /root/reference/graph_driver/xrays.cpp:955-1037 
 xrays.cpp:413-529): one host thread per device, rays split batch/extra (xrays.cpp:423-432), initial
 conditions drawn per shard in the order w, kx, ky, kz, z, (x, y) (xrays.cpp:448-453), `--init_kx`
 etc. select the component solved from the dispersion relation, every `sub_steps` steps a record is
-written.  Differences: the random stream is numpy's (seeded with the shard index; the reference
-uses std::mt19937_64), equilibrium files are GFBT (tools/gfbt.py converts netCDF), results are
-result<shard>.gfbt with one (time, num_rays) variable per quantity, and the absorption and
-power stages (complex arithmetic) are not part of this back end.
+written.  With --absorption_model=weak_damping the second and third stage of the reference driver
+(calculate_power xrays.cpp:573-641, bin_power :674-793) and the binning of utilities/bin.py run on
+the device between blocks of steps instead of re-reading the result files; result files then also
+hold kamp (imaginary part), power and d_power, and bins.gfbt holds bins = sum(d_power)/num_rays with
+the bin edges xbins/ybins/zbins (bin.py:20-33, 106; options --num_x --min_x --max_x ... as bin.py).
+Differences: the random stream is numpy's (seeded with the shard index; the reference uses
+std::mt19937_64), equilibrium files are GFBT (tools/gfbt.py converts netCDF), results are
+result<shard>.gfbt with one (time, num_rays) variable per quantity; the root_find absorption model
+(complex root search) is not part of this back end.
 """
 import argparse
 import threading
 import time
 
+import os
+
 import numpy as np
 
 from ._lib import lib
 from .rays import RayTracer, STATE, shard_offsets
-from .tools.gfbt import write_trajectory
+from .tools.gfbt import write_gfbt, write_trajectory
 
 VARS = ("w", "kx", "ky", "kz", "x", "y", "z")
 
@@ -47,6 +54,11 @@ def parser():
         p.add_argument("--init_%s" % v, action="store_true", help="solve this component from the dispersion relation")
     p.add_argument("--use_cyl_xy", action="store_true")
     p.add_argument("--seed", action="store_true", help="fixed seeds (shard index), as the reference's --seed")
+    p.add_argument("--absorption_model", default="", choices=["", "weak_damping"])
+    for a, lo, hi in (("x", 0.0, 3.0), ("y", -3.0, 3.0), ("z", -3.0, 3.0)):
+        p.add_argument("--num_%s" % a, type=int, default=32)
+        p.add_argument("--min_%s" % a, type=float, default=lo)
+        p.add_argument("--max_%s" % a, type=float, default=hi)
     p.add_argument("--output", default="result", help="result<shard>.gfbt prefix")
     p.add_argument("--devices", type=int, default=0, help="0 = all")
     return p
@@ -77,18 +89,30 @@ def initial_conditions(args, shard, n):
 def trace_shard(args, shard, n, device, report):
     t0 = time.perf_counter()
     dt = args.endtime/args.num_times
+    absorb = args.absorption_model == "weak_damping"
     tr = RayTracer(args.dispersion, args.equilibrium, n, dt, solver=args.solver, table_file=args.equilibrium_file,
-                   device=device, options="fused_steps=%d" % args.sub_steps)
+                   device=device, options="fused_steps=%d absorption=%d" % (args.sub_steps, absorb))
     tr.set_state(initial_conditions(args, shard, n))
     solve_for = [v for v in ("kx", "ky", "kz") if getattr(args, "init_" + v)]
     tr.init(solve_for[0] if solve_for else "")
     tr.compile()
     t1 = time.perf_counter()
-    records = tr.trace(max(args.num_times//args.sub_steps, 1), args.sub_steps)
+    blocks = max(args.num_times//args.sub_steps, 1)
+    profile = None
+    if absorb:
+        bins = (args.num_x, args.num_y, args.num_z)
+        records, absorbed, profile = tr.trace_absorb(blocks, args.sub_steps, bins=bins,
+                                                     lo=(args.min_x, args.min_y, args.min_z),
+                                                     hi=(args.max_x, args.max_y, args.max_z))
+        records = np.concatenate([records, absorbed], axis=1)
+        names = ("t", "w", "x", "y", "z", "kx", "ky", "kz", "residual", "kamp", "power", "d_power")
+    else:
+        records = tr.trace(blocks, args.sub_steps)
+        names = ("t", "w", "x", "y", "z", "kx", "ky", "kz", "residual")
     t2 = time.perf_counter()
-    write_trajectory("%s%d.gfbt" % (args.output, shard), records)
+    write_trajectory("%s%d.gfbt" % (args.output, shard), records, names)
     tr.close()
-    report[shard] = {"rays": n, "setup_s": t1 - t0, "trace_s": t2 - t1, "records": records.shape[0],
+    report[shard] = {"profile": profile,"rays": n, "setup_s": t1 - t0, "trace_s": t2 - t1, "records": records.shape[0],
                      "max_residual": float(np.max(records[-1][8])) if n else 0.0}
 
 
@@ -110,6 +134,17 @@ def main(argv=None):
     total = time.perf_counter() - t0
     steps = max(args.num_times//args.sub_steps, 1)*args.sub_steps
     slowest = max(r["trace_s"] for r in report.values())
+    if args.absorption_model:
+#  bin.py:106: every shard's histogram summed, divided by the total number of rays.
+        total_profile = sum(r.pop("profile") for r in report.values())/float(args.num_rays)
+        write_gfbt(os.path.join(os.path.dirname(args.output), "bins.gfbt"),
+                   {"bins": total_profile,
+                    "xbins": np.linspace(args.min_x, args.max_x, args.num_x + 1),
+                    "ybins": np.linspace(args.min_y, args.max_y, args.num_y + 1),
+                    "zbins": np.linspace(args.min_z, args.max_z, args.num_z + 1)})
+    else:
+        for r in report.values():
+            r.pop("profile")
     print("xrays: %d rays x %d steps on %d device(s): trace %.3f s (%.3e ray-steps/s incl. output copies), total %.3f s"
           % (args.num_rays, steps, devices, slowest, args.num_rays*steps/slowest, total))
     if args.verbose:

@@ -34,6 +34,7 @@ enum { GFB_T = 0, GFB_W, GFB_X, GFB_Y, GFB_Z, GFB_KX, GFB_KY, GFB_KZ, GFB_NUM_ST
  * options    : NULL or space separated key=value list:
  *              block=<threads> minblocks=<n> stage_tables=<0|1> share_rcp=<0|1> fast_div=<0|1> unroll_stages=<0|1>
  *              fused_steps=<max steps per launch>
+ *              absorption=<0|1>  also build the weak-damping and power kernels (gfb_rays_trace_absorb)
  * Mirrors the constructor sequence of xrays_bench.cpp:53-85. */
 gfb_rays *gfb_rays_create(const char *dispersion, const char *equilibrium, const char *table_file,
                           const char *solver, size_t num_rays, double dt, int device, const char *options);
@@ -66,6 +67,21 @@ int gfb_rays_step_host(gfb_rays *r, size_t num_steps, const double *const state_
  * `out` receives num_blocks records of 9 arrays of num_rays doubles ([block][9][ray]); the
  * device->host transfer of block b overlaps the stepping of block b + 1.  Pinned memory recommended. */
 int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out);
+/* Trace with power absorption (options "absorption=1").  Replaces the second and third stage of the
+ * reference driver, which re-read the trajectory files: absorption::weak_damping
+ * (absorption.hpp:327-484, run per record at xrays.cpp:556-558) and bin_power (xrays.cpp:674-793),
+ * plus the binning of utilities/bin.py:53-106.  Per block: sub_steps RK steps, then on the state left
+ * in device memory  k_amp = |k| - D_warm/(k_hat . dD_cold/dk),  dl = |X - X_last|,
+ * p_next = exp(-2 k_sum), d_power = |p_next - power|, k_sum += Im k_amp dl, power = p_next.
+ *   records : NULL or [num_blocks][9][num_rays] as gfb_rays_trace
+ *   absorbed: NULL or [num_blocks][3][num_rays]  Im k_amp, power, d_power
+ *   profile : NULL or [bins[0]][bins[1]][bins[2]] doubles; d_power of every record is ADDED at the ray
+ *             position (half-open uniform bins between lo[3] and hi[3]); pass zeros to start
+ * The first call (or gfb_rays_absorption_reset) starts a power calculation at the current state:
+ * X_last = X, power = 1, k_sum = 0; further calls continue it. */
+int gfb_rays_trace_absorb(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *records, double *absorbed,
+                          double *profile, const double *lo, const double *hi, const int *bins);
+int gfb_rays_absorption_reset(gfb_rays *r);
 /* Device pointer of state array `which` (GFB_T..GFB_KZ) or of the residual (which = GFB_NUM_STATE). */
 int gfb_rays_device_ptr(gfb_rays *r, int which, void **device_ptr);
 /* The underlying device context (timers, launch counters, deposit, ...). */
