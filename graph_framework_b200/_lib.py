@@ -73,6 +73,8 @@ def _load():
         "gfb_rays_get_state": (I, [P, ctypes.POINTER(c_double_p), c_double_p]),
         "gfb_rays_put_state": (I, [P, ctypes.POINTER(c_double_p)]),
         "gfb_rays_step_host": (I, [P, SZ, ctypes.POINTER(c_double_p), ctypes.POINTER(c_double_p), c_double_p, I]),
+        "gfb_host_alloc": (I, [SZ, c_void_pp]),
+        "gfb_host_free": (I, [P]),
         "gfb_rays_trace": (I, [P, SZ, SZ, c_double_p]),
         "gfb_rays_trace_absorb": (I, [P, SZ, SZ, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                       ctypes.POINTER(ctypes.c_int)]),

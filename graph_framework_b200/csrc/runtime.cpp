@@ -760,6 +760,13 @@ int gfb_timer_stop(gfb_ctx *c, float *ms) {
 }
 void *gfb_stream(gfb_ctx *c) { return c->stream; }
 
+int gfb_host_alloc(size_t bytes, void **host_ptr) {
+    return check(cudaMallocHost(host_ptr, bytes ? bytes : 8), "cudaMallocHost") ? 1 : 0;
+}
+int gfb_host_free(void *host_ptr) {
+    return check(cudaFreeHost(host_ptr), "cudaFreeHost") ? 1 : 0;
+}
+
 int gfb_deposit(gfb_ctx *c, const double *x, const double *y, const double *z, const double *weight,
                 size_t n, double *hist, const double *lo, const double *hi, const int *bins) {
     if (flush(c)) return 1;

@@ -19,6 +19,29 @@ _DEFAULT_EFIT = os.path.join(_GOLDEN, "efit.gfbt")
 _DEFAULT_VMEC = os.path.join(_GOLDEN, "vmec.gfbt")
 
 
+class _Pinned:
+    """One page-locked allocation, released when the last numpy view of it is collected."""
+    def __init__(self, nbytes):
+        self.ptr = ctypes.c_void_p()
+        check(lib.gfb_host_alloc(int(nbytes), ctypes.byref(self.ptr)), "host_alloc")
+
+    def __del__(self):
+        if getattr(self, "ptr", None) is not None and self.ptr.value:
+            lib.gfb_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (cudaMallocHost through the C ABI): device<->host
+    copies into it run at full rate and overlap with kernels."""
+    count = int(np.prod(shape))
+    nbytes = max(count*np.dtype(dtype).itemsize, 8)
+    owner = _Pinned(nbytes)
+    buffer = (ctypes.c_byte*nbytes).from_address(owner.ptr.value)
+    buffer._owner = owner               # numpy keeps `buffer` alive through .base, and with it the owner
+    return np.frombuffer(buffer, dtype=dtype, count=count).reshape(shape)
+
+
 def _ptr_array(arrays, n):
     arr_t = c_double_p * n
     return arr_t(*[a.ctypes.data_as(c_double_p) if a is not None else None for a in arrays])
@@ -117,11 +140,7 @@ class RayTracer:
         The copy of block b overlaps the stepping of block b + 1; `out` may be a preallocated
         (pinned) array of that shape."""
         if out is None:
-            try:
-                import torch
-                out = torch.empty((num_blocks, 9, self.n), dtype=torch.float64).pin_memory().numpy()
-            except Exception:       # torch is plumbing only; plain pageable memory works too
-                out = np.empty((num_blocks, 9, self.n), dtype=np.float64)
+            out = pinned_empty((num_blocks, 9, self.n))
         assert out.shape == (num_blocks, 9, self.n) and out.dtype == np.float64 and out.flags.c_contiguous
         check(lib.gfb_rays_trace(self.h, int(num_blocks), int(sub_steps), out.ctypes.data_as(c_double_p)), "trace")
         return out
@@ -132,8 +151,8 @@ class RayTracer:
         second and third stage (absorption.hpp:395-412, xrays.cpp:693-736) run on the state in
         device memory.  Returns (records [blocks, 9, n] or None, absorbed [blocks, 3, n] with rows
         Im k_amp, power, d_power, profile [bins] or None).  `profile` continues an earlier one."""
-        rec = np.empty((num_blocks, 9, self.n), dtype=np.float64) if records else None
-        absorbed = np.empty((num_blocks, 3, self.n), dtype=np.float64)
+        rec = pinned_empty((num_blocks, 9, self.n)) if records else None
+        absorbed = pinned_empty((num_blocks, 3, self.n))
         args = [None, None, None, None]
         if bins is not None:
             bins = tuple(int(b) for b in bins)

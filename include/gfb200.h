@@ -122,6 +122,10 @@ int gfb_check_value(gfb_ctx *ctx, uint64_t key, size_t index, double *value);
  * gfb_wait() completes all outstanding snapshots. */
 int gfb_snapshot_async(gfb_ctx *ctx, const uint64_t *keys, int num_keys, size_t bytes_each, void *host_destination);
 
+/* Page-locked host memory for snapshot / step-from-host buffers (any thread, any context). */
+int gfb_host_alloc(size_t bytes, void **host_ptr);
+int gfb_host_free(void *host_ptr);
+
 /* Device timing on the context's stream (CUDA events). */
 int gfb_timer_start(gfb_ctx *ctx);
 int gfb_timer_stop(gfb_ctx *ctx, float *milliseconds);

@@ -1,5 +1,6 @@
 """Where does the xrays-style trace spend its time at 1e5 rays? (GPU box)"""
-import sys, time
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from graph_framework_b200.rays import RayTracer
 from graph_framework_b200 import workloads
