@@ -15,8 +15,11 @@ for opts in ("", "block=64", "block=256"):
         tr.step(blk); tr.wait()
         t0 = time.perf_counter(); tr.step(blk*10); tr.wait(); t1 = time.perf_counter()
         print("  step(%d) x10: %.3e ray-steps/s" % (blk, n*blk*10/(t1 - t0)))
-    t0 = time.perf_counter(); rec = tr.trace(10, 1000); t1 = time.perf_counter()
-    print("  trace(10,1000): %.3e ray-steps/s; finite %s" % (n*1e4/(t1 - t0), np.isfinite(rec[-1]).mean()))
+    for label in ("first", "second"):
+        t0 = time.perf_counter(); rec = tr.trace(10, 1000); t1 = time.perf_counter()
+        print("  %s trace(10,1000): %.3e ray-steps/s; finite %s" % (label, n*1e4/(t1 - t0), np.isfinite(rec[-1]).mean()))
+    t0 = time.perf_counter(); rec = tr.trace(10, 1000, out=rec); t1 = time.perf_counter()
+    print("  trace into the same pinned buffer: %.3e ray-steps/s" % (n*1e4/(t1 - t0)))
     s = tr.get_state()
     print("  R range after %g s: %.3f..%.3f" % (s["t"][0], np.hypot(s["x"], s["y"]).min(), np.hypot(s["x"], s["y"]).max()))
     tr.close()
