@@ -108,6 +108,7 @@ def _load():
         "graph_sqrt": (P, [P, P]),
         "graph_exp": (P, [P, P]),
         "graph_log": (P, [P, P]),
+        "graph_erfi": (P, [P, P]),
         "graph_pow": (P, [P, P, P]),
         "graph_sin": (P, [P, P]),
         "graph_cos": (P, [P, P]),

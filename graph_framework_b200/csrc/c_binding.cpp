@@ -104,6 +104,7 @@ GFB_BINARY(graph_atan, graph::atan(l, r))
 GFB_UNARY(graph_sqrt, graph::sqrt(a))
 GFB_UNARY(graph_exp, graph::exp(a))
 GFB_UNARY(graph_log, graph::log(a))
+GFB_UNARY(graph_erfi, graph::erfi(a))
 GFB_UNARY(graph_sin, graph::sin(a))
 GFB_UNARY(graph_cos, graph::cos(a))
 graph_node graph_fma(graph_c_context *c, graph_node a, graph_node b, graph_node d) {

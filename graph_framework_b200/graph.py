@@ -80,6 +80,7 @@ class Context:
     def sqrt(self, x): return Node(self, lib.graph_sqrt(self.c, x.h))
     def exp(self, x): return Node(self, lib.graph_exp(self.c, x.h))
     def log(self, x): return Node(self, lib.graph_log(self.c, x.h))
+    def erfi(self, x): return Node(self, lib.graph_erfi(self.c, x.h))
     def sin(self, x): return Node(self, lib.graph_sin(self.c, x.h))
     def cos(self, x): return Node(self, lib.graph_cos(self.c, x.h))
     def pow(self, x, y): return Node(self, lib.graph_pow(self.c, x.h, x._other(y).h))

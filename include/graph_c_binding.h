@@ -7,8 +7,10 @@
  *    - only type DOUBLE with use_safe_math == false is accepted (the FP64 ray
  *      path of the north star); other types make graph_construct_context
  *      return NULL and print why;
- *    - graph_random_state / graph_random / graph_erfi / graph_constant_c /
- *      graph_index_1D / graph_index_2D are not on the ray path and are absent.
+ *    - graph_random_state / graph_random / graph_constant_c / graph_index_1D /
+ *      graph_index_2D are not on the ray path and are absent;
+ *    - graph_erfi takes a real argument (the reference's needs a complex context;
+ *      ray state is real, special_functions.hpp:1504-1512 is the branch it takes).
  *  Nodes are opaque `void *`; identical expressions give identical pointers
  *  (the reference's c_binding_test.c:43-68 relies on that).
  *----------------------------------------------------------------------------*/
@@ -57,6 +59,7 @@ graph_node graph_fma(STRUCT_TAG graph_c_context *c, graph_node a, graph_node b, 
 graph_node graph_sqrt(STRUCT_TAG graph_c_context *c, graph_node arg);
 graph_node graph_exp(STRUCT_TAG graph_c_context *c, graph_node arg);
 graph_node graph_log(STRUCT_TAG graph_c_context *c, graph_node arg);
+graph_node graph_erfi(STRUCT_TAG graph_c_context *c, graph_node arg);      /* graph_c_binding.h:349 */
 graph_node graph_pow(STRUCT_TAG graph_c_context *c, graph_node left, graph_node right);
 graph_node graph_sin(STRUCT_TAG graph_c_context *c, graph_node arg);
 graph_node graph_cos(STRUCT_TAG graph_c_context *c, graph_node arg);

@@ -139,3 +139,19 @@ def test_xrays_driver_options_and_sampling():
     assert np.abs(np.arctan2(a["y"], a["x"])).max() < 0.3
     with pytest.raises(SystemExit):
         xrays.parser().parse_args(["--solver=euler"])
+
+
+def test_erfi_node_matches_reference_values(g):
+    """graph_erfi (real argument): host evaluation with this repository's own w_im fits against the
+    reference's special_functions.hpp values, and d/dx erfi = 2/sqrt(pi) exp(x^2)."""
+    from conftest import golden
+    ref = golden("ref_erfi")
+    x = g.variable(len(ref["x"]), "x", ref["x"])
+    mine = g.erfi(x).evaluate()
+    fin = np.isfinite(ref["erfi"]) & (ref["erfi"] != 0.0)
+    assert np.array_equal(np.isinf(mine), np.isinf(ref["erfi"]))
+    assert np.max(np.abs(mine[fin] - ref["erfi"][fin])/np.abs(ref["erfi"][fin])) < 5.0e-15
+    small = np.abs(ref["x"]) < 20.0
+    d = np.broadcast_to(g.erfi(x).df(x).evaluate(), ref["x"].shape)
+    assert np.allclose(d[small], 2.0/np.sqrt(np.pi)*np.exp(ref["x"][small]**2), rtol=1e-14)
+    assert g.erfi(g.constant(0.0)) == g.constant(0.0)

@@ -137,3 +137,40 @@ def test_port_deposit_matches_numpy_histogram():
     ok = (np.abs(x) < 1) & (np.abs(y) < 1) & (np.abs(z) < 1)
     ref, _ = np.histogramdd(np.stack([x[ok], y[ok], z[ok]], 1), bins=bins, range=list(zip(lo, hi)), weights=w[ok])
     assert np.allclose(h, ref, rtol=1e-12)
+
+
+def test_port_erfi_matches_reference():
+    """special::erfi for real arguments (special_functions.hpp:1504-1512, 545-562): the port's scipy
+    based evaluation against values produced by the reference's own header."""
+    from oracle import port
+    g = golden("ref_erfi")
+    mine = port.erfi_real(g["x"])
+    fin = np.isfinite(g["erfi"])
+    assert np.array_equal(np.isinf(mine), np.isinf(g["erfi"]))
+    assert rel_dev(mine[fin], g["erfi"][fin]) < 5.0e-15
+
+
+def test_port_absorption_matches_reference(efit):
+    """Weak damping k_amp and the power stage against the reference's own JIT kernels
+    (complex<double>, SAFE_MATH; oracle/_ref absorb mode).  Im k_amp carries exp(-zeta^2): relative
+    1e-8 with an absolute floor of 1e-11 (1e-14 of |k|); Re k_amp only where the reference value is
+    defined (|zeta| < 26.6, below the overflow of erfi)."""
+    from oracle import port
+    g = golden("ref_absorb_ordinary_wave_efit")
+    rec = g["records"]
+    k = np.array([port.weak_damping(efit, unpack(r[:8])) for r in rec])
+    assert np.isfinite(k.real).all() and np.isfinite(k.imag).all()
+    assert np.max(np.abs(k.imag - g["kamp_im"]) - 1.0e-8*np.abs(g["kamp_im"])) < 1.0e-11
+    with np.errstate(all="ignore"):
+        zeta = []
+        for r in rec:
+            s = unpack(r[:8])
+            e = port._expansion_terms(efit, s["w"], (s["kx"], s["ky"], s["kz"]), s["x"], s["y"], s["z"])
+            zeta.append((1.0 - e["ec"]/s["w"])/(e["npara"]*np.sqrt(2.0*port.Q*e["f"]["te"]/port.ME)/port.C))
+    ok = np.abs(np.array(zeta)) < 26.6
+    assert ok.mean() > 0.4
+    assert rel_dev(k.real[ok], g["kamp_re"][ok]) < 1.0e-11
+    power, d_power = port.power_stage(rec[:, 2:5], g["kamp_im"])
+    assert np.max(np.abs(power - g["power"])) < 1.0e-13
+    assert np.max(np.abs(d_power - g["d_power"])) < 1.0e-13
+    assert np.median(g["power"][-1]) < 0.6 and g["kamp_im"].max() > 5.0
