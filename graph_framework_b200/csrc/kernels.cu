@@ -54,20 +54,46 @@ __global__ void __launch_bounds__(256) max_kernel(const double *__restrict__ in,
     }
 }
 
+//  A traced beam is narrow: most lanes of a warp land in a handful of bins and, away from the
+//  resonance, carry a weight of exactly zero.  Zero weights are skipped (adding +0 changes nothing)
+//  and lanes with the same bin are summed in the warp first (match.any), so one atomic is issued per
+//  distinct bin per warp instead of one per ray.
 __global__ void __launch_bounds__(256) deposit_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                                       const double *__restrict__ z, const double *__restrict__ w,
                                                       const unsigned long long n, double *__restrict__ hist,
                                                       const double x0, const double y0, const double z0,
                                                       const double ix, const double iy, const double iz,
                                                       const int nx, const int ny, const int nz) {
-    for (unsigned long long i = static_cast<unsigned long long> (blockIdx.x)*blockDim.x + threadIdx.x; i < n;
-         i += static_cast<unsigned long long> (gridDim.x)*blockDim.x) {
-        const double fx = floor((__ldg(x + i) - x0)*ix);
-        const double fy = floor((__ldg(y + i) - y0)*iy);
-        const double fz = floor((__ldg(z + i) - z0)*iz);
-        if (fx >= 0.0 && fx < nx && fy >= 0.0 && fy < ny && fz >= 0.0 && fz < nz) {
-            const size_t bin = (static_cast<size_t> (fx)*ny + static_cast<size_t> (fy))*nz + static_cast<size_t> (fz);
-            atomicAdd(hist + bin, __ldg(w + i));
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long stride = static_cast<unsigned long long> (gridDim.x)*blockDim.x;
+    const unsigned long long rounded = (n + 31ull) & ~31ull;          // whole warps stay in the loop together
+    for (unsigned long long i = static_cast<unsigned long long> (blockIdx.x)*blockDim.x + threadIdx.x; i < rounded;
+         i += stride) {
+        bool active = false;
+        unsigned long long bin = 0;
+        double weight = 0.0;
+        if (i < n) {
+            weight = __ldg(w + i);
+            const double fx = floor((__ldg(x + i) - x0)*ix);
+            const double fy = floor((__ldg(y + i) - y0)*iy);
+            const double fz = floor((__ldg(z + i) - z0)*iz);
+            active = weight != 0.0 && fx >= 0.0 && fx < nx && fy >= 0.0 && fy < ny && fz >= 0.0 && fz < nz;
+            if (active) {
+                bin = (static_cast<unsigned long long> (fx)*ny + static_cast<unsigned long long> (fy))*nz +
+                      static_cast<unsigned long long> (fz);
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const unsigned peers = __match_any_sync(mask, bin);
+            const unsigned leader = __ffs(peers) - 1u;
+            double sum = 0.0;
+            for (unsigned rest = peers; rest; rest &= rest - 1u) {
+                sum += __shfl_sync(peers, weight, __ffs(rest) - 1);
+            }
+            if (lane == leader) {
+                atomicAdd(hist + bin, sum);
+            }
         }
     }
 }

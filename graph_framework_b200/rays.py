@@ -145,14 +145,20 @@ class RayTracer:
         check(lib.gfb_rays_trace(self.h, int(num_blocks), int(sub_steps), out.ctypes.data_as(c_double_p)), "trace")
         return out
 
-    def trace_absorb(self, num_blocks, sub_steps, bins=None, lo=None, hi=None, profile=None, records=True):
+    def trace_absorb(self, num_blocks, sub_steps, bins=None, lo=None, hi=None, profile=None, records=True,
+                     records_out=None, absorbed_out=None):
         """Trace with power absorption (tracer created with options "absorption=1"): after every
         block of sub_steps steps the weak-damping and power kernels of the reference driver's
         second and third stage (absorption.hpp:395-412, xrays.cpp:693-736) run on the state in
         device memory.  Returns (records [blocks, 9, n] or None, absorbed [blocks, 3, n] with rows
-        Im k_amp, power, d_power, profile [bins] or None).  `profile` continues an earlier one."""
-        rec = pinned_empty((num_blocks, 9, self.n)) if records else None
-        absorbed = pinned_empty((num_blocks, 3, self.n))
+        Im k_amp, power, d_power, profile [bins] or None).  `profile` continues an earlier one;
+        `records_out` / `absorbed_out` are preallocated (pinned) arrays of those shapes."""
+        rec = None
+        if records:
+            rec = records_out if records_out is not None else pinned_empty((num_blocks, 9, self.n))
+            assert rec.shape == (num_blocks, 9, self.n) and rec.dtype == np.float64 and rec.flags.c_contiguous
+        absorbed = absorbed_out if absorbed_out is not None else pinned_empty((num_blocks, 3, self.n))
+        assert absorbed.shape == (num_blocks, 3, self.n) and absorbed.dtype == np.float64 and absorbed.flags.c_contiguous
         args = [None, None, None, None]
         if bins is not None:
             bins = tuple(int(b) for b in bins)
