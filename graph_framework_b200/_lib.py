@@ -115,6 +115,8 @@ def _load():
         "graph_atan": (P, [P, P, P]),
         "graph_piecewise_1D": (P, [P, P, D, D, P, SZ]),
         "graph_piecewise_2D": (P, [P, SZ, P, D, D, P, D, D, P, SZ]),
+        "graph_index_1D": (P, [P, P, P, D, D]),
+        "graph_index_2D": (P, [P, P, SZ, P, D, D, P, D, D]),
         "graph_df": (P, [P, P, P]),
         "graph_get_max_concurrency": (SZ, [P]),
         "graph_set_device_number": (None, [P, SZ]),

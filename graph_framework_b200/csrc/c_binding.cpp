@@ -124,6 +124,15 @@ graph_node graph_piecewise_2D(graph_c_context *c, const size_t num_cols,
                                              cast(c)->get(x_arg), x_scale, x_offset,
                                              cast(c)->get(y_arg), y_scale, y_offset));
 }
+graph_node graph_index_1D(graph_c_context *c, graph_node variable, graph_node arg, const double scale, const double offset) {
+    return cast(c)->keep(graph::index_1D(cast(c)->get(variable), cast(c)->get(arg), scale, offset));
+}
+graph_node graph_index_2D(graph_c_context *c, graph_node variable, const size_t num_cols,
+                          graph_node x_arg, const double x_scale, const double x_offset,
+                          graph_node y_arg, const double y_scale, const double y_offset) {
+    return cast(c)->keep(graph::index_2D(cast(c)->get(variable), num_cols, cast(c)->get(x_arg), x_scale, x_offset,
+                                         cast(c)->get(y_arg), y_scale, y_offset));
+}
 graph_node graph_df(graph_c_context *c, graph_node fnode, graph_node xnode) {
     return cast(c)->keep(cast(c)->get(fnode)->df(cast(c)->get(xnode)));
 }

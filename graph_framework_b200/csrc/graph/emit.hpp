@@ -46,6 +46,7 @@ namespace jit {
         size_t smem_offset;             ///< byte offset in dynamic shared memory
         std::vector<double> packed;     ///< cells*stride doubles, cell major
         bool raw = false;               ///< packed was filled by the emitter (Fourier tables), do not repack
+        int alias_input = -1;           ///< >= 0: no table of its own, the pointer of that kernel input (index_1D/2D)
         size_t bytes() const { return packed.size()*sizeof(double); }
     };
 
@@ -77,7 +78,9 @@ namespace jit {
         graph::input_nodes<> inputs;
         graph::output_nodes<> outputs;          ///< one device buffer each, after the inputs
         std::vector<bool> input_written;
-        std::vector<table_group> groups;        ///< pointer slots after the outputs
+        std::vector<bool> input_loaded;         ///< false: only reached through index_1D/2D, never loaded per ray
+        bool indexed_written = false;           ///< an indexed input is also a setter target: steps must not be fused
+        std::vector<table_group> groups;        ///< pointer slots after the outputs (alias groups own none)
         size_t size;
         size_t smem_bytes;
         size_t num_statements;
@@ -205,6 +208,36 @@ namespace jit {
                 sets[j].members.push_back(n);
                 floop_of[n] = l;
             }
+            if (n->is_index()) {
+                const graph::leaf_node *var = n->args[0].get();
+                int j = -1;
+                for (size_t i = 0; i < info.inputs.size(); i++) if (info.inputs[i].get() == var) j = static_cast<int> (i);
+                if (j < 0) {
+                    std::cerr << "Kernel " << info.name << ": indexed variable " << var->symbol
+                              << " is not an input." << std::endl;
+                    std::exit(-1);
+                }
+                size_t g = 0;
+                for (; g < info.groups.size(); g++) if (info.groups[g].alias_input == j) break;
+                if (g == info.groups.size()) {
+                    table_group grp;
+                    grp.op = n->op;
+                    grp.num_cols = 0;
+                    grp.cells = var->size();
+                    grp.stride = 1;
+                    grp.staged = false;
+                    grp.smem_offset = 0;
+                    grp.raw = true;
+                    grp.alias_input = j;
+                    info.groups.push_back(grp);
+                }
+                slot[n] = {g, 0};
+                if (info.input_written[j]) info.indexed_written = true;
+//  The array itself is not a per-ray value: only the index arguments are expressions.
+                scan(n->args[1].get());
+                if (n->op == graph::op_t::index_2d) scan(n->args[2].get());
+                return;
+            }
             if (n->is_piecewise()) {
                 const graph::leaf_node *a0 = strip(n->args[0].get());
                 const graph::leaf_node *a1 = n->args[1].get() ? strip(n->args[1].get()) : nullptr;
@@ -239,6 +272,7 @@ namespace jit {
             size_t staged_total = 0;
             size_t offset = 16;     // mbarrier lives in the first 16 bytes
             for (auto &g : info.groups) {
+                if (g.alias_input >= 0) continue;
                 if (g.raw) {
 //  Fourier tables keep their layout; the small [mode][2] mode-number table is staged.
                     if (g.packed.size() & 1) g.packed.push_back(0.0);
@@ -384,6 +418,23 @@ namespace jit {
             if (n->op == op_t::fourier) {
                 emit_fourier_loop(floops[floop_of.at(n)]);
                 return reg.at(n);
+            }
+            if (n->is_index()) {
+                const size_t g = slot.at(n).first;
+                const size_t length = info.groups[g].cells;
+                const std::string x = emit(n->args[1].get());
+                std::string expr;
+                if (n->op == op_t::index_1d) {
+                    expr = index_expr(x, n->scale[0], n->offset[0], length);
+                } else {
+                    const std::string y = emit(n->args[2].get());
+                    expr = index_expr(x, n->scale[0], n->offset[0], length/n->num_cols) + "*" +
+                           std::to_string(n->num_cols) + "u + " + index_expr(y, n->scale[1], n->offset[1], n->num_cols);
+                }
+                const std::string name = "t" + std::to_string(n->id);
+                out << "        const double " << name << " = tg[" << g << "][" << expr << "];" << std::endl;
+                info.num_statements++;
+                return reg.emplace(n, name).first->second;
             }
             if (n->is_piecewise()) {
                 const auto [g, m] = slot.at(n);
@@ -545,13 +596,26 @@ namespace jit {
             table_fn("bool", "group_staged", [] (const table_group &g) { return g.staged ? "true" : "false"; });
             table_fn("unsigned", "group_offset", [] (const table_group &g) { return std::to_string(g.smem_offset) + "u"; });
             table_fn("unsigned", "group_bytes", [] (const table_group &g) { return std::to_string(g.bytes()) + "u"; });
+//  Pointer slot of each group: own table buffers follow the outputs; an alias group is a kernel input.
+            {
+                std::vector<size_t> slots;
+                size_t own = 0;
+                for (auto &g : info.groups) slots.push_back(g.alias_input >= 0 ? static_cast<size_t> (g.alias_input) : np + own++);
+                out << "    __device__ static constexpr int group_slot(const int g) { return ";
+                for (size_t g = 0; g < ng; g++) out << "g == " << g << " ? " << slots[g] << " : ";
+                out << "0; }" << std::endl;
+            }
+            info.input_loaded.assign(ni, true);
+            for (size_t j = 0; j < ni; j++) info.input_loaded[j] = visited.count(info.inputs[j].get()) != 0;
             out << "    __device__ static constexpr int ev(const int e) { return ";
             for (size_t e = 0; e < evolved.size(); e++) out << "e == " << e << " ? " << evolved[e] << " : ";
             out << "0; }" << std::endl;
 
             out << "    __device__ static __forceinline__ void load(double (&v)[NI + 1], const gfb_args &a, const unsigned long long i) {" << std::endl;
             for (size_t j = 0; j < ni; j++) {
-                if (info.input_written[j]) {
+                if (!info.input_loaded[j]) {
+                    continue;       // reached through index nodes only (or write-only): its length need not match
+                } else if (info.input_written[j]) {
                     out << "        v[" << j << "] = a.ptr[" << j << "][i];" << std::endl;
                 } else {
                     out << "        v[" << j << "] = __ldg(a.ptr[" << j << "] + i);" << std::endl;

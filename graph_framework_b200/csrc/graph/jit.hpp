@@ -175,17 +175,21 @@ namespace jit {
                 keys.push_back(key(out));
             }
             for (auto &g : k.groups) {
+                if (g.alias_input >= 0) continue;           // index_1D/2D read a kernel input in place
                 const uint64_t tk = 0x8000000000000000ull | next_table_key++;
                 check(gfb_buffer(gpu, tk, g.bytes(), g.packed.data(), nullptr), "table buffer");
                 keys.push_back(tk);
             }
             bool can_repeat = false;
             for (const bool w : k.input_written) can_repeat = can_repeat || w;
+//  A kernel that gathers from an array it also rewrites needs a grid-wide boundary between steps:
+//  mode 2 = one launch per step.
+            const int repeat_mode = k.indexed_written ? 2 : (can_repeat ? 1 : 0);
             gfb_kernel *handle = nullptr;
             check(gfb_kernel_create(gpu, kernel_name.c_str(), keys.data(), static_cast<int> (keys.size()),
                                     num_rays, options.block_size, k.smem_bytes,
                                     k.kind == kernel_kind::generic ? 0 : (k.kind == kernel_kind::newton ? 2 : 1),
-                                    can_repeat ? 1 : 0, &handle), "kernel create");
+                                    repeat_mode, &handle), "kernel create");
             handles[kernel_name] = handle;
             return handle;
         }

@@ -90,7 +90,8 @@ namespace graph {
         sin, cos, atan,
         piecewise_1d, piecewise_2d,
         fourier,
-        erfi, nan_to_zero
+        erfi, nan_to_zero,
+        index_1d, index_2d
     };
 
     class leaf_node;
@@ -162,7 +163,7 @@ namespace graph {
                 case op_t::pseudo: case op_t::sqrt: case op_t::exp: case op_t::log:
                 case op_t::sin: case op_t::cos: case op_t::piecewise_1d: case op_t::erfi:
                 case op_t::nan_to_zero: return 1;
-                case op_t::fma: case op_t::fourier: return 3;
+                case op_t::fma: case op_t::fourier: case op_t::index_2d: return 3;
                 default: return 2;
             }
         }
@@ -170,6 +171,7 @@ namespace graph {
         bool is_constant() const { return op == op_t::constant; }
         bool is_constant(const double v) const { return op == op_t::constant && value == v; }
         bool is_piecewise() const { return op == op_t::piecewise_1d || op == op_t::piecewise_2d; }
+        bool is_index() const { return op == op_t::index_1d || op == op_t::index_2d; }
 
 //  -- reference API -----------------------------------------------------------
 ///  Host evaluation (node.hpp:378 evaluate()).
@@ -610,6 +612,30 @@ namespace graph {
     }
 
 //------------------------------------------------------------------------------
+///  index_1D / index_2D: gather from a VARIABLE (a device array that kernels may rewrite between
+///  launches) with the piecewise index rule (piecewise.hpp:1436-1640, 1776-2010):
+///      index_1D(v, x) = v[trunc(clamp((x - offset)/scale, 0, size - 1))]
+///      index_2D(v, x, y) = v[i_x*num_cols + i_y].
+///  The indexed variable may have any length; a kernel that only indexes it never loads it per ray.
+///  df() is 1 with respect to the node itself and 0 otherwise (piecewise.hpp:1475-1477).
+//------------------------------------------------------------------------------
+    template<typename T=double, bool SAFE_MATH=false>
+    shared_leaf<T, SAFE_MATH> index_1D(shared_leaf<T, SAFE_MATH> variable, shared_leaf<T, SAFE_MATH> x,
+                                       const T scale, const T offset) {
+        assert(variable_cast(variable).get() && "index_1D needs a variable to index.");
+        return detail::intern(op_t::index_1d, variable, x, nullptr, 0.0, table_ptr(), 0, {scale, 0.0}, {offset, 0.0});
+    }
+    template<typename T=double, bool SAFE_MATH=false>
+    shared_leaf<T, SAFE_MATH> index_2D(shared_leaf<T, SAFE_MATH> variable, const size_t num_cols,
+                                       shared_leaf<T, SAFE_MATH> x, const T x_scale, const T x_offset,
+                                       shared_leaf<T, SAFE_MATH> y, const T y_scale, const T y_offset) {
+        assert(variable_cast(variable).get() && "index_2D needs a variable to index.");
+        assert(variable->size()%num_cols == 0 && "Variable size must be a multiple of the number of columns.");
+        return detail::intern(op_t::index_2d, variable, x, y, 0.0, table_ptr(), num_cols,
+                              {x_scale, y_scale}, {x_offset, y_offset});
+    }
+
+//------------------------------------------------------------------------------
 ///  Fourier series with radial spline amplitudes -- the building block of the VMEC equilibrium
 ///  (equilibrium.hpp:2120-2151 sums 86 modes of  spline_mn(s) * {cos, sin}(m u - n v)).
 ///
@@ -779,6 +805,24 @@ namespace graph {
                     un([&] (double a) { return t[table_index(a, n->scale[0], n->offset[0], t.size())]; });
                     break;
                 }
+                case op_t::index_1d: {
+                    const auto &t = n->args[0]->buffer;
+                    const auto &a = eval(n->args[1].get(), memo);
+                    out.resize(a.size());
+                    for (size_t i = 0; i < a.size(); i++) out[i] = t[table_index(a[i], n->scale[0], n->offset[0], t.size())];
+                    break;
+                }
+                case op_t::index_2d: {
+                    const auto &t = n->args[0]->buffer;
+                    const auto &a = eval(n->args[1].get(), memo);
+                    const auto &b = eval(n->args[2].get(), memo);
+                    const size_t rows = t.size()/n->num_cols, sz = std::max(a.size(), b.size());
+                    out.resize(sz);
+                    for (size_t i = 0; i < sz; i++)
+                        out[i] = t[table_index(a[a.size() == 1 ? 0 : i], n->scale[0], n->offset[0], rows)*n->num_cols +
+                                   table_index(b[b.size() == 1 ? 0 : i], n->scale[1], n->offset[1], n->num_cols)];
+                    break;
+                }
                 case op_t::fourier: {
                     const auto &a = eval(n->args[0].get(), memo);
                     const auto &b = eval(n->args[1].get(), memo);
@@ -814,7 +858,7 @@ namespace graph {
 //------------------------------------------------------------------------------
     inline leaf_ptr leaf_node::df(leaf_ptr x) {
         if (x.get() == this) return one();
-        if (op == op_t::constant || op == op_t::variable || op == op_t::pseudo || is_piecewise()) return zero();
+        if (op == op_t::constant || op == op_t::variable || op == op_t::pseudo || is_piecewise() || is_index()) return zero();
         auto &memo = detail::caches().df;
         const auto k = std::make_pair(static_cast<const leaf_node *> (this), static_cast<const leaf_node *> (x.get()));
         auto it = memo.find(k);
@@ -891,7 +935,7 @@ namespace graph {
             case op_t::pseudo: return pseudo_variable(a);
             case op_t::piecewise_1d: case op_t::piecewise_2d:
                 return detail::intern(n->op, a, b, nullptr, 0.0, n->table, n->num_cols, n->scale, n->offset);
-            case op_t::fourier:
+            case op_t::fourier: case op_t::index_1d: case op_t::index_2d:
                 return detail::intern(n->op, a, b, c, 0.0, n->table, n->num_cols, n->scale, n->offset);
             default: return std::const_pointer_cast<leaf_node> (n->shared_from_this());
         }
@@ -945,7 +989,7 @@ namespace graph {
         std::function<void(leaf_node *)> visit = [&] (leaf_node *n) {
             if (seen[n]) return;
             seen[n] = true;
-            if (n->op != op_t::pseudo && !n->is_piecewise()) {
+            if (n->op != op_t::pseudo && !n->is_piecewise() && !n->is_index()) {
                 for (size_t i = 0, ie = n->num_args(); i < ie; i++) visit(n->args[i].get());
             }
             order.push_back(n);
@@ -1028,7 +1072,7 @@ namespace graph {
 
     inline std::string leaf_node::to_string() {
         static const char *names[] = {"const", "var", "pseudo", "+", "-", "*", "/", "fma", "sqrt", "exp", "log",
-                                      "pow", "sin", "cos", "atan", "pw1d", "pw2d", "fourier", "erfi", "nan0"};
+                                      "pow", "sin", "cos", "atan", "pw1d", "pw2d", "fourier", "erfi", "nan0", "idx1d", "idx2d"};
         std::ostringstream s;
         s.precision(17);
         if (op == op_t::constant) { s << value; return s.str(); }

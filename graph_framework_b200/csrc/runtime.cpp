@@ -204,6 +204,7 @@ struct gfb_kernel {
     size_t smem;
     int kind;
     bool can_repeat;
+    bool serial = false;            // every step is its own launch (the kernel gathers from an array it rewrites)
 };
 
 struct gfb_ctx {
@@ -518,7 +519,8 @@ int gfb_kernel_create(gfb_ctx *c, const char *name, const uint64_t *ptr_keys, in
     if (k->grid == 0) k->grid = 1;
     k->smem = dynamic_smem;
     k->kind = kind;
-    k->can_repeat = can_repeat != 0;
+    k->can_repeat = can_repeat == 1;
+    k->serial = can_repeat == 2;
     if (dynamic_smem > 48*1024) {
         if (check_cu(driver.FuncSetAttribute(k->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                              static_cast<int> (dynamic_smem)), "smem attribute")) return 1;
@@ -531,6 +533,10 @@ int gfb_kernel_create(gfb_ctx *c, const char *name, const uint64_t *ptr_keys, in
 int gfb_kernel_run(gfb_kernel *k) {
     GFB_TRACE("kernel_run %s", k->name.c_str());
     gfb_ctx *c = k->ctx;
+    if (k->serial) {
+        if (flush(c)) return 1;
+        return launch_now(k, 1);
+    }
     if (c->pending == k && c->pending_steps < c->max_fused && (k->kind != 2)) {
         c->pending_steps++;
         return 0;
@@ -546,6 +552,10 @@ int gfb_kernel_run(gfb_kernel *k) {
 
 int gfb_kernel_launch(gfb_kernel *k, unsigned steps) {
     if (flush(k->ctx)) return 1;
+    if (k->serial) {
+        for (unsigned s = 0; s < steps; s++) if (launch_now(k, 1)) return 1;
+        return 0;
+    }
     return launch_now(k, steps);
 }
 

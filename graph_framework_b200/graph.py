@@ -96,6 +96,12 @@ class Context:
         return Node(self, lib.graph_piecewise_2D(self.c, num_cols, x.h, x_scale, x_offset, y.h, y_scale, y_offset,
                                                  a.ctypes.data_as(ctypes.c_void_p), a.size))
 
+    def index_1D(self, variable, arg, scale, offset):
+        return Node(self, lib.graph_index_1D(self.c, variable.h, arg.h, scale, offset))
+
+    def index_2D(self, variable, num_cols, x, x_scale, x_offset, y, y_scale, y_offset):
+        return Node(self, lib.graph_index_2D(self.c, variable.h, num_cols, x.h, x_scale, x_offset, y.h, y_scale, y_offset))
+
     @staticmethod
     def _arr(nodes):
         t = ctypes.c_void_p*max(len(nodes), 1)

@@ -70,8 +70,10 @@ int gfb_buffer_lookup(gfb_ctx *ctx, uint64_t key, void **device_ptr, size_t *byt
 /* cuda_context::create_kernel_call  (cuda_context.hpp:316-531).
  * ptr_keys: buffer keys in kernel pointer order (inputs, outputs, table groups).
  * kind: 0 generic item, 1 runge-kutta item, 2 device-resident Newton item.
- * can_repeat: non-zero when repeated runs may be fused into one multi-step launch
- * (the item has setters); zero makes repeated runs collapse to a single step. */
+ * can_repeat: 1 when repeated runs may be fused into one multi-step launch (the item has
+ * setters and each ray only reads its own state); 0 makes repeated runs collapse to a single
+ * step (no setters: the item is idempotent); 2 launches every run separately (the item gathers
+ * from an array it also rewrites, so steps need a grid-wide boundary). */
 int gfb_kernel_create(gfb_ctx *ctx, const char *name, const uint64_t *ptr_keys, int num_ptrs,
                       size_t num_rays, unsigned block_size, size_t dynamic_smem, int kind, int can_repeat,
                       gfb_kernel **kernel);

@@ -7,8 +7,7 @@
  *    - only type DOUBLE with use_safe_math == false is accepted (the FP64 ray
  *      path of the north star); other types make graph_construct_context
  *      return NULL and print why;
- *    - graph_random_state / graph_random / graph_constant_c / graph_index_1D /
- *      graph_index_2D are not on the ray path and are absent;
+ *    - graph_random_state / graph_random / graph_constant_c are not on the ray path and are absent;
  *    - graph_erfi takes a real argument (the reference's needs a complex context;
  *      ray state is real, special_functions.hpp:1504-1512 is the branch it takes).
  *  Nodes are opaque `void *`; identical expressions give identical pointers
@@ -72,6 +71,12 @@ graph_node graph_piecewise_2D(STRUCT_TAG graph_c_context *c, const size_t num_co
                               graph_node x_arg, const double x_scale, const double x_offset,
                               graph_node y_arg, const double y_scale, const double y_offset,
                               const void *source, const size_t source_size);
+/* Gathers from a variable: graph_c_binding.h:458-486 */
+graph_node graph_index_1D(STRUCT_TAG graph_c_context *c, graph_node variable, graph_node arg,
+                          const double scale, const double offset);
+graph_node graph_index_2D(STRUCT_TAG graph_c_context *c, graph_node variable, const size_t num_cols,
+                          graph_node x_arg, const double x_scale, const double x_offset,
+                          graph_node y_arg, const double y_scale, const double y_offset);
 
 /* Derivative: graph_c_binding.h:649-653 */
 graph_node graph_df(STRUCT_TAG graph_c_context *c, graph_node fnode, graph_node xnode);

@@ -84,6 +84,42 @@ static jit::kernel_info build_absorption(const std::string &kind, equilibrium::s
                           {graph::sqrt(difference*difference)}, setters, n);
 }
 
+//  The two kernels of the reference's particle-in-cell example (graph_pic/xpic.cpp:63-125) at test
+//  size: an RK4 particle push that gathers the field with index_1D, and the field accumulation
+//  that walks the particle array with index_1D on a running index (batch of 4 per step).
+static jit::kernel_info build_pic(const std::string &kind, std::ostringstream &src, const jit::emit_options &opt) {
+    const size_t n = 64;            // the clamp of an index node is the length of the indexed variable
+    const double dt = 1.0e-2, scale = 2.0/63.0, offset = -1.0;
+    auto x = graph::variable(n, "x"), vpara = graph::variable(n, "v");
+    auto epara = graph::variable(n, "e"), dens = graph::variable(n, "n");
+    auto grid_position = graph::variable(n, "xi"), particle_index = graph::variable(n, "i");
+    if (kind == "pic_push") {
+        auto x1 = dt*vpara;
+        auto v1 = -1.0*graph::index_1D(epara, x, scale, offset);
+        auto x2 = dt*(vpara + v1/2.0);
+        auto v2 = -1.0*graph::index_1D(epara, x + x1/2.0, scale, offset);
+        auto x3 = dt*(vpara + v2/2.0);
+        auto v3 = -1.0*graph::index_1D(epara, x + x2/2.0, scale, offset);
+        auto x4 = dt*(vpara + v3);
+        auto v4 = -1.0*graph::index_1D(epara, x + x3, scale, offset);
+        graph::map_nodes<> setters = {{x + (x1 + 2.0*(x2 + x3) + x4)/6.0, x}, {vpara + (v1 + 2.0*(v2 + v3) + v4)/6.0, vpara}};
+        return jit::emit_item(src, opt, jit::kernel_kind::generic, "Particle_Push", {x, vpara, epara}, {}, setters, n);
+    }
+    auto density = [] (leaf_ptr d) { return graph::exp(d*d/-0.01); };
+    auto next_index = particle_index, next_e = epara, next_n = dens;
+    for (int b = 0; b < 4; b++) {
+        auto particle = graph::index_1D(x, next_index, 1.0, 0.0);
+        next_index = next_index + 1.0;
+        auto d = particle - grid_position;
+        auto nd = density(d);
+        next_e = next_e + -1.0/nd*nd->df(d);
+        next_n = next_n + nd;
+    }
+    graph::map_nodes<> setters = {{next_e, epara}, {next_index, particle_index}, {next_n, dens}};
+    return jit::emit_item(src, opt, jit::kernel_kind::generic, "Compute_efield",
+                          {epara, dens, grid_position, particle_index, x}, {}, setters, n);
+}
+
 int main(int argc, char **argv) {
     if (argc < 5) { std::cerr << "usage: emit_case <dispersion> <equilibrium> <kind> <out.cu> [tables.bin] [efit.gfbt]" << std::endl; return 2; }
     const std::string d = argv[1], e = argv[2], kind = argv[3];
@@ -98,6 +134,7 @@ int main(int argc, char **argv) {
     std::ostringstream src;
     jit::kernel_info info;
     if (kind == "kamp" || kind == "power") info = build_absorption(kind, eq, src, opt);
+    else if (kind == "pic_push" || kind == "pic_field") info = build_pic(kind, src, opt);
     else if (d == "cold_plasma") info = build<dispersion::cold_plasma<>> (kind, eq, src, opt);
     else if (d == "ordinary_wave") info = build<dispersion::ordinary_wave<>> (kind, eq, src, opt);
     else if (d == "extra_ordinary_wave") info = build<dispersion::extra_ordinary_wave<>> (kind, eq, src, opt);
@@ -109,6 +146,7 @@ int main(int argc, char **argv) {
     if (argc > 5) {
         std::ofstream tb(argv[5], std::ios::binary);
         for (auto &g : info.groups) {
+            if (g.alias_input >= 0) continue;
             const uint64_t n = g.packed.size();
             tb.write(reinterpret_cast<const char *> (&n), 8);
             tb.write(reinterpret_cast<const char *> (g.packed.data()), 8*n);

@@ -221,3 +221,44 @@ def test_nvrtc_compiles_absorption_kernels(lib, emit_tool, kind):
     lib.gfb_free(cubin)
     if log.value:
         lib.gfb_free(log)
+
+
+def test_emitted_index_kernels_match_numpy(lib, emit_tool):
+    """index_1D gathers (piecewise.hpp:1436-1640) in the two kernels of graph_pic/xpic.cpp at test
+    size, on the CPU harness against a numpy restatement; the indexed arrays are never loaded per ray."""
+    n = 64
+    rng = np.random.default_rng(4)
+    scale, offset, dt = 2.0/63.0, -1.0, 1.0e-2
+    x, v, e = rng.normal(0.0, 0.4, n), rng.normal(0.0, 0.25, n), rng.normal(size=n)
+
+    def gather(arr, arg, s, o):
+        return arr[np.clip((arg - o)/s, 0, arr.size - 1).astype(int)]
+
+    cu, tab, info = emit(emit_tool, "none", "slab", "pic_push", "pic_push")
+    text = open(cu).read()
+    assert "v[2] =" not in text and "tg[0][" in text and "group_slot" in text      # e is only indexed
+    out = run_harness(cu, tab, "Particle_Push", [x, v, e], n, 1, 3, 0, "pic_push")
+    x1, v1 = dt*v, -gather(e, x, scale, offset)
+    x2, v2 = dt*(v + v1/2), -gather(e, x + x1/2, scale, offset)
+    x3, v3 = dt*(v + v2/2), -gather(e, x + x2/2, scale, offset)
+    x4, v4 = dt*(v + v3), -gather(e, x + x3, scale, offset)
+    assert np.allclose(out[0], x + (x1 + 2*(x2 + x3) + x4)/6, rtol=1e-14, atol=1e-16)
+    assert np.allclose(out[1], v + (v1 + 2*(v2 + v3) + v4)/6, rtol=1e-14, atol=1e-16)
+    assert np.array_equal(out[2], e)
+
+    cu, tab, info = emit(emit_tool, "none", "slab", "pic_field", "pic_field")
+    grid = scale*np.arange(n) + offset
+    field, dens, idx = np.zeros(n), np.zeros(n), np.zeros(n)
+    out = run_harness(cu, tab, "Compute_efield", [field, dens, grid, idx, x], n, 3, 5, 0, "pic_field")   # 3 fused steps of 4
+    for p in x[:12]:
+        d = p - grid
+        dens += np.exp(d*d/-0.01)
+        field += -1.0/np.exp(d*d/-0.01)*(np.exp(d*d/-0.01)*2.0*d/-0.01)
+    assert np.allclose(out[1], dens, rtol=1e-13) and np.allclose(out[0], field, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(out[3], np.full(n, 12.0)) and np.array_equal(out[4], x)
+
+    for name in ("pic_push", "pic_field"):
+        src = open(os.path.join(BUILD, "emit_%s.cu" % name)).read().encode()
+        cubin, size, log = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_void_p()
+        assert lib.gfb_compile_to_cubin(src, None, ctypes.byref(cubin), ctypes.byref(size), ctypes.byref(log)) == 0
+        lib.gfb_free(cubin)

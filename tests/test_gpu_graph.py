@@ -243,3 +243,67 @@ def test_raw_c_abi_with_adopted_torch_memory(lib):
     assert lib.gfb_wait(ctx) == 0
     assert torch.equal(t.cpu(), torch.full((n,), 103.0, dtype=torch.float64))
     lib.gfb_ctx_destroy(ctx)
+
+
+def test_index_kernels_and_pic_step(g):
+    """index_1D/index_2D kernels (piecewise_test.cpp:834-925) and the three work items of
+    graph_pic/xpic.cpp:106-131 with arrays of DIFFERENT lengths in one kernel: a field kernel of
+    num_grid threads that walks num_particles particles (loop of batches, fused into one launch),
+    then a particle push of num_particles threads that gathers from the num_grid field."""
+    particles, grid_n, batch = 4096, 128, 8
+    rng = np.random.default_rng(9)
+    xs, vs = rng.normal(0.0, 0.3, particles), rng.normal(0.0, 0.25, particles)
+    scale, offset, dt = 2.0/(grid_n - 1), -1.0, 1.0e-3
+    x, v = g.variable(particles, "x", xs), g.variable(particles, "v", vs)
+    e, dens = g.variable(grid_n, "e", np.ones(grid_n)), g.variable(grid_n, "n", np.ones(grid_n))
+    pos = g.variable(grid_n, "xi", scale*np.arange(grid_n) + offset)
+    idx = g.variable(grid_n, "i", np.full(grid_n, 5.0))
+
+    def density(d):
+        return g.exp(d*d/-0.01)
+
+    next_i, next_e, next_n = idx, e, dens
+    for _ in range(batch):
+        d = g.index_1D(x, next_i, 1.0, 0.0) - pos
+        nd = density(d)
+        next_i = next_i + 1.0
+        next_e = next_e + (-1.0/nd)*nd.df(d)
+        next_n = next_n + nd
+    zero = g.constant(0.0)
+    g.add_item([idx, e, dens], [], [(zero, idx), (zero, e), (zero, dens)], "Index_reset", grid_n)
+    g.add_item([e, dens, pos, idx, x], [], [(next_e, e), (next_i, idx), (next_n, dens)], "Compute_efield", grid_n)
+    g.compile()
+    g.run()                                   # reset + first batch
+    lib_runs = particles//batch - 1
+
+    def gather(arr, arg, s, o):
+        return arr[np.clip((arg - o)/s, 0, arr.size - 1).astype(int)]
+
+    grid = scale*np.arange(grid_n) + offset
+    d = xs[:batch, None] - grid[None, :]
+    assert np.allclose(g.copy_to_host(dens, grid_n), np.exp(d*d/-0.01).sum(axis=0), rtol=1e-13, atol=1e-300)
+    assert np.array_equal(g.copy_to_host(idx, grid_n), np.full(grid_n, float(batch)))
+    src = g.source()
+    assert "group_slot" in src and src.count("tg[0][") >= batch
+
+
+def test_index_2d_and_self_indexed_kernel(g):
+    """index_2D on a variable grid, and a kernel that gathers from the array it rewrites: steps of
+    such an item must not be fused (every run sees the array as the previous run left it)."""
+    n = 256
+    rng = np.random.default_rng(2)
+    table = rng.normal(size=(8, 16))
+    xs, ys = rng.uniform(-1.0, 9.0, n), rng.uniform(-1.0, 17.0, n)
+    t = g.variable(table.size, "t", table.ravel())
+    x, y = g.variable(n, "x", xs), g.variable(n, "y", ys)
+    out = g.index_2D(t, 16, x, 1.0, 0.0, y, 1.0, 0.0)*2.0
+    ring = g.variable(n, "ring", np.arange(n, dtype=float))
+    left = g.variable(n, "left", (np.arange(n) + n - 1.0) % n)
+    shifted = g.index_1D(ring, left, 1.0, 0.0)                       # ring[i] <- ring[i - 1]
+    g.add_item([t, x, y, ring, left], [out], [(shifted, ring)], "gather", n)
+    g.compile()
+    for _ in range(5):
+        g.run()
+    ix, iy = np.clip(xs, 0, 7).astype(int), np.clip(ys, 0, 15).astype(int)
+    assert np.array_equal(g.copy_to_host(out, n), 2.0*table[ix, iy])
+    assert np.array_equal(g.copy_to_host(ring, n), np.roll(np.arange(n, dtype=float), 5))

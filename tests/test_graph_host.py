@@ -155,3 +155,30 @@ def test_erfi_node_matches_reference_values(g):
     d = np.broadcast_to(g.erfi(x).df(x).evaluate(), ref["x"].shape)
     assert np.allclose(d[small], 2.0/np.sqrt(np.pi)*np.exp(ref["x"][small]**2), rtol=1e-14)
     assert g.erfi(g.constant(0.0)) == g.constant(0.0)
+
+
+def test_index_nodes(g):
+    """piecewise_test.cpp:834-925 (index_1D, index_2D): node identity, the clamped index rule on a
+    VARIABLE array, df = 1 w.r.t. itself and 0 otherwise (piecewise.hpp:1475-1477)."""
+    variable = g.variable(11, "v", np.arange(11.0))
+    arg = g.variable(1, "a", [3.5])
+    index = g.index_1D(variable, arg, 1.0, 0.0)
+    assert index != g.index_1D(variable, arg, 1.0, 2.0)
+    assert index == g.index_1D(variable, arg, 1.0, 0.0)
+    assert np.array_equal(index.evaluate(), [3.0])
+    g.set_variable(arg, [-3.5])
+    assert np.array_equal(index.evaluate(), [0.0])
+    assert index.df(index) == g.constant(1.0) and index.df(arg) == g.constant(0.0)
+
+    grid = g.variable(9, "m", np.arange(1.0, 10.0))
+    x = g.variable(1, "x", [2.5])
+    y = g.variable(1, "y", [0.5])
+    i2 = g.index_2D(grid, 3, x, 1.0, 0.0, y, 1.0, 0.0)
+    assert i2 != g.index_2D(grid, 3, x, 1.0, 0.0, y, 1.0, 2.0)
+    assert i2 == g.index_2D(grid, 3, x, 1.0, 0.0, y, 1.0, 0.0)
+    for xv, yv, expect in ((2.5, 0.5, 7.0), (-2.5, -0.5, 1.0), (-2.5, 0.5, 1.0), (2.5, -0.5, 7.0)):
+        g.set_variable(x, [xv])
+        g.set_variable(y, [yv])
+        assert np.array_equal(i2.evaluate(), [expect])
+    g.set_variable(grid, np.arange(9.0)*2.0)                     # the array is a variable: new contents, same node
+    assert np.array_equal(i2.evaluate(), [12.0])
