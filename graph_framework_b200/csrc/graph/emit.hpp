@@ -605,8 +605,13 @@ namespace jit {
                 for (size_t g = 0; g < ng; g++) out << "g == " << g << " ? " << slots[g] << " : ";
                 out << "0; }" << std::endl;
             }
+//  An input that is only the array of index nodes is not a per-ray value: no load, any length.
             info.input_loaded.assign(ni, true);
-            for (size_t j = 0; j < ni; j++) info.input_loaded[j] = visited.count(info.inputs[j].get()) != 0;
+            for (auto &g : info.groups) {
+                if (g.alias_input < 0) continue;
+                const size_t j = static_cast<size_t> (g.alias_input);
+                info.input_loaded[j] = visited.count(info.inputs[j].get()) != 0 || info.input_written[j];
+            }
             out << "    __device__ static constexpr int ev(const int e) { return ";
             for (size_t e = 0; e < evolved.size(); e++) out << "e == " << e << " ? " << evolved[e] << " : ";
             out << "0; }" << std::endl;
@@ -614,7 +619,7 @@ namespace jit {
             out << "    __device__ static __forceinline__ void load(double (&v)[NI + 1], const gfb_args &a, const unsigned long long i) {" << std::endl;
             for (size_t j = 0; j < ni; j++) {
                 if (!info.input_loaded[j]) {
-                    continue;       // reached through index nodes only (or write-only): its length need not match
+                    continue;       // reached through index nodes only: its length need not match the kernel's
                 } else if (info.input_written[j]) {
                     out << "        v[" << j << "] = a.ptr[" << j << "][i];" << std::endl;
                 } else {
