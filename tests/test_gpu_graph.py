@@ -206,6 +206,7 @@ struct add_one_k {
     __device__ static constexpr bool group_staged(const int) { return false; }
     __device__ static constexpr unsigned group_offset(const int) { return 0; }
     __device__ static constexpr unsigned group_bytes(const int) { return 0; }
+    __device__ static constexpr int group_slot(const int g) { return NP + g; }
     __device__ static constexpr int ev(const int) { return 0; }
     __device__ static __forceinline__ void load(double (&v)[2], const gfb_args &a, const unsigned long long i) { v[0] = a.ptr[0][i]; }
     __device__ static __forceinline__ void apply(double (&v)[2], const double (&r)[2]) { v[0] = r[0]; }
