@@ -79,6 +79,10 @@ def _load():
         "gfb_rays_trace_absorb": (I, [P, SZ, SZ, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                       ctypes.POINTER(ctypes.c_int)]),
         "gfb_rays_absorption_reset": (I, [P]),
+        "gfb_rays_set_binning": (I, [P, I, D, D, ctypes.c_uint, SZ]),
+        "gfb_bin_rays": (I, [P, ctypes.c_uint64, D, D, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64), I, SZ]),
+        "gfb_unbin_rays": (I, [P, ctypes.POINTER(ctypes.c_uint64), I, SZ]),
+        "gfb_is_binned": (I, [P]),
         "gfb_rays_device_ptr": (I, [P, I, c_void_pp]),
         "gfb_rays_ctx": (P, [P]),
         "gfb_rays_source": (S, [P]),

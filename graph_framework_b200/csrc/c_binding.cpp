@@ -339,6 +339,37 @@ struct gfb_rays {
     bool absorption_started = false;
     char profile_tag = 0;             // its address keys the deposition profile buffer
     std::string source;
+//  Binning by table cell (gfb_rays_set_binning): applied before stepping, undone before anything
+//  reads or writes rays by index.
+    int bin_state = -1;
+    double bin_lo = 0.0, bin_hi = 1.0;
+    unsigned bin_cells = 0;
+    size_t rebin_every = 0, steps_since_bin = 0;
+    std::vector<uint64_t> ray_keys(const bool with_residual) const {
+        std::vector<uint64_t> keys;
+        for (auto &v : vars) keys.push_back(reinterpret_cast<uint64_t> (v.get()));
+        if (with_residual) keys.push_back(reinterpret_cast<uint64_t> (impl->residual().get()));
+        return keys;
+    }
+//  Back to the caller's ray order: the state and the residual of the last launch.
+    int unbin() {
+        if (bin_state < 0 || !compiled) return 0;
+        auto keys = ray_keys(true);
+        return gfb_unbin_rays(impl->context().device(), keys.data(), static_cast<int> (keys.size()), n);
+    }
+//  Before a block of steps: (re)sort the state by cell.  The residual is rewritten by the launch.
+    int bin(const size_t steps) {
+        if (bin_state < 0 || !compiled) return 0;
+        if (rebin_every && steps_since_bin >= rebin_every && unbin()) return 1;
+        auto keys = ray_keys(false);
+        gfb_ctx *ctx = impl->context().device();
+        if (!gfb_is_binned(ctx)) {
+            if (gfb_bin_rays(ctx, keys[bin_state], bin_lo, bin_hi, bin_cells, keys.data(), static_cast<int> (keys.size()), n)) return 1;
+            steps_since_bin = 0;
+        }
+        steps_since_bin += steps;
+        return 0;
+    }
 };
 
 namespace {
@@ -394,7 +425,10 @@ int gfb_rays_set_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]) {
     for (int i = 0; i < GFB_NUM_STATE; i++) {
         if (state[i]) r->vars[i]->set(std::vector<double> (state[i], state[i] + r->n));
     }
-    if (r->compiled) r->impl->sync_device();
+    if (r->compiled) {
+        if (r->unbin()) return 1;
+        r->impl->sync_device();
+    }
     return 0;
 }
 int gfb_rays_init(gfb_rays *r, const char *var, double tolerance, size_t max_iterations, int mode) {
@@ -414,6 +448,7 @@ int gfb_rays_compile(gfb_rays *r) {
 }
 int gfb_rays_step(gfb_rays *r, size_t num_steps) {
     if (!r->compiled) return rays_fail("step before compile");
+    if (r->bin(num_steps)) return 1;
     r->impl->step(num_steps);
     return gfb_flush(r->impl->context().device());
 }
@@ -421,7 +456,20 @@ int gfb_rays_wait(gfb_rays *r) {
     r->impl->wait();
     return 0;
 }
+int gfb_rays_set_binning(gfb_rays *r, int which_state, double lo, double hi, unsigned cells, size_t rebin_every) {
+    if (which_state >= GFB_NUM_STATE) return rays_fail("bad state index");
+    if (r->impl->damping) return rays_fail("binning and absorption=1 cannot be combined");
+    if (r->unbin()) return 1;
+    if (which_state >= 0 && (cells == 0 || !(hi > lo))) return rays_fail("bad binning grid");
+    r->bin_state = which_state;
+    r->bin_lo = lo;
+    r->bin_hi = hi;
+    r->bin_cells = cells;
+    r->rebin_every = rebin_every;
+    return 0;
+}
 int gfb_rays_get_state(gfb_rays *r, double *const state[GFB_NUM_STATE], double *residual) {
+    if (r->unbin()) return 1;
     if (state) {
         for (int i = 0; i < GFB_NUM_STATE; i++) {
             if (!state[i]) continue;
@@ -438,6 +486,7 @@ int gfb_rays_get_state(gfb_rays *r, double *const state[GFB_NUM_STATE], double *
 }
 int gfb_rays_put_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]) {
     if (!r->compiled) return gfb_rays_set_state(r, state);
+    if (r->unbin()) return 1;
     for (int i = 0; i < GFB_NUM_STATE; i++) {
         if (state[i]) r->impl->context().copy_to_device(r->vars[i], const_cast<double *> (state[i]));
     }
@@ -446,6 +495,7 @@ int gfb_rays_put_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]) {
 int gfb_rays_step_host(gfb_rays *r, size_t num_steps, const double *const state_in[GFB_NUM_STATE],
                        double *const state_out[GFB_NUM_STATE], double *residual_out, int chunks) {
     if (!r->compiled) return rays_fail("step_host before compile");
+    if (r->unbin()) return 1;
 //  Pointer slots of solver_kernel: the 8 inputs in solver order (= GFB_T..GFB_KZ), then the residual.
     const void *src[GFB_NUM_STATE + 1];
     void *dst[GFB_NUM_STATE + 1];
@@ -465,7 +515,9 @@ int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out
     keys.push_back(reinterpret_cast<uint64_t> (r->impl->residual().get()));
     gfb_ctx *ctx = r->impl->context().device();
     for (size_t b = 0; b < num_blocks; b++) {
+        if (r->bin(sub_steps)) return 1;
         r->impl->step(sub_steps);
+        if (r->unbin()) return 1;           // records are in the caller's ray order
         if (gfb_snapshot_async(ctx, keys.data(), static_cast<int> (keys.size()), sizeof(double)*r->n,
                                out + b*keys.size()*r->n)) return 1;
     }
@@ -522,6 +574,7 @@ int gfb_rays_trace_absorb(gfb_rays *r, size_t num_blocks, size_t sub_steps, doub
 }
 int gfb_rays_device_ptr(gfb_rays *r, int which, void **device_ptr) {
     if (!r->compiled) return rays_fail("device_ptr before compile");
+    if (r->unbin()) return 1;
     if (which < 0 || which > GFB_NUM_STATE) return rays_fail("bad state index");
     *device_ptr = r->impl->context().device_pointer(which == GFB_NUM_STATE ? r->impl->residual() : r->vars[which]);
     return 0;

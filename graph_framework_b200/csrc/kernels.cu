@@ -98,6 +98,56 @@ __global__ void __launch_bounds__(256) deposit_kernel(const double *__restrict__
     }
 }
 
+//------------------------------------------------------------------------------
+//  Binning of rays by table cell (counting sort).  Rays are independent, so their order in the SoA
+//  arrays is free; putting rays of the same cell next to each other lets a warp share the
+//  coefficient rows it gathers (VMEC: 86 modes x 3 quantities per cell).  The order inside a cell is
+//  whatever the atomics give -- per-ray results do not depend on the slot a ray occupies.
+//------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bin_count_kernel(const double *__restrict__ v, const unsigned n,
+                                                        const double lo, const double inv_width, const unsigned cells,
+                                                        unsigned *__restrict__ cell_of, unsigned *__restrict__ count) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned rounded = (n + 31u) & ~31u;
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < rounded; i += gridDim.x*blockDim.x) {
+        const bool active = i < n;
+        unsigned cell = 0;
+        if (active) {
+            cell = static_cast<unsigned> (fmin(fmax((__ldg(v + i) - lo)*inv_width, 0.0), static_cast<double> (cells - 1u)));
+            cell_of[i] = cell;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const unsigned peers = __match_any_sync(mask, cell);
+            if (lane == __ffs(peers) - 1u) atomicAdd(count + cell, static_cast<unsigned> (__popc(peers)));
+        }
+    }
+}
+//  Exclusive scan of the (few hundred) cell counts; also primes the placement cursors.
+__global__ void bin_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ cursor, const unsigned cells) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned sum = 0;
+        for (unsigned c = 0; c < cells; c++) {
+            cursor[c] = sum;
+            sum += count[c];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) bin_place_kernel(const unsigned *__restrict__ cell_of, const unsigned n,
+                                                        unsigned *__restrict__ cursor, unsigned *__restrict__ perm) {
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+        perm[atomicAdd(cursor + cell_of[i], 1u)] = i;
+    }
+}
+__global__ void __launch_bounds__(256) gather_kernel(double *__restrict__ dst, const double *__restrict__ src,
+                                                     const unsigned *__restrict__ perm, const unsigned n) {
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) dst[i] = __ldg(src + perm[i]);
+}
+__global__ void __launch_bounds__(256) scatter_kernel(double *__restrict__ dst, const double *__restrict__ src,
+                                                      const unsigned *__restrict__ perm, const unsigned n) {
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) dst[perm[i]] = __ldg(src + i);
+}
+
 //  8 independent FMA chains per thread keep the FP64 pipe saturated.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, const int iters, const double a, const double b) {
     double r0 = threadIdx.x, r1 = r0 + 1.0, r2 = r0 + 2.0, r3 = r0 + 3.0;
@@ -151,6 +201,23 @@ int gfb_k_deposit(const double *x, const double *y, const double *z, const doubl
     deposit_kernel<<<grid ? grid : 1, 256, 0, s>>> (x, y, z, w, n, hist, lo[0], lo[1], lo[2],
                                                      bins[0]/(hi[0] - lo[0]), bins[1]/(hi[1] - lo[1]), bins[2]/(hi[2] - lo[2]),
                                                      bins[0], bins[1], bins[2]);
+    return static_cast<int> (cudaGetLastError());
+}
+//  perm[slot] = ray that moves into `slot`.  work: cells*2 + n unsigned (count, cursor, cell_of).
+int gfb_k_bin_permutation(const double *values, unsigned n, double lo, double hi, unsigned cells,
+                          unsigned *work, unsigned *perm, int sms, cudaStream_t s) {
+    unsigned *count = work, *cursor = work + cells, *cell_of = work + 2*cells;
+    const unsigned grid = static_cast<unsigned> ((n + 255u)/256u < static_cast<unsigned> (sms)*8u ? (n + 255u)/256u : sms*8);
+    cudaMemsetAsync(count, 0, sizeof(unsigned)*cells, s);
+    bin_count_kernel<<<grid ? grid : 1, 256, 0, s>>> (values, n, lo, cells/(hi - lo), cells, cell_of, count);
+    bin_scan_kernel<<<1, 32, 0, s>>> (count, cursor, cells);
+    bin_place_kernel<<<grid ? grid : 1, 256, 0, s>>> (cell_of, n, cursor, perm);
+    return static_cast<int> (cudaGetLastError());
+}
+int gfb_k_permute(double *dst, const double *src, const unsigned *perm, unsigned n, int scatter, int sms, cudaStream_t s) {
+    const unsigned grid = static_cast<unsigned> ((n + 255u)/256u < static_cast<unsigned> (sms)*16u ? (n + 255u)/256u : sms*16);
+    if (scatter) scatter_kernel<<<grid ? grid : 1, 256, 0, s>>> (dst, src, perm, n);
+    else gather_kernel<<<grid ? grid : 1, 256, 0, s>>> (dst, src, perm, n);
     return static_cast<int> (cudaGetLastError());
 }
 int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s) {

@@ -38,6 +38,9 @@ double gfb_k_unorder(unsigned long long key);
 int gfb_k_deposit(const double *x, const double *y, const double *z, const double *w, unsigned long long n,
                   double *hist, const double *lo, const double *hi, const int *bins, int sms, cudaStream_t s);
 int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s);
+int gfb_k_bin_permutation(const double *values, unsigned n, double lo, double hi, unsigned cells,
+                          unsigned *work, unsigned *perm, int sms, cudaStream_t s);
+int gfb_k_permute(double *dst, const double *src, const unsigned *perm, unsigned n, int scatter, int sms, cudaStream_t s);
 int gfb_k_fill(double *p, size_t n, double v, int sms, cudaStream_t s);
 }
 
@@ -233,6 +236,12 @@ struct gfb_ctx {
     cudaEvent_t drained[2] = {nullptr, nullptr};    // slot copied out (copy stream)
     unsigned next_slot = 0;
     cudaStream_t upload_stream = nullptr;
+//  Ray binning: the permutation in force (perm[slot] = original ray), scratch for the moves.
+    unsigned *bin_perm = nullptr;
+    unsigned *bin_work = nullptr;
+    double *bin_scratch = nullptr;
+    size_t bin_capacity = 0, bin_cells = 0;
+    bool binned = false;
 };
 
 namespace {
@@ -313,6 +322,9 @@ void gfb_ctx_destroy(gfb_ctx *c) {
     if (c->module) driver.ModuleUnload(c->module);
     if (c->scratch) cudaFree(c->scratch);
     if (c->scratch_host) cudaFreeHost(c->scratch_host);
+    if (c->bin_perm) cudaFree(c->bin_perm);
+    if (c->bin_work) cudaFree(c->bin_work);
+    if (c->bin_scratch) cudaFree(c->bin_scratch);
     if (c->flush_buffer) cudaFree(c->flush_buffer);
     if (c->upload_stream) {
         cudaStreamSynchronize(c->upload_stream);
@@ -769,6 +781,59 @@ int gfb_timer_stop(gfb_ctx *c, float *ms) {
     return check(cudaEventElapsedTime(ms, c->ev_start, c->ev_stop), "cudaEventElapsedTime");
 }
 void *gfb_stream(gfb_ctx *c) { return c->stream; }
+
+namespace {
+int move_rays(gfb_ctx *c, const uint64_t *keys, int num_keys, size_t n, int scatter) {
+    for (int i = 0; i < num_keys; i++) {
+        auto it = c->buffers.find(keys[i]);
+        if (it == c->buffers.end()) return fail("ray binning: unknown buffer key");
+        if (it->second.bytes < n*sizeof(double)) return fail("ray binning: buffer shorter than the ray count");
+        double *data = static_cast<double *> (it->second.dev);
+        if (gfb_k_permute(c->bin_scratch, data, c->bin_perm, static_cast<unsigned> (n), scatter, c->sms, c->stream)) {
+            return fail("ray binning: permute launch failed");
+        }
+        if (check(cudaMemcpyAsync(data, c->bin_scratch, n*sizeof(double), cudaMemcpyDeviceToDevice, c->stream), "bin copy back")) return 1;
+        c->launches++;
+    }
+    return 0;
+}
+}
+
+int gfb_bin_rays(gfb_ctx *c, uint64_t sort_key, double lo, double hi, unsigned cells,
+                 const uint64_t *keys, int num_keys, size_t n) {
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    if (c->binned) return fail("gfb_bin_rays: already binned, call gfb_unbin_rays first");
+    if (cells == 0 || !(hi > lo) || n == 0 || n > 0xffffffffull) return fail("gfb_bin_rays: bad arguments");
+    if (c->bin_capacity < n || c->bin_cells < cells) {
+        cudaStreamSynchronize(c->stream);
+        if (c->bin_perm) cudaFree(c->bin_perm);
+        if (c->bin_work) cudaFree(c->bin_work);
+        if (c->bin_scratch) cudaFree(c->bin_scratch);
+        if (check(cudaMalloc(&c->bin_perm, n*sizeof(unsigned)), "bin perm")) return 1;
+        if (check(cudaMalloc(&c->bin_work, (n + 2*static_cast<size_t> (cells))*sizeof(unsigned)), "bin work")) return 1;
+        if (check(cudaMalloc(&c->bin_scratch, n*sizeof(double)), "bin scratch")) return 1;
+        c->bin_capacity = n;
+        c->bin_cells = cells;
+    }
+    auto it = c->buffers.find(sort_key);
+    if (it == c->buffers.end()) return fail("gfb_bin_rays: unknown sort key");
+    if (gfb_k_bin_permutation(static_cast<const double *> (it->second.dev), static_cast<unsigned> (n), lo, hi, cells,
+                              c->bin_work, c->bin_perm, c->sms, c->stream)) return fail("gfb_bin_rays: launch failed");
+    c->launches += 3;
+    if (move_rays(c, keys, num_keys, n, 0)) return 1;
+    c->binned = true;
+    return 0;
+}
+int gfb_is_binned(gfb_ctx *c) { return c->binned ? 1 : 0; }
+int gfb_unbin_rays(gfb_ctx *c, const uint64_t *keys, int num_keys, size_t n) {
+    if (!c->binned) return 0;
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    if (move_rays(c, keys, num_keys, n, 1)) return 1;
+    c->binned = false;
+    return 0;
+}
 
 int gfb_host_alloc(size_t bytes, void **host_ptr) {
     return check(cudaMallocHost(host_ptr, bytes ? bytes : 8), "cudaMallocHost") ? 1 : 0;

@@ -175,6 +175,12 @@ class RayTracer:
                                         absorbed.ctypes.data_as(c_double_p), *args), "trace_absorb")
         return rec, absorbed, profile
 
+    def set_binning(self, name, lo, hi, cells, rebin_every=0):
+        """Keep rays sorted by the table cell of state `name` while stepping (include/gfb_rays.h
+        gfb_rays_set_binning); invisible to the caller.  name=None switches it off."""
+        which = -1 if name is None else STATE.index(name)
+        check(lib.gfb_rays_set_binning(self.h, which, float(lo), float(hi), int(cells), int(rebin_every)), "set_binning")
+
     def absorption_reset(self):
         check(lib.gfb_rays_absorption_reset(self.h), "absorption_reset")
 

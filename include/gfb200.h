@@ -124,6 +124,16 @@ int gfb_check_value(gfb_ctx *ctx, uint64_t key, size_t index, double *value);
  * gfb_wait() completes all outstanding snapshots. */
 int gfb_snapshot_async(gfb_ctx *ctx, const uint64_t *keys, int num_keys, size_t bytes_each, void *host_destination);
 
+/* Ray binning.  Rays are independent, so their order in the SoA arrays is free: gfb_bin_rays sorts the
+ * rays by the table cell of one array (cell = trunc(clamp((v - lo)/(hi - lo)*cells, 0, cells - 1)), the
+ * piecewise index rule) and applies the permutation to every listed per-ray buffer, so that a warp
+ * works on rays of the same cell and shares the coefficient rows it gathers.  gfb_unbin_rays restores
+ * the caller's order (no-op when not binned).  No reference counterpart: the reference never reorders. */
+int gfb_bin_rays(gfb_ctx *ctx, uint64_t sort_key, double lo, double hi, unsigned cells,
+                 const uint64_t *keys, int num_keys, size_t n);
+int gfb_unbin_rays(gfb_ctx *ctx, const uint64_t *keys, int num_keys, size_t n);
+int gfb_is_binned(gfb_ctx *ctx);
+
 /* Page-locked host memory for snapshot / step-from-host buffers (any thread, any context). */
 int gfb_host_alloc(size_t bytes, void **host_ptr);
 int gfb_host_free(void *host_ptr);

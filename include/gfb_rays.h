@@ -67,6 +67,13 @@ int gfb_rays_step_host(gfb_rays *r, size_t num_steps, const double *const state_
  * `out` receives num_blocks records of 9 arrays of num_rays doubles ([block][9][ray]); the
  * device->host transfer of block b overlaps the stepping of block b + 1.  Pinned memory recommended. */
 int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out);
+/* Keep the rays sorted by the table cell of one state array while stepping (gfb_bin_rays in gfb200.h):
+ * cell = trunc(clamp((state[which] - lo)/(hi - lo)*cells, 0, cells - 1)).  The state is re-sorted before a
+ * block of steps when it is in the caller's order, or after `rebin_every` steps (0 = never re-sort while
+ * stepping), and restored before every call that reads or writes rays by index, so the caller never sees
+ * the permutation.  For VMEC (which = GFB_X, the radial coordinate s in [0, 1], cells = the radial grid) a
+ * warp then shares the Fourier coefficient rows it reads.  which_state < 0 switches binning off. */
+int gfb_rays_set_binning(gfb_rays *r, int which_state, double lo, double hi, unsigned cells, size_t rebin_every);
 /* Trace with power absorption (options "absorption=1").  Replaces the second and third stage of the
  * reference driver, which re-read the trajectory files: absorption::weak_damping
  * (absorption.hpp:327-484, run per record at xrays.cpp:556-558) and bin_power (xrays.cpp:674-793),

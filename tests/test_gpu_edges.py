@@ -144,3 +144,65 @@ def test_xrays_driver_efit_example(lib, tmp_path):
     assert np.isfinite(out["kx"]).all() and np.max(out["residual"][-1]) < 1.0e-18
     r = np.sqrt(out["x"]**2 + out["y"]**2)
     assert np.all(r[-1] < r[0])                    # launched inward from R = 2.5
+
+
+def test_ray_binning_is_invisible_and_exact(lib):
+    """gfb_rays_set_binning: rays are kept sorted by table cell while stepping.  Each ray's arithmetic
+    does not depend on the slot it occupies, so state, residual and trajectory records must be
+    BIT-IDENTICAL to the run without binning, in the caller's order, also across re-sorts."""
+    from graph_framework_b200.rays import RayTracer
+    from graph_framework_b200 import workloads
+    n = 20000
+    state = workloads.efit_ensemble(n, seed=12)
+    runs = []
+    for binning in (False, True):
+        tr = RayTracer("extra_ordinary_wave", "efit", n, 2.0e-5)
+        tr.set_state(state)
+        tr.init("kx")
+        tr.compile()
+        if binning:
+            tr.set_binning("y", -0.3, 0.3, 64, rebin_every=150)
+        tr.step(100)
+        mid = tr.get_state()
+        rec = tr.trace(3, 100)
+        tr.step(50)
+        tr.step(50)
+        end = tr.get_state()
+        runs.append((mid, rec.copy(), end))
+        tr.close()
+    for a, b in zip(runs[0], runs[1]):
+        if isinstance(a, dict):
+            for k in a:
+                assert np.array_equal(a[k], b[k]), k
+        else:
+            assert np.array_equal(a, b)
+
+
+def test_bin_rays_sorts_by_cell_and_unbin_restores(lib):
+    """The device-layer calls by hand: after gfb_bin_rays every listed array is the same permutation
+    of its input, sorted by the cell of the key array; gfb_unbin_rays restores the input."""
+    n, cells = 100003, 37
+    rng = np.random.default_rng(21)
+    key = rng.uniform(-0.2, 1.2, n)
+    key[:5] = [np.nan, -5.0, 7.0, 0.0, 1.0]
+    other = np.arange(n, dtype=np.float64)
+    ctx = lib.gfb_ctx_create(0)
+    for k, a in ((11, key), (12, other)):
+        assert lib.gfb_buffer(ctx, k, a.nbytes, a.ctypes.data_as(ctypes.c_void_p), None) == 0
+    keys = (ctypes.c_uint64*2)(11, 12)
+    assert lib.gfb_bin_rays(ctx, 11, 0.0, 1.0, cells, keys, 2, n) == 0, lib.gfb_last_error()
+    assert lib.gfb_is_binned(ctx) == 1
+    k2, o2 = np.empty(n), np.empty(n)
+    assert lib.gfb_copy_d2h(ctx, 11, k2.ctypes.data_as(ctypes.c_void_p), 0) == 0
+    assert lib.gfb_copy_d2h(ctx, 12, o2.ctypes.data_as(ctypes.c_void_p), 0) == 0
+    perm = o2.astype(np.int64)
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    assert np.array_equal(k2, key[perm], equal_nan=True)
+    with np.errstate(invalid="ignore"):
+        cell = np.clip(np.nan_to_num(k2*cells, nan=0.0), 0, cells - 1).astype(int)
+    assert np.all(np.diff(cell) >= 0)
+    assert lib.gfb_unbin_rays(ctx, keys, 2, n) == 0 and lib.gfb_is_binned(ctx) == 0
+    assert lib.gfb_copy_d2h(ctx, 11, k2.ctypes.data_as(ctypes.c_void_p), 0) == 0
+    assert lib.gfb_copy_d2h(ctx, 12, o2.ctypes.data_as(ctypes.c_void_p), 0) == 0
+    assert np.array_equal(k2, key, equal_nan=True) and np.array_equal(o2, other)
+    lib.gfb_ctx_destroy(ctx)

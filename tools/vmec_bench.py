@@ -24,6 +24,8 @@ t1 = time.perf_counter()
 tr.init("kx")
 t2 = time.perf_counter()
 tr.compile()
+if os.environ.get("GFB_BIN_RAYS"):
+    tr.set_binning("x", 0.0, 1.0, 197, rebin_every=int(os.environ.get("GFB_REBIN", "0")))      # radial cells of the VMEC grid
 t3 = time.perf_counter()
 tr.step(steps)
 tr.wait()
@@ -39,4 +41,4 @@ import numpy as np
 print(json.dumps({"workload": "vmec %s RK4" % disp, "rays": n, "steps_per_launch": steps,
                   "ray_steps_per_s": n*steps*reps/(ms*1e-3), "ms_per_launch": ms/reps,
                   "finite": bool(np.isfinite(st["x"]).all()), "max_residual": float(np.max(st["residual"])),
-                  "kernel": stats, "setup_s": t1 - t0, "newton_s": t2 - t1, "jit_s": t3 - t2, "options": opts}))
+                  "binned": bool(os.environ.get("GFB_BIN_RAYS")), "kernel": stats, "setup_s": t1 - t0, "newton_s": t2 - t1, "jit_s": t3 - t2, "options": opts}))
