@@ -257,6 +257,10 @@ def main():
     tracer.init("kx")                                      # device-resident per-ray Newton
     t_compile = time.perf_counter()
     tracer.compile()
+    if eq == "vmec":
+        # rays of one radial cell share Fourier coefficient rows: keep them sorted by cell (198-point s grid),
+        # re-sorted every 10 blocks; the cost of the sorts is inside the timed region when they happen
+        tracer.set_binning("x", 0.0, 1.0, 197, rebin_every=10*SUB_STEPS)
     t_ready = time.perf_counter()
     stats = tracer.kernel_stats()
     fp64_peak = tracer.fp64_peak()
