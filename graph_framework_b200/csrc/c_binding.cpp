@@ -357,17 +357,30 @@ struct gfb_rays {
         auto keys = ray_keys(true);
         return gfb_unbin_rays(impl->context().device(), keys.data(), static_cast<int> (keys.size()), n);
     }
-//  Before a block of steps: (re)sort the state by cell.  The residual is rewritten by the launch.
-    int bin(const size_t steps) {
+//  Before a block of steps: sort the state by cell if it is in the caller's order or the last sort
+//  is `rebin_every` steps old (re-sorting composes permutations, no round trip through the caller's
+//  order).  The residual is rewritten by the launch, so it is not moved here.
+    int bin() {
         if (bin_state < 0 || !compiled) return 0;
-        if (rebin_every && steps_since_bin >= rebin_every && unbin()) return 1;
-        auto keys = ray_keys(false);
         gfb_ctx *ctx = impl->context().device();
-        if (!gfb_is_binned(ctx)) {
-            if (gfb_bin_rays(ctx, keys[bin_state], bin_lo, bin_hi, bin_cells, keys.data(), static_cast<int> (keys.size()), n)) return 1;
-            steps_since_bin = 0;
+        if (gfb_is_binned(ctx) && !(rebin_every && steps_since_bin >= rebin_every)) return 0;
+        auto keys = ray_keys(false);
+        if (gfb_bin_rays(ctx, keys[bin_state], bin_lo, bin_hi, bin_cells, keys.data(), static_cast<int> (keys.size()), n)) return 1;
+        steps_since_bin = 0;
+        return 0;
+    }
+//  num_steps steps in pieces that end where the next re-sort is due.
+    int step_binned(const size_t num_steps) {
+        size_t left = num_steps;
+        while (left) {
+            if (bin()) return 1;
+            size_t piece = left;
+            if (bin_state >= 0 && rebin_every) piece = std::min(left, rebin_every - std::min(steps_since_bin, rebin_every - 1));
+            impl->step(piece);
+            if (bin_state >= 0 && rebin_every && gfb_flush(impl->context().device())) return 1;
+            steps_since_bin += piece;
+            left -= piece;
         }
-        steps_since_bin += steps;
         return 0;
     }
 };
@@ -448,8 +461,7 @@ int gfb_rays_compile(gfb_rays *r) {
 }
 int gfb_rays_step(gfb_rays *r, size_t num_steps) {
     if (!r->compiled) return rays_fail("step before compile");
-    if (r->bin(num_steps)) return 1;
-    r->impl->step(num_steps);
+    if (r->step_binned(num_steps)) return 1;
     return gfb_flush(r->impl->context().device());
 }
 int gfb_rays_wait(gfb_rays *r) {
@@ -515,8 +527,7 @@ int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out
     keys.push_back(reinterpret_cast<uint64_t> (r->impl->residual().get()));
     gfb_ctx *ctx = r->impl->context().device();
     for (size_t b = 0; b < num_blocks; b++) {
-        if (r->bin(sub_steps)) return 1;
-        r->impl->step(sub_steps);
+        if (r->step_binned(sub_steps)) return 1;
         if (r->unbin()) return 1;           // records are in the caller's ray order
         if (gfb_snapshot_async(ctx, keys.data(), static_cast<int> (keys.size()), sizeof(double)*r->n,
                                out + b*keys.size()*r->n)) return 1;

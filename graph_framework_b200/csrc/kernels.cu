@@ -148,6 +148,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(double *__restrict__ dst, 
     for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) dst[perm[i]] = __ldg(src + i);
 }
 
+//  Composition of two permutations: total[i] = first[second[i]].
+__global__ void __launch_bounds__(256) compose_kernel(unsigned *__restrict__ total, const unsigned *__restrict__ first,
+                                                      const unsigned *__restrict__ second, const unsigned n) {
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) total[i] = first[second[i]];
+}
+
 //  8 independent FMA chains per thread keep the FP64 pipe saturated.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, const int iters, const double a, const double b) {
     double r0 = threadIdx.x, r1 = r0 + 1.0, r2 = r0 + 2.0, r3 = r0 + 3.0;
@@ -218,6 +224,11 @@ int gfb_k_permute(double *dst, const double *src, const unsigned *perm, unsigned
     const unsigned grid = static_cast<unsigned> ((n + 255u)/256u < static_cast<unsigned> (sms)*16u ? (n + 255u)/256u : sms*16);
     if (scatter) scatter_kernel<<<grid ? grid : 1, 256, 0, s>>> (dst, src, perm, n);
     else gather_kernel<<<grid ? grid : 1, 256, 0, s>>> (dst, src, perm, n);
+    return static_cast<int> (cudaGetLastError());
+}
+int gfb_k_compose(unsigned *total, const unsigned *first, const unsigned *second, unsigned n, int sms, cudaStream_t s) {
+    const unsigned grid = static_cast<unsigned> ((n + 255u)/256u < static_cast<unsigned> (sms)*16u ? (n + 255u)/256u : sms*16);
+    compose_kernel<<<grid ? grid : 1, 256, 0, s>>> (total, first, second, n);
     return static_cast<int> (cudaGetLastError());
 }
 int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s) {

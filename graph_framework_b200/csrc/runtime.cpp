@@ -41,6 +41,7 @@ int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s);
 int gfb_k_bin_permutation(const double *values, unsigned n, double lo, double hi, unsigned cells,
                           unsigned *work, unsigned *perm, int sms, cudaStream_t s);
 int gfb_k_permute(double *dst, const double *src, const unsigned *perm, unsigned n, int scatter, int sms, cudaStream_t s);
+int gfb_k_compose(unsigned *total, const unsigned *first, const unsigned *second, unsigned n, int sms, cudaStream_t s);
 int gfb_k_fill(double *p, size_t n, double v, int sms, cudaStream_t s);
 }
 
@@ -238,6 +239,7 @@ struct gfb_ctx {
     cudaStream_t upload_stream = nullptr;
 //  Ray binning: the permutation in force (perm[slot] = original ray), scratch for the moves.
     unsigned *bin_perm = nullptr;
+    unsigned *bin_step = nullptr;       // the permutation of one re-sort, before it is composed into bin_perm
     unsigned *bin_work = nullptr;
     double *bin_scratch = nullptr;
     size_t bin_capacity = 0, bin_cells = 0;
@@ -323,6 +325,7 @@ void gfb_ctx_destroy(gfb_ctx *c) {
     if (c->scratch) cudaFree(c->scratch);
     if (c->scratch_host) cudaFreeHost(c->scratch_host);
     if (c->bin_perm) cudaFree(c->bin_perm);
+    if (c->bin_step) cudaFree(c->bin_step);
     if (c->bin_work) cudaFree(c->bin_work);
     if (c->bin_scratch) cudaFree(c->bin_scratch);
     if (c->flush_buffer) cudaFree(c->flush_buffer);
@@ -783,13 +786,13 @@ int gfb_timer_stop(gfb_ctx *c, float *ms) {
 void *gfb_stream(gfb_ctx *c) { return c->stream; }
 
 namespace {
-int move_rays(gfb_ctx *c, const uint64_t *keys, int num_keys, size_t n, int scatter) {
+int move_rays(gfb_ctx *c, const unsigned *perm, const uint64_t *keys, int num_keys, size_t n, int scatter) {
     for (int i = 0; i < num_keys; i++) {
         auto it = c->buffers.find(keys[i]);
         if (it == c->buffers.end()) return fail("ray binning: unknown buffer key");
         if (it->second.bytes < n*sizeof(double)) return fail("ray binning: buffer shorter than the ray count");
         double *data = static_cast<double *> (it->second.dev);
-        if (gfb_k_permute(c->bin_scratch, data, c->bin_perm, static_cast<unsigned> (n), scatter, c->sms, c->stream)) {
+        if (gfb_k_permute(c->bin_scratch, data, perm, static_cast<unsigned> (n), scatter, c->sms, c->stream)) {
             return fail("ray binning: permute launch failed");
         }
         if (check(cudaMemcpyAsync(data, c->bin_scratch, n*sizeof(double), cudaMemcpyDeviceToDevice, c->stream), "bin copy back")) return 1;
@@ -803,14 +806,16 @@ int gfb_bin_rays(gfb_ctx *c, uint64_t sort_key, double lo, double hi, unsigned c
                  const uint64_t *keys, int num_keys, size_t n) {
     if (flush(c)) return 1;
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
-    if (c->binned) return fail("gfb_bin_rays: already binned, call gfb_unbin_rays first");
     if (cells == 0 || !(hi > lo) || n == 0 || n > 0xffffffffull) return fail("gfb_bin_rays: bad arguments");
     if (c->bin_capacity < n || c->bin_cells < cells) {
+        if (c->binned) return fail("gfb_bin_rays: cannot grow while binned, call gfb_unbin_rays first");
         cudaStreamSynchronize(c->stream);
         if (c->bin_perm) cudaFree(c->bin_perm);
+        if (c->bin_step) cudaFree(c->bin_step);
         if (c->bin_work) cudaFree(c->bin_work);
         if (c->bin_scratch) cudaFree(c->bin_scratch);
         if (check(cudaMalloc(&c->bin_perm, n*sizeof(unsigned)), "bin perm")) return 1;
+        if (check(cudaMalloc(&c->bin_step, n*sizeof(unsigned)), "bin step")) return 1;
         if (check(cudaMalloc(&c->bin_work, (n + 2*static_cast<size_t> (cells))*sizeof(unsigned)), "bin work")) return 1;
         if (check(cudaMalloc(&c->bin_scratch, n*sizeof(double)), "bin scratch")) return 1;
         c->bin_capacity = n;
@@ -818,10 +823,19 @@ int gfb_bin_rays(gfb_ctx *c, uint64_t sort_key, double lo, double hi, unsigned c
     }
     auto it = c->buffers.find(sort_key);
     if (it == c->buffers.end()) return fail("gfb_bin_rays: unknown sort key");
+//  Already binned: sort the current order again and fold the new permutation into the one in force,
+//  so that gfb_unbin_rays still restores the caller's order with one scatter per array.
+    unsigned *perm = c->binned ? c->bin_step : c->bin_perm;
     if (gfb_k_bin_permutation(static_cast<const double *> (it->second.dev), static_cast<unsigned> (n), lo, hi, cells,
-                              c->bin_work, c->bin_perm, c->sms, c->stream)) return fail("gfb_bin_rays: launch failed");
+                              c->bin_work, perm, c->sms, c->stream)) return fail("gfb_bin_rays: launch failed");
     c->launches += 3;
-    if (move_rays(c, keys, num_keys, n, 0)) return 1;
+    if (move_rays(c, perm, keys, num_keys, n, 0)) return 1;
+    if (c->binned) {
+        unsigned *total = c->bin_work + 2*static_cast<size_t> (cells);      // the cell_of area is free again
+        if (gfb_k_compose(total, c->bin_perm, c->bin_step, static_cast<unsigned> (n), c->sms, c->stream)) return fail("gfb_bin_rays: compose failed");
+        if (check(cudaMemcpyAsync(c->bin_perm, total, n*sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream), "bin compose copy")) return 1;
+        c->launches++;
+    }
     c->binned = true;
     return 0;
 }
@@ -830,7 +844,7 @@ int gfb_unbin_rays(gfb_ctx *c, const uint64_t *keys, int num_keys, size_t n) {
     if (!c->binned) return 0;
     if (flush(c)) return 1;
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
-    if (move_rays(c, keys, num_keys, n, 1)) return 1;
+    if (move_rays(c, c->bin_perm, keys, num_keys, n, 1)) return 1;
     c->binned = false;
     return 0;
 }
