@@ -259,8 +259,8 @@ def main():
     tracer.compile()
     if eq == "vmec":
         # rays of one radial cell share Fourier coefficient rows: keep them sorted by cell (198-point s grid),
-        # re-sorted every 20 steps (rays cross about one cell per 50 steps); the sorts are inside the timed region
-        tracer.set_binning("x", 0.0, 1.0, 197, rebin_every=20)
+        # re-sorted every 50 steps; the sorts are inside the timed region
+        tracer.set_binning("x", 0.0, 1.0, 197, rebin_every=50)
     t_ready = time.perf_counter()
     stats = tracer.kernel_stats()
     fp64_peak = tracer.fp64_peak()
