@@ -81,6 +81,8 @@ def _load():
         "gfb_rays_absorption_reset": (I, [P]),
         "gfb_rays_set_binning": (I, [P, I, D, D, ctypes.c_uint, SZ]),
         "gfb_bin_rays": (I, [P, ctypes.c_uint64, D, D, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64), I, SZ]),
+        "gfb_bin_rays_rz": (I, [P, ctypes.POINTER(ctypes.c_uint64), c_double_p, c_double_p, ctypes.POINTER(ctypes.c_uint),
+                                ctypes.POINTER(ctypes.c_uint64), I, SZ]),
         "gfb_unbin_rays": (I, [P, ctypes.POINTER(ctypes.c_uint64), I, SZ]),
         "gfb_is_binned": (I, [P]),
         "gfb_rays_device_ptr": (I, [P, I, c_void_pp]),
@@ -94,6 +96,7 @@ def _load():
         "gfb_boris_compile": (I, [P]),
         "gfb_boris_step": (I, [P, SZ]),
         "gfb_boris_get_state": (I, [P, ctypes.POINTER(c_double_p)]),
+        "gfb_boris_set_binning": (I, [P, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_uint), SZ]),
         "gfb_boris_info": (I, [P, c_double_p, c_double_p]),
         "gfb_boris_ctx": (P, [P]),
         # graph_c_binding.h

@@ -637,6 +637,30 @@ struct gfb_boris {
     std::unique_ptr<workflow::manager<>> work;
     double b0 = 0.0, larmor = 0.0;
     bool compiled = false;
+//  Particles kept sorted by the (R, Z) cell of the field tables (gfb_boris_set_binning).
+    bool binning = false;
+    double bin_lo[2] = {0.0, 0.0}, bin_hi[2] = {1.0, 1.0};
+    unsigned bin_cells[2] = {0, 0};
+    size_t rebin_every = 0, steps_since_bin = 0;
+    std::vector<uint64_t> keys() const {
+        std::vector<uint64_t> k;
+        for (auto &v : vars) k.push_back(reinterpret_cast<uint64_t> (v.get()));
+        return k;
+    }
+    int unbin() {
+        if (!binning || !compiled) return 0;
+        auto k = keys();
+        return gfb_unbin_rays(work->get_context().device(), k.data(), static_cast<int> (k.size()), n);
+    }
+    int bin() {
+        if (!binning || !compiled) return 0;
+        gfb_ctx *ctx = work->get_context().device();
+        if (gfb_is_binned(ctx) && !(rebin_every && steps_since_bin >= rebin_every)) return 0;
+        auto k = keys();
+        if (gfb_bin_rays_rz(ctx, k.data(), bin_lo, bin_hi, bin_cells, k.data(), static_cast<int> (k.size()), n)) return 1;
+        steps_since_bin = 0;
+        return 0;
+    }
 };
 
 extern "C" {
@@ -703,7 +727,21 @@ gfb_boris *gfb_boris_create(const char *equilibrium_name, const char *table_file
     return b.release();
 }
 void gfb_boris_destroy(gfb_boris *b) { delete b; }
+int gfb_boris_set_binning(gfb_boris *b, const double *lo, const double *hi, const unsigned *cells, size_t rebin_every) {
+    if (b->unbin()) return 1;
+    b->binning = cells && cells[0] && cells[1];
+    if (b->binning) {
+        for (int i = 0; i < 2; i++) {
+            b->bin_lo[i] = lo[i];
+            b->bin_hi[i] = hi[i];
+            b->bin_cells[i] = cells[i];
+        }
+    }
+    b->rebin_every = rebin_every;
+    return 0;
+}
 int gfb_boris_set_state(gfb_boris *b, const double *const state[6]) {
+    if (b->unbin()) return 1;
     for (int i = 0; i < 6; i++) {
         if (!state[i]) continue;
         b->vars[i]->set(std::vector<double> (state[i], state[i] + b->n));
@@ -720,10 +758,20 @@ int gfb_boris_compile(gfb_boris *b) {
 }
 int gfb_boris_step(gfb_boris *b, size_t num_steps) {
     if (!b->compiled) return rays_fail("step before compile");
-    for (size_t i = 0; i < num_steps; i++) b->work->run();
-    return gfb_flush(b->work->get_context().device());
+    size_t left = num_steps;
+    while (left) {
+        if (b->bin()) return 1;
+        size_t piece = left;
+        if (b->binning && b->rebin_every) piece = std::min(left, b->rebin_every - std::min(b->steps_since_bin, b->rebin_every - 1));
+        for (size_t i = 0; i < piece; i++) b->work->run();
+        if (gfb_flush(b->work->get_context().device())) return 1;
+        b->steps_since_bin += piece;
+        left -= piece;
+    }
+    return 0;
 }
 int gfb_boris_get_state(gfb_boris *b, double *const state[7]) {
+    if (b->unbin()) return 1;
     for (int i = 0; i < 7; i++) if (state[i]) b->work->copy_to_host(b->vars[i], state[i]);
     return 0;
 }

@@ -104,8 +104,21 @@ __global__ void __launch_bounds__(256) deposit_kernel(const double *__restrict__
 //  coefficient rows it gathers (VMEC: 86 modes x 3 quantities per cell).  The order inside a cell is
 //  whatever the atomics give -- per-ray results do not depend on the slot a ray occupies.
 //------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bin_count_kernel(const double *__restrict__ v, const unsigned n,
-                                                        const double lo, const double inv_width, const unsigned cells,
+//  Cell of ray i: 1-D grid on array a, or the (R, Z) grid of an axisymmetric table on arrays
+//  (a, b, c) = (x, y, z) with R = sqrt(x^2 + y^2).  Same clamp as the table look-ups; NaN lands in cell 0.
+struct cell_grid {
+    const double *a, *b, *c;
+    double lo0, inv0, lo1, inv1;
+    unsigned n0, n1;                // n1 = 0: one dimensional
+    __device__ __forceinline__ unsigned operator()(const unsigned i) const {
+        const double u = n1 ? sqrt(__ldg(a + i)*__ldg(a + i) + __ldg(b + i)*__ldg(b + i)) : __ldg(a + i);
+        const unsigned i0 = static_cast<unsigned> (fmin(fmax((u - lo0)*inv0, 0.0), static_cast<double> (n0 - 1u)));
+        if (!n1) return i0;
+        const unsigned i1 = static_cast<unsigned> (fmin(fmax((__ldg(c + i) - lo1)*inv1, 0.0), static_cast<double> (n1 - 1u)));
+        return i0*n1 + i1;
+    }
+};
+__global__ void __launch_bounds__(256) bin_count_kernel(const cell_grid grid, const unsigned n,
                                                         unsigned *__restrict__ cell_of, unsigned *__restrict__ count) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned rounded = (n + 31u) & ~31u;
@@ -113,7 +126,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const double *__restrict
         const bool active = i < n;
         unsigned cell = 0;
         if (active) {
-            cell = static_cast<unsigned> (fmin(fmax((__ldg(v + i) - lo)*inv_width, 0.0), static_cast<double> (cells - 1u)));
+            cell = grid(i);
             cell_of[i] = cell;
         }
         const unsigned mask = __ballot_sync(0xffffffffu, active);
@@ -210,12 +223,18 @@ int gfb_k_deposit(const double *x, const double *y, const double *z, const doubl
     return static_cast<int> (cudaGetLastError());
 }
 //  perm[slot] = ray that moves into `slot`.  work: cells*2 + n unsigned (count, cursor, cell_of).
-int gfb_k_bin_permutation(const double *values, unsigned n, double lo, double hi, unsigned cells,
-                          unsigned *work, unsigned *perm, int sms, cudaStream_t s) {
+//  values[1], values[2] non-null select the (R, Z) grid; cells = cells0*max(cells1, 1).
+int gfb_k_bin_permutation(const double *const values[3], unsigned n, const double lo[2], const double hi[2],
+                          const unsigned cells01[2], unsigned *work, unsigned *perm, int sms, cudaStream_t s) {
+    const unsigned cells = cells01[0]*(cells01[1] ? cells01[1] : 1u);
     unsigned *count = work, *cursor = work + cells, *cell_of = work + 2*cells;
     const unsigned grid = static_cast<unsigned> ((n + 255u)/256u < static_cast<unsigned> (sms)*8u ? (n + 255u)/256u : sms*8);
+    cell_grid g;
+    g.a = values[0]; g.b = values[1]; g.c = values[2];
+    g.lo0 = lo[0]; g.inv0 = cells01[0]/(hi[0] - lo[0]); g.n0 = cells01[0];
+    g.lo1 = lo[1]; g.inv1 = cells01[1] ? cells01[1]/(hi[1] - lo[1]) : 0.0; g.n1 = cells01[1];
     cudaMemsetAsync(count, 0, sizeof(unsigned)*cells, s);
-    bin_count_kernel<<<grid ? grid : 1, 256, 0, s>>> (values, n, lo, cells/(hi - lo), cells, cell_of, count);
+    bin_count_kernel<<<grid ? grid : 1, 256, 0, s>>> (g, n, cell_of, count);
     bin_scan_kernel<<<1, 32, 0, s>>> (count, cursor, cells);
     bin_place_kernel<<<grid ? grid : 1, 256, 0, s>>> (cell_of, n, cursor, perm);
     return static_cast<int> (cudaGetLastError());

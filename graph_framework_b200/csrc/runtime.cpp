@@ -38,8 +38,8 @@ double gfb_k_unorder(unsigned long long key);
 int gfb_k_deposit(const double *x, const double *y, const double *z, const double *w, unsigned long long n,
                   double *hist, const double *lo, const double *hi, const int *bins, int sms, cudaStream_t s);
 int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s);
-int gfb_k_bin_permutation(const double *values, unsigned n, double lo, double hi, unsigned cells,
-                          unsigned *work, unsigned *perm, int sms, cudaStream_t s);
+int gfb_k_bin_permutation(const double *const values[3], unsigned n, const double lo[2], const double hi[2],
+                          const unsigned cells01[2], unsigned *work, unsigned *perm, int sms, cudaStream_t s);
 int gfb_k_permute(double *dst, const double *src, const unsigned *perm, unsigned n, int scatter, int sms, cudaStream_t s);
 int gfb_k_compose(unsigned *total, const unsigned *first, const unsigned *second, unsigned n, int sms, cudaStream_t s);
 int gfb_k_fill(double *p, size_t n, double v, int sms, cudaStream_t s);
@@ -802,11 +802,15 @@ int move_rays(gfb_ctx *c, const unsigned *perm, const uint64_t *keys, int num_ke
 }
 }
 
-int gfb_bin_rays(gfb_ctx *c, uint64_t sort_key, double lo, double hi, unsigned cells,
-                 const uint64_t *keys, int num_keys, size_t n) {
+namespace {
+int bin_rays(gfb_ctx *c, const uint64_t *sort_keys, int num_sort_keys, const double lo[2], const double hi[2],
+             const unsigned cells01[2], const uint64_t *keys, int num_keys, size_t n) {
     if (flush(c)) return 1;
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
-    if (cells == 0 || !(hi > lo) || n == 0 || n > 0xffffffffull) return fail("gfb_bin_rays: bad arguments");
+    const size_t cells = static_cast<size_t> (cells01[0])*(cells01[1] ? cells01[1] : 1u);
+    if (cells == 0 || cells > (1u << 24) || !(hi[0] > lo[0]) || (cells01[1] && !(hi[1] > lo[1])) || n == 0 || n > 0xffffffffull) {
+        return fail("gfb_bin_rays: bad arguments");
+    }
     if (c->bin_capacity < n || c->bin_cells < cells) {
         if (c->binned) return fail("gfb_bin_rays: cannot grow while binned, call gfb_unbin_rays first");
         cudaStreamSynchronize(c->stream);
@@ -816,28 +820,47 @@ int gfb_bin_rays(gfb_ctx *c, uint64_t sort_key, double lo, double hi, unsigned c
         if (c->bin_scratch) cudaFree(c->bin_scratch);
         if (check(cudaMalloc(&c->bin_perm, n*sizeof(unsigned)), "bin perm")) return 1;
         if (check(cudaMalloc(&c->bin_step, n*sizeof(unsigned)), "bin step")) return 1;
-        if (check(cudaMalloc(&c->bin_work, (n + 2*static_cast<size_t> (cells))*sizeof(unsigned)), "bin work")) return 1;
+        if (check(cudaMalloc(&c->bin_work, (n + 2*cells)*sizeof(unsigned)), "bin work")) return 1;
         if (check(cudaMalloc(&c->bin_scratch, n*sizeof(double)), "bin scratch")) return 1;
         c->bin_capacity = n;
         c->bin_cells = cells;
     }
-    auto it = c->buffers.find(sort_key);
-    if (it == c->buffers.end()) return fail("gfb_bin_rays: unknown sort key");
+    const double *values[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < num_sort_keys; i++) {
+        auto it = c->buffers.find(sort_keys[i]);
+        if (it == c->buffers.end()) return fail("gfb_bin_rays: unknown sort key");
+        if (it->second.bytes < n*sizeof(double)) return fail("gfb_bin_rays: sort array shorter than the ray count");
+        values[i] = static_cast<const double *> (it->second.dev);
+    }
 //  Already binned: sort the current order again and fold the new permutation into the one in force,
 //  so that gfb_unbin_rays still restores the caller's order with one scatter per array.
     unsigned *perm = c->binned ? c->bin_step : c->bin_perm;
-    if (gfb_k_bin_permutation(static_cast<const double *> (it->second.dev), static_cast<unsigned> (n), lo, hi, cells,
-                              c->bin_work, perm, c->sms, c->stream)) return fail("gfb_bin_rays: launch failed");
+    if (gfb_k_bin_permutation(values, static_cast<unsigned> (n), lo, hi, cells01, c->bin_work, perm, c->sms, c->stream)) {
+        return fail("gfb_bin_rays: launch failed");
+    }
     c->launches += 3;
     if (move_rays(c, perm, keys, num_keys, n, 0)) return 1;
     if (c->binned) {
-        unsigned *total = c->bin_work + 2*static_cast<size_t> (cells);      // the cell_of area is free again
+        unsigned *total = c->bin_work + 2*cells;        // the cell_of area is free again
         if (gfb_k_compose(total, c->bin_perm, c->bin_step, static_cast<unsigned> (n), c->sms, c->stream)) return fail("gfb_bin_rays: compose failed");
         if (check(cudaMemcpyAsync(c->bin_perm, total, n*sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream), "bin compose copy")) return 1;
         c->launches++;
     }
     c->binned = true;
     return 0;
+}
+}
+
+int gfb_bin_rays(gfb_ctx *c, uint64_t sort_key, double lo, double hi, unsigned cells,
+                 const uint64_t *keys, int num_keys, size_t n) {
+    const double lo2[2] = {lo, 0.0}, hi2[2] = {hi, 1.0};
+    const unsigned cells2[2] = {cells, 0u};
+    return bin_rays(c, &sort_key, 1, lo2, hi2, cells2, keys, num_keys, n);
+}
+int gfb_bin_rays_rz(gfb_ctx *c, const uint64_t *xyz_keys, const double *lo, const double *hi, const unsigned *cells,
+                    const uint64_t *keys, int num_keys, size_t n) {
+    if (!cells[1]) return fail("gfb_bin_rays_rz: needs cells in both directions");
+    return bin_rays(c, xyz_keys, 3, lo, hi, cells, keys, num_keys, n);
 }
 int gfb_is_binned(gfb_ctx *c) { return c->binned ? 1 : 0; }
 int gfb_unbin_rays(gfb_ctx *c, const uint64_t *keys, int num_keys, size_t n) {

@@ -258,6 +258,18 @@ class BorisPusher:
     def compile(self):
         check(lib.gfb_boris_compile(self.h), "boris compile")
 
+    def set_binning(self, r_grid, z_grid, rebin_every=100):
+        """Keep particles sorted by the (R, Z) cell of the field tables while stepping; invisible to
+        the caller.  r_grid, z_grid = (lo, hi, cells); None switches it off."""
+        if r_grid is None:
+            check(lib.gfb_boris_set_binning(self.h, None, None, None, 0), "boris set_binning")
+            return
+        lo = np.array([r_grid[0], z_grid[0]], dtype=np.float64)
+        hi = np.array([r_grid[1], z_grid[1]], dtype=np.float64)
+        cells = (ctypes.c_uint*2)(int(r_grid[2]), int(z_grid[2]))
+        check(lib.gfb_boris_set_binning(self.h, lo.ctypes.data_as(c_double_p), hi.ctypes.data_as(c_double_p), cells,
+                                        int(rebin_every)), "boris set_binning")
+
     def step(self, n=1):
         check(lib.gfb_boris_step(self.h, int(n)), "boris step")
 

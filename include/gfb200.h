@@ -131,6 +131,10 @@ int gfb_snapshot_async(gfb_ctx *ctx, const uint64_t *keys, int num_keys, size_t 
  * the caller's order (no-op when not binned).  No reference counterpart: the reference never reorders. */
 int gfb_bin_rays(gfb_ctx *ctx, uint64_t sort_key, double lo, double hi, unsigned cells,
                  const uint64_t *keys, int num_keys, size_t n);
+/* The same with the (R, Z) cell of an axisymmetric 2-D table: xyz_keys = the x, y, z arrays,
+ * R = sqrt(x^2 + y^2); lo/hi/cells = {R, Z}; cell = i_R*cells[1] + i_Z (the piecewise_2D layout). */
+int gfb_bin_rays_rz(gfb_ctx *ctx, const uint64_t *xyz_keys, const double *lo, const double *hi, const unsigned *cells,
+                    const uint64_t *keys, int num_keys, size_t n);
 int gfb_unbin_rays(gfb_ctx *ctx, const uint64_t *keys, int num_keys, size_t n);
 int gfb_is_binned(gfb_ctx *ctx);
 

@@ -112,6 +112,10 @@ int gfb_boris_set_state(gfb_boris *b, const double *const state[6]);
 int gfb_boris_compile(gfb_boris *b);          /* also runs the initialize_gamma pre-item */
 int gfb_boris_step(gfb_boris *b, size_t num_steps);
 int gfb_boris_get_state(gfb_boris *b, double *const state[7]);
+/* Keep the particles sorted by the (R, Z) cell of the field tables while stepping (gfb_bin_rays_rz in
+ * gfb200.h): lo/hi/cells = {R, Z} grid, re-sorted every `rebin_every` steps (0: only when the order was
+ * restored by a call that reads or writes particles by index).  cells = NULL switches it off. */
+int gfb_boris_set_binning(gfb_boris *b, const double *lo, const double *hi, const unsigned *cells, size_t rebin_every);
 int gfb_boris_info(gfb_boris *b, double *b0, double *larmor_radius);
 gfb_ctx *gfb_boris_ctx(gfb_boris *b);
 
