@@ -163,9 +163,8 @@ def boris_arm(args, rank, local_rank, world):
     push = BorisPusher("efit", n, dt=0.5, device=local_rank, options="fused_steps=%d %s" % (SUB_STEPS, args.options))
     push.set_state(x, y, z, ux, uy, uz)
     push.compile()
-    # particles of one (R, Z) cell of the EFIT tables (64 x 64, tests/golden/efit.gfbt) share coefficient rows:
-    # keep them sorted by cell on the device, re-sorted every 1000 pushes (inside the timed region when due)
-    push.set_binning((0.84, 0.84 + 64*0.0265625, 64), (-1.6, 1.6, 64), rebin_every=1000)
+    # (the pusher keeps particles sorted by the (R, Z) cell of the EFIT tables, re-sorted every 1000 pushes,
+    #  inside the timed region when due; --options bin_rays=0 switches it off)
     for _ in range(args.warmup):
         push.step(SUB_STEPS)
     torch.cuda.synchronize()
@@ -261,10 +260,9 @@ def main():
     tracer.init("kx")                                      # device-resident per-ray Newton
     t_compile = time.perf_counter()
     tracer.compile()
-    if eq == "vmec":
-        # rays of one radial cell share Fourier coefficient rows: keep them sorted by cell (198-point s grid),
-        # re-sorted every 50 steps; the sorts are inside the timed region
-        tracer.set_binning("x", 0.0, 1.0, 197, rebin_every=50)
+    # (tabulated equilibria: the tracer keeps rays sorted by table cell while stepping -- EFIT (R, Z) cells,
+    #  re-sorted every 1000 steps; VMEC radial cells, every 50 steps -- inside the timed region when due;
+    #  --options bin_rays=0 switches it off)
     t_ready = time.perf_counter()
     stats = tracer.kernel_stats()
     fp64_peak = tracer.fp64_peak()

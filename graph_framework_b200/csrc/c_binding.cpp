@@ -215,6 +215,7 @@ struct run_options {
     int unroll_stages = -1;         // -1: decided by body size (jit::context::compile)
     unsigned fused_steps = 0;
     bool absorption = false;
+    int bin_rays = -1;              // -1: on when the equilibrium has tables; 0 off; > 0 re-sort period in steps
 };
 run_options parse_options(const char *options) {
     run_options o;
@@ -235,6 +236,7 @@ run_options parse_options(const char *options) {
         else if (k == "unroll_stages") o.unroll_stages = v != 0 ? 1 : 0;
         else if (k == "fused_steps") o.fused_steps = static_cast<unsigned> (v);
         else if (k == "absorption") o.absorption = v != 0;
+        else if (k == "bin_rays") o.bin_rays = static_cast<int> (v);
     }
     return o;
 }
@@ -339,11 +341,12 @@ struct gfb_rays {
     bool absorption_started = false;
     char profile_tag = 0;             // its address keys the deposition profile buffer
     std::string source;
-//  Binning by table cell (gfb_rays_set_binning): applied before stepping, undone before anything
-//  reads or writes rays by index.
+//  Binning by table cell: applied before stepping, undone before anything reads or writes rays by
+//  index.  bin_dims = 1: cells of state[bin_state]; 2: (R, Z) cells of (x, y, z).
+    int bin_dims = 0;
     int bin_state = -1;
-    double bin_lo = 0.0, bin_hi = 1.0;
-    unsigned bin_cells = 0;
+    double bin_lo[2] = {0.0, 0.0}, bin_hi[2] = {1.0, 1.0};
+    unsigned bin_cells[2] = {0, 0};
     size_t rebin_every = 0, steps_since_bin = 0;
     std::vector<uint64_t> ray_keys(const bool with_residual) const {
         std::vector<uint64_t> keys;
@@ -353,7 +356,7 @@ struct gfb_rays {
     }
 //  Back to the caller's ray order: the state and the residual of the last launch.
     int unbin() {
-        if (bin_state < 0 || !compiled) return 0;
+        if (!bin_dims || !compiled) return 0;
         auto keys = ray_keys(true);
         return gfb_unbin_rays(impl->context().device(), keys.data(), static_cast<int> (keys.size()), n);
     }
@@ -361,11 +364,17 @@ struct gfb_rays {
 //  is `rebin_every` steps old (re-sorting composes permutations, no round trip through the caller's
 //  order).  The residual is rewritten by the launch, so it is not moved here.
     int bin() {
-        if (bin_state < 0 || !compiled) return 0;
+        if (!bin_dims || !compiled) return 0;
         gfb_ctx *ctx = impl->context().device();
         if (gfb_is_binned(ctx) && !(rebin_every && steps_since_bin >= rebin_every)) return 0;
         auto keys = ray_keys(false);
-        if (gfb_bin_rays(ctx, keys[bin_state], bin_lo, bin_hi, bin_cells, keys.data(), static_cast<int> (keys.size()), n)) return 1;
+        if (bin_dims == 1) {
+            if (gfb_bin_rays(ctx, keys[bin_state], bin_lo[0], bin_hi[0], bin_cells[0], keys.data(),
+                             static_cast<int> (keys.size()), n)) return 1;
+        } else {
+            const uint64_t xyz[3] = {keys[GFB_X], keys[GFB_Y], keys[GFB_Z]};
+            if (gfb_bin_rays_rz(ctx, xyz, bin_lo, bin_hi, bin_cells, keys.data(), static_cast<int> (keys.size()), n)) return 1;
+        }
         steps_since_bin = 0;
         return 0;
     }
@@ -375,9 +384,9 @@ struct gfb_rays {
         while (left) {
             if (bin()) return 1;
             size_t piece = left;
-            if (bin_state >= 0 && rebin_every) piece = std::min(left, rebin_every - std::min(steps_since_bin, rebin_every - 1));
+            if (bin_dims && rebin_every) piece = std::min(left, rebin_every - std::min(steps_since_bin, rebin_every - 1));
             impl->step(piece);
-            if (bin_state >= 0 && rebin_every && gfb_flush(impl->context().device())) return 1;
+            if (bin_dims && rebin_every && gfb_flush(impl->context().device())) return 1;
             steps_since_bin += piece;
             left -= piece;
         }
@@ -430,6 +439,19 @@ gfb_rays *gfb_rays_create(const char *dispersion_name, const char *equilibrium_n
     }
     r->impl.reset(t);
     if (o.absorption) t->attach_absorption(eq, num_rays);
+//  Tabulated equilibria: keep rays sorted by table cell while stepping (options: bin_rays=0 off,
+//  bin_rays=<steps> re-sort period).  Not combined with absorption, whose arrays are not moved.
+    const equilibrium::cell_grid grid = eq->get_cell_grid();
+    if (grid.dims && o.bin_rays != 0 && !o.absorption) {
+        r->bin_dims = grid.dims;
+        r->bin_state = GFB_X;
+        for (int i = 0; i < 2; i++) {
+            r->bin_lo[i] = grid.lo[i];
+            r->bin_hi[i] = grid.hi[i];
+            r->bin_cells[i] = grid.cells[i];
+        }
+        r->rebin_every = o.bin_rays > 0 ? static_cast<size_t> (o.bin_rays) : grid.drift_steps;
+    }
     return r.release();
 }
 void gfb_rays_destroy(gfb_rays *r) { delete r; }
@@ -470,13 +492,15 @@ int gfb_rays_wait(gfb_rays *r) {
 }
 int gfb_rays_set_binning(gfb_rays *r, int which_state, double lo, double hi, unsigned cells, size_t rebin_every) {
     if (which_state >= GFB_NUM_STATE) return rays_fail("bad state index");
-    if (r->impl->damping) return rays_fail("binning and absorption=1 cannot be combined");
+    if (which_state >= 0 && r->impl->damping) return rays_fail("binning and absorption=1 cannot be combined");
     if (r->unbin()) return 1;
     if (which_state >= 0 && (cells == 0 || !(hi > lo))) return rays_fail("bad binning grid");
+    r->bin_dims = which_state >= 0 ? 1 : 0;
     r->bin_state = which_state;
-    r->bin_lo = lo;
-    r->bin_hi = hi;
-    r->bin_cells = cells;
+    r->bin_lo[0] = lo;
+    r->bin_hi[0] = hi;
+    r->bin_cells[0] = cells;
+    r->bin_cells[1] = 0;
     r->rebin_every = rebin_every;
     return 0;
 }
@@ -724,6 +748,18 @@ gfb_boris *gfb_boris_create(const char *equilibrium_name, const char *table_file
         {pos_next->get_x(), x}, {pos_next->get_y(), y}, {pos_next->get_z(), z},
         {u_next->get_x(), ux}, {u_next->get_y(), uy}, {u_next->get_z(), uz}, {gamma_next, gamma}
     }, graph::shared_random_state<> (), "step", num_particles);
+//  Particles of one (R, Z) cell share the coefficient rows of the field tables: keep them sorted by
+//  cell while stepping (options: bin_rays=0 off, bin_rays=<steps> re-sort period).
+    const equilibrium::cell_grid grid = eq->get_cell_grid();
+    if (grid.dims == 2 && o.bin_rays != 0) {
+        b->binning = true;
+        for (int i = 0; i < 2; i++) {
+            b->bin_lo[i] = grid.lo[i];
+            b->bin_hi[i] = grid.hi[i];
+            b->bin_cells[i] = grid.cells[i];
+        }
+        b->rebin_every = o.bin_rays > 0 ? static_cast<size_t> (o.bin_rays) : 1000;
+    }
     return b.release();
 }
 void gfb_boris_destroy(gfb_boris *b) { delete b; }

@@ -84,6 +84,15 @@ namespace equilibrium {
 //------------------------------------------------------------------------------
 ///  Interface (equilibrium.hpp:214-470).
 //------------------------------------------------------------------------------
+///  The grid of the largest coefficient tables of an equilibrium, for keeping rays sorted by cell
+///  on the device (gfb_bin_rays / gfb_bin_rays_rz in include/gfb200.h).  dims = 0: no tables.
+    struct cell_grid {
+        int dims = 0;                   ///< 1: uniform in the first coordinate; 2: (R, Z) with R = sqrt(x^2 + y^2)
+        double lo[2] = {0.0, 0.0}, hi[2] = {1.0, 1.0};
+        unsigned cells[2] = {0, 0};
+        size_t drift_steps = 1000;      ///< hint: steps after which a re-sort pays
+    };
+
     template<typename T=double, bool SAFE_MATH=false>
     class generic {
     protected:
@@ -112,6 +121,8 @@ namespace equilibrium {
         virtual leaf_ptr get_x(leaf_ptr x1, leaf_ptr, leaf_ptr) { return x1; }
         virtual leaf_ptr get_y(leaf_ptr, leaf_ptr x2, leaf_ptr) { return x2; }
         virtual leaf_ptr get_z(leaf_ptr, leaf_ptr, leaf_ptr x3) { return x3; }
+///  Extension (no reference counterpart): see cell_grid.
+        virtual cell_grid get_cell_grid() const { return cell_grid(); }
     };
 
     template<typename T=double, bool SAFE_MATH=false>
@@ -286,6 +297,17 @@ namespace equilibrium {
         virtual leaf_ptr get_ion_temperature(const size_t, leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return ti_cache; }
         virtual vector_ptr get_magnetic_field(leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return b_cache; }
         leaf_ptr get_psi(leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return psi_cache; }
+///  The psi(R, Z) tables: numr x numz cells.  A ray at the speed of light crosses one cell in
+///  dr/dt steps; the hint assumes the reference's example step (2e-5).
+        virtual cell_grid get_cell_grid() const {
+            cell_grid g;
+            const size_t num_rows = tab.psi[0][0].size()/tab.num_cols;
+            g.dims = 2;
+            g.lo[0] = tab.rmin; g.hi[0] = tab.rmin + tab.dr*static_cast<double> (num_rows); g.cells[0] = static_cast<unsigned> (num_rows);
+            g.lo[1] = tab.zmin; g.hi[1] = tab.zmin + tab.dz*static_cast<double> (tab.num_cols); g.cells[1] = static_cast<unsigned> (tab.num_cols);
+            g.drift_steps = 1000;
+            return g;
+        }
 
 ///  |B| on the magnetic axis, found by a damped Newton search (step 0.1) for the
 ///  minimum of the normalised flux starting from (1.7, 0, 0)  (equilibrium.hpp:1584-1615).
@@ -458,6 +480,15 @@ namespace equilibrium {
         virtual leaf_ptr get_characteristic_field(const size_t=0) final {
             auto zero = graph::zero();
             return get_magnetic_field(zero, zero, zero)->length();
+        }
+///  The radial full grid of the Fourier amplitude splines (first coordinate s).
+        virtual cell_grid get_cell_grid() const {
+            cell_grid g;
+            const size_t cells = tab.rmnc[0].empty() ? 0 : tab.rmnc[0][0].size();
+            g.dims = cells ? 1 : 0;
+            g.lo[0] = tab.sminf; g.hi[0] = tab.sminf + tab.ds*static_cast<double> (cells); g.cells[0] = static_cast<unsigned> (cells);
+            g.drift_steps = 50;
+            return g;
         }
         virtual leaf_ptr get_x(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return x_cache; }
         virtual leaf_ptr get_y(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return y_cache; }

@@ -96,8 +96,6 @@ def trace_shard(args, shard, n, device, report):
     solve_for = [v for v in ("kx", "ky", "kz") if getattr(args, "init_" + v)]
     tr.init(solve_for[0] if solve_for else "")
     tr.compile()
-    if args.equilibrium == "vmec" and not absorb:
-        tr.set_binning("x", 0.0, 1.0, 197, rebin_every=50)                   # sorted by radial cell while stepping
     t1 = time.perf_counter()
     blocks = max(args.num_times//args.sub_steps, 1)
     profile = None

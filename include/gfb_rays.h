@@ -35,6 +35,8 @@ enum { GFB_T = 0, GFB_W, GFB_X, GFB_Y, GFB_Z, GFB_KX, GFB_KY, GFB_KZ, GFB_NUM_ST
  *              block=<threads> minblocks=<n> stage_tables=<0|1> share_rcp=<0|1> fast_div=<0|1> unroll_stages=<0|1>
  *              fused_steps=<max steps per launch>
  *              absorption=<0|1>  also build the weak-damping and power kernels (gfb_rays_trace_absorb)
+ *              bin_rays=<0|steps> rays of tabulated equilibria (efit, vmec) are kept sorted by table cell
+ *                                 while stepping (default on, re-sorted every 1000 / 50 steps); 0 = off
  * Mirrors the constructor sequence of xrays_bench.cpp:53-85. */
 gfb_rays *gfb_rays_create(const char *dispersion, const char *equilibrium, const char *table_file,
                           const char *solver, size_t num_rays, double dt, int device, const char *options);
@@ -67,7 +69,8 @@ int gfb_rays_step_host(gfb_rays *r, size_t num_steps, const double *const state_
  * `out` receives num_blocks records of 9 arrays of num_rays doubles ([block][9][ray]); the
  * device->host transfer of block b overlaps the stepping of block b + 1.  Pinned memory recommended. */
 int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out);
-/* Keep the rays sorted by the table cell of one state array while stepping (gfb_bin_rays in gfb200.h):
+/* Override the automatic choice (see bin_rays above) with a 1-D grid on one state array.
+ * Keeps the rays sorted by the table cell of that array while stepping (gfb_bin_rays in gfb200.h):
  * cell = trunc(clamp((state[which] - lo)/(hi - lo)*cells, 0, cells - 1)).  The state is re-sorted before a
  * block of steps when it is in the caller's order, or after `rebin_every` steps (0 = never re-sort while
  * stepping), and restored before every call that reads or writes rays by index, so the caller never sees

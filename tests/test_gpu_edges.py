@@ -147,20 +147,21 @@ def test_xrays_driver_efit_example(lib, tmp_path):
 
 
 def test_ray_binning_is_invisible_and_exact(lib):
-    """gfb_rays_set_binning: rays are kept sorted by table cell while stepping.  Each ray's arithmetic
-    does not depend on the slot it occupies, so state, residual and trajectory records must be
-    BIT-IDENTICAL to the run without binning, in the caller's order, also across re-sorts."""
+    """Rays of tabulated equilibria are kept sorted by table cell while stepping (automatic (R, Z)
+    binning for EFIT, gfb_rays_set_binning for a 1-D grid).  Each ray's arithmetic does not depend on
+    the slot it occupies, so state, residual and trajectory records must be BIT-IDENTICAL to the run
+    without binning, in the caller's order, also across re-sorts."""
     from graph_framework_b200.rays import RayTracer
     from graph_framework_b200 import workloads
     n = 20000
     state = workloads.efit_ensemble(n, seed=12)
     runs = []
-    for binning in (False, True):
-        tr = RayTracer("extra_ordinary_wave", "efit", n, 2.0e-5)
+    for variant in ("bin_rays=0", "bin_rays=150", "1d"):
+        tr = RayTracer("extra_ordinary_wave", "efit", n, 2.0e-5, options=None if variant == "1d" else variant)
         tr.set_state(state)
         tr.init("kx")
         tr.compile()
-        if binning:
+        if variant == "1d":
             tr.set_binning("y", -0.3, 0.3, 64, rebin_every=150)
         tr.step(100)
         mid = tr.get_state()
@@ -170,12 +171,13 @@ def test_ray_binning_is_invisible_and_exact(lib):
         end = tr.get_state()
         runs.append((mid, rec.copy(), end))
         tr.close()
-    for a, b in zip(runs[0], runs[1]):
-        if isinstance(a, dict):
-            for k in a:
-                assert np.array_equal(a[k], b[k]), k
-        else:
-            assert np.array_equal(a, b)
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            if isinstance(a, dict):
+                for k in a:
+                    assert np.array_equal(a[k], b[k]), k
+            else:
+                assert np.array_equal(a, b)
 
 
 def test_bin_rays_sorts_by_cell_and_unbin_restores(lib):
@@ -217,7 +219,7 @@ def test_boris_binning_is_invisible_and_exact(lib):
     start = workloads.boris_ensemble(n, seed=4)
     out = []
     for binning in (False, True):
-        b = BorisPusher("efit", n, dt=0.5)
+        b = BorisPusher("efit", n, dt=0.5, options="bin_rays=0")
         b.set_state(*start)
         b.compile()
         if binning:

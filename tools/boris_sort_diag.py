@@ -15,7 +15,7 @@ for mode in ("unsorted", "sorted", "device binning 100", "device binning 300", "
         iz = np.clip((p["z"] + 1.6)/0.05, 0, 63).astype(np.int64)
         order = np.argsort(ir*64 + iz, kind="stable")
         s = {k: v[order] for k, v in p.items()}
-    push = BorisPusher("efit", n, dt=0.5, options="fused_steps=100")
+    push = BorisPusher("efit", n, dt=0.5, options="fused_steps=100 bin_rays=0")
     push.set_state(s["x"], s["y"], s["z"], s["ux"], s["uy"], s["uz"])
     push.compile()
     if mode.startswith("device binning"):

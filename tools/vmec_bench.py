@@ -18,14 +18,16 @@ if os.environ.get("GFB_SORT_RAYS"):
     order = __import__("numpy").argsort(state["x"], kind="stable")      # radial cell locality experiment
     state = {k: v[order] for k, v in state.items()}
 t0 = time.perf_counter()
+if not os.environ.get("GFB_BIN_RAYS"):
+    opts += " bin_rays=0"                                                # default: binned by radial cell, re-sorted every 50 steps
+elif os.environ.get("GFB_REBIN"):
+    opts += " bin_rays=" + os.environ["GFB_REBIN"]
 tr = RayTracer(disp, "vmec", n, 1.0e-4, options=("fused_steps=%d " % steps) + opts)
 tr.set_state(state)
 t1 = time.perf_counter()
 tr.init("kx")
 t2 = time.perf_counter()
 tr.compile()
-if os.environ.get("GFB_BIN_RAYS"):
-    tr.set_binning("x", 0.0, 1.0, 197, rebin_every=int(os.environ.get("GFB_REBIN", "0")))      # radial cells of the VMEC grid
 t3 = time.perf_counter()
 tr.step(steps)
 tr.wait()
