@@ -137,7 +137,7 @@ def test_fused_steps_equal_single_steps(lib):
     n = start["w"].size
     out = []
     for fused in (1, 64):
-        tr = RayTracer("extra_ordinary_wave", "efit", n, float(g["dt"]), options="fused_steps=%d" % fused)
+        tr = RayTracer("extra_ordinary_wave", "efit", n, float(g["dt"]), options="fused_steps=%d bin_rays=0" % fused)      # binning adds its own launches
         tr.set_state(start)
         tr.init("")
         tr.compile()
