@@ -30,8 +30,8 @@ SUB_STEPS = 100
 #  From the committed ncu --set full captures of exactly this command (profiles/r1_ncu_*.txt):
 #  DRAM bytes read + written per launch, and the share of cycles the FP64 pipe was busy.
 NCU = {
-    "efit_xmode": {"traffic": 64075776 + 15862784, "fp64_pipe_active_pct": 71.9, "source": "profiles/r1_ncu_efit_xmode_solver_kernel.txt"},
-    "efit_cold": {"traffic": 64069120 + 8540672, "fp64_pipe_active_pct": 69.7, "source": "profiles/r1_ncu_efit_cold_solver_kernel.txt"},
+    "efit_xmode": {"traffic": 64113152 + 16543488, "fp64_pipe_active_pct": 75.6, "source": "profiles/r1_ncu_efit_xmode_solver_kernel.txt"},
+    "efit_cold": {"traffic": 64047360 + 9921792, "fp64_pipe_active_pct": 73.9, "source": "profiles/r1_ncu_efit_cold_solver_kernel.txt"},
 }
 WORKLOADS = {
     # name: (dispersion, equilibrium, default rays per GPU, dt)

@@ -136,20 +136,46 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const cell_grid grid, co
         }
     }
 }
-//  Exclusive scan of the (few hundred) cell counts; also primes the placement cursors.
-__global__ void bin_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ cursor, const unsigned cells) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned sum = 0;
-        for (unsigned c = 0; c < cells; c++) {
-            cursor[c] = sum;
-            sum += count[c];
-        }
+//  Exclusive scan of the cell counts by one block (cells <= 2^24); also primes the placement cursors.
+__global__ void __launch_bounds__(1024) bin_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ cursor,
+                                                        const unsigned cells) {
+    __shared__ unsigned partial[1024];
+    const unsigned per = (cells + blockDim.x - 1u)/blockDim.x;
+    const unsigned begin = min(threadIdx.x*per, cells), end = min(begin + per, cells);
+    unsigned sum = 0;
+    for (unsigned c = begin; c < end; c++) sum += count[c];
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    for (unsigned stride = 1; stride < blockDim.x; stride <<= 1) {      // Hillis-Steele inclusive scan
+        const unsigned v = threadIdx.x >= stride ? partial[threadIdx.x - stride] : 0u;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned offset = threadIdx.x ? partial[threadIdx.x - 1u] : 0u;
+    for (unsigned c = begin; c < end; c++) {
+        cursor[c] = offset;
+        offset += count[c];
     }
 }
+//  Lanes of a warp that go to the same cell reserve their slots with ONE atomic (a narrow beam puts
+//  most of a warp in one cell) and keep their relative order.
 __global__ void __launch_bounds__(256) bin_place_kernel(const unsigned *__restrict__ cell_of, const unsigned n,
                                                         unsigned *__restrict__ cursor, unsigned *__restrict__ perm) {
-    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
-        perm[atomicAdd(cursor + cell_of[i], 1u)] = i;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned rounded = (n + 31u) & ~31u;
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < rounded; i += gridDim.x*blockDim.x) {
+        const bool active = i < n;
+        const unsigned cell = active ? cell_of[i] : 0u;
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const unsigned peers = __match_any_sync(mask, cell);
+            const unsigned leader = __ffs(peers) - 1u;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(cursor + cell, static_cast<unsigned> (__popc(peers)));
+            base = __shfl_sync(peers, base, leader);
+            perm[base + __popc(peers & ((1u << lane) - 1u))] = i;
+        }
     }
 }
 __global__ void __launch_bounds__(256) gather_kernel(double *__restrict__ dst, const double *__restrict__ src,
@@ -235,7 +261,7 @@ int gfb_k_bin_permutation(const double *const values[3], unsigned n, const doubl
     g.lo1 = lo[1]; g.inv1 = cells01[1] ? cells01[1]/(hi[1] - lo[1]) : 0.0; g.n1 = cells01[1];
     cudaMemsetAsync(count, 0, sizeof(unsigned)*cells, s);
     bin_count_kernel<<<grid ? grid : 1, 256, 0, s>>> (g, n, cell_of, count);
-    bin_scan_kernel<<<1, 32, 0, s>>> (count, cursor, cells);
+    bin_scan_kernel<<<1, 1024, 0, s>>> (count, cursor, cells);
     bin_place_kernel<<<grid ? grid : 1, 256, 0, s>>> (cell_of, n, cursor, perm);
     return static_cast<int> (cudaGetLastError());
 }
