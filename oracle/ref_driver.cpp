@@ -315,6 +315,9 @@ static int korc(int argc, char **argv) {
 }
 
 //  The weak damping stage followed by the power stage, as xrays.cpp main() chains them.
+//  (GFB_REF_DRIVER_REAL_ONLY: builds of this driver on a device context that implements the FP64
+//  path only -- integration/Makefile -- leave the complex<double> stage out.)
+#ifndef GFB_REF_DRIVER_REAL_ONLY
 static int absorb(int argc, char **argv) {
     typedef std::complex<double> C;
     constexpr bool SAFE = true;
@@ -434,6 +437,8 @@ static int absorb(int argc, char **argv) {
     return 0;
 }
 
+#endif
+
 static int erfi_values(int argc, char **argv) {
     const size_t n = std::stoul(argv[2]);
     auto in = read_arrays(argv[3], 1, n);
@@ -475,8 +480,10 @@ int main(int argc, char **argv) {
         if (d == "simple") return rhs_impl<dispersion::simple<T>> (argc, argv);
     } else if (mode == "korc" && argc == 7) {
         return korc(argc, argv);
+#ifndef GFB_REF_DRIVER_REAL_ONLY
     } else if (mode == "absorb" && argc == 7) {
         return absorb(argc, argv);
+#endif
     } else if (mode == "erfi" && argc == 5) {
         return erfi_values(argc, argv);
     }
