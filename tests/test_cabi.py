@@ -51,3 +51,11 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h", ".inc")):
                 text = open(os.path.join(base, f), errors="replace").read()
                 assert not pattern.search(text), os.path.join(base, f)
+
+
+def test_build_entry_nvrtc_smoke(lib):
+    """The hand-written traits struct that __graft_entry__.build() compiles must follow the skeleton."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+    __graft_entry__.nvrtc_smoke()
