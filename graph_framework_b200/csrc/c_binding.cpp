@@ -505,18 +505,21 @@ int gfb_rays_set_binning(gfb_rays *r, int which_state, double lo, double hi, uns
     return 0;
 }
 int gfb_rays_get_state(gfb_rays *r, double *const state[GFB_NUM_STATE], double *residual) {
-    if (r->unbin()) return 1;
+//  Straight from the device into the caller's (ideally pinned) memory, in the caller's ray order; rays
+//  that are binned at the moment stay binned on the device.
+    gfb_ctx *ctx = r->compiled ? r->impl->context().device() : nullptr;
     if (state) {
         for (int i = 0; i < GFB_NUM_STATE; i++) {
             if (!state[i]) continue;
-//  Straight from the device into the caller's (ideally pinned) memory.
-            if (r->compiled) r->impl->context().copy_to_host(r->vars[i], state[i]);
-            else std::memcpy(state[i], r->vars[i]->data(), sizeof(double)*r->n);
+            if (r->compiled) {
+                if (gfb_copy_rays_d2h(ctx, reinterpret_cast<uint64_t> (r->vars[i].get()), state[i], r->n)) return 1;
+            } else {
+                std::memcpy(state[i], r->vars[i]->data(), sizeof(double)*r->n);
+            }
         }
     }
     if (residual && r->compiled) {
-        auto res = r->impl->residual();
-        r->impl->context().copy_to_host(res, residual);
+        if (gfb_copy_rays_d2h(ctx, reinterpret_cast<uint64_t> (r->impl->residual().get()), residual, r->n)) return 1;
     }
     return 0;
 }
@@ -552,7 +555,8 @@ int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out
     gfb_ctx *ctx = r->impl->context().device();
     for (size_t b = 0; b < num_blocks; b++) {
         if (r->step_binned(sub_steps)) return 1;
-        if (r->unbin()) return 1;           // records are in the caller's ray order
+//  Records are in the caller's ray order: while the rays are binned the snapshot un-permutes them
+//  on its way to the staging buffer (state and residual are both in the order of the last launch).
         if (gfb_snapshot_async(ctx, keys.data(), static_cast<int> (keys.size()), sizeof(double)*r->n,
                                out + b*keys.size()*r->n)) return 1;
     }

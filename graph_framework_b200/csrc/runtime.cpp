@@ -242,7 +242,7 @@ struct gfb_ctx {
     unsigned *bin_step = nullptr;       // the permutation of one re-sort, before it is composed into bin_perm
     unsigned *bin_work = nullptr;
     double *bin_scratch = nullptr;
-    size_t bin_capacity = 0, bin_cells = 0;
+    size_t bin_capacity = 0, bin_cells = 0, bin_n = 0;
     bool binned = false;
 };
 
@@ -720,8 +720,16 @@ int gfb_snapshot_async(gfb_ctx *c, const uint64_t *keys, int num_keys, size_t by
         auto it = c->buffers.find(keys[i]);
         if (it == c->buffers.end()) return fail("gfb_snapshot_async: unknown key");
         if (it->second.bytes < bytes_each) return fail("gfb_snapshot_async: buffer smaller than bytes_each");
-        if (check(cudaMemcpyAsync(static_cast<char *> (c->stage[slot]) + bytes_each*i, it->second.dev, bytes_each,
-                                  cudaMemcpyDeviceToDevice, c->stream), "snapshot d2d")) return 1;
+        char *staged = static_cast<char *> (c->stage[slot]) + bytes_each*i;
+        if (c->binned) {
+//  Rays are sorted by cell: the staging copy puts them back in the caller's order on the way out.
+            if (bytes_each != c->bin_n*sizeof(double)) return fail("gfb_snapshot_async: binned rays need whole ray arrays");
+            if (gfb_k_permute(reinterpret_cast<double *> (staged), static_cast<const double *> (it->second.dev), c->bin_perm,
+                              static_cast<unsigned> (c->bin_n), 1, c->sms, c->stream)) return fail("snapshot scatter failed");
+            c->launches++;
+        } else if (check(cudaMemcpyAsync(staged, it->second.dev, bytes_each, cudaMemcpyDeviceToDevice, c->stream), "snapshot d2d")) {
+            return 1;
+        }
     }
     if (check(cudaEventRecord(c->staged[slot], c->stream), "record staged")) return 1;
     if (check(cudaStreamWaitEvent(c->copy_stream, c->staged[slot], 0), "wait staged")) return 1;
@@ -847,6 +855,7 @@ int bin_rays(gfb_ctx *c, const uint64_t *sort_keys, int num_sort_keys, const dou
         c->launches++;
     }
     c->binned = true;
+    c->bin_n = n;
     return 0;
 }
 }
@@ -863,6 +872,19 @@ int gfb_bin_rays_rz(gfb_ctx *c, const uint64_t *xyz_keys, const double *lo, cons
     return bin_rays(c, xyz_keys, 3, lo, hi, cells, keys, num_keys, n);
 }
 int gfb_is_binned(gfb_ctx *c) { return c->binned ? 1 : 0; }
+int gfb_copy_rays_d2h(gfb_ctx *c, uint64_t key, void *destination, size_t n) {
+    if (!c->binned) return gfb_copy_d2h(c, key, destination, n*sizeof(double));
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    auto it = c->buffers.find(key);
+    if (it == c->buffers.end()) return fail("gfb_copy_rays_d2h: unknown key");
+    if (n != c->bin_n || it->second.bytes < n*sizeof(double)) return fail("gfb_copy_rays_d2h: not a whole per-ray array");
+    if (gfb_k_permute(c->bin_scratch, static_cast<const double *> (it->second.dev), c->bin_perm, static_cast<unsigned> (n), 1,
+                      c->sms, c->stream)) return fail("gfb_copy_rays_d2h: scatter failed");
+    c->launches++;
+    if (check(cudaMemcpyAsync(destination, c->bin_scratch, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream), "d2h")) return 1;
+    return check(cudaStreamSynchronize(c->stream), "d2h sync");
+}
 int gfb_unbin_rays(gfb_ctx *c, const uint64_t *keys, int num_keys, size_t n) {
     if (!c->binned) return 0;
     if (flush(c)) return 1;

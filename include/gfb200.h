@@ -121,7 +121,8 @@ int gfb_check_value(gfb_ctx *ctx, uint64_t key, size_t index, double *value);
  * every buffer device->device into one of two staging slots on the compute stream, then moves
  * the slot to `host_destination` (num_keys consecutive blocks of `bytes_each`; pinned memory
  * recommended) on a second stream, so the next block of steps overlaps the transfer.
- * gfb_wait() completes all outstanding snapshots. */
+ * gfb_wait() completes all outstanding snapshots.  While rays are binned (gfb_bin_rays) the keys must be
+ * whole per-ray arrays; the snapshot delivers them in the caller's order. */
 int gfb_snapshot_async(gfb_ctx *ctx, const uint64_t *keys, int num_keys, size_t bytes_each, void *host_destination);
 
 /* Ray binning.  Rays are independent, so their order in the SoA arrays is free: gfb_bin_rays sorts the
@@ -137,6 +138,9 @@ int gfb_bin_rays_rz(gfb_ctx *ctx, const uint64_t *xyz_keys, const double *lo, co
                     const uint64_t *keys, int num_keys, size_t n);
 int gfb_unbin_rays(gfb_ctx *ctx, const uint64_t *keys, int num_keys, size_t n);
 int gfb_is_binned(gfb_ctx *ctx);
+/* Device -> host copy of one per-ray array of n doubles in the CALLER's order, whether or not the rays
+ * are binned at the moment (binned: un-permuted through a scratch buffer; the device order is kept). */
+int gfb_copy_rays_d2h(gfb_ctx *ctx, uint64_t key, void *destination, size_t n);
 
 /* Page-locked host memory for snapshot / step-from-host buffers (any thread, any context). */
 int gfb_host_alloc(size_t bytes, void **host_ptr);
