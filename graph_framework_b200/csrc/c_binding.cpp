@@ -351,6 +351,12 @@ struct gfb_rays {
     std::vector<uint64_t> ray_keys(const bool with_residual) const {
         std::vector<uint64_t> keys;
         for (auto &v : vars) keys.push_back(reinterpret_cast<uint64_t> (v.get()));
+//  The running absorption state travels with its ray.
+        if (impl->damping) {
+            for (auto v : {impl->kamp_re, impl->kamp_im, impl->x_last, impl->y_last, impl->z_last, impl->power, impl->k_sum}) {
+                keys.push_back(reinterpret_cast<uint64_t> (v.get()));
+            }
+        }
         if (with_residual) keys.push_back(reinterpret_cast<uint64_t> (impl->residual().get()));
         return keys;
     }
@@ -440,9 +446,9 @@ gfb_rays *gfb_rays_create(const char *dispersion_name, const char *equilibrium_n
     r->impl.reset(t);
     if (o.absorption) t->attach_absorption(eq, num_rays);
 //  Tabulated equilibria: keep rays sorted by table cell while stepping (options: bin_rays=0 off,
-//  bin_rays=<steps> re-sort period).  Not combined with absorption, whose arrays are not moved.
+//  bin_rays=<steps> re-sort period).
     const equilibrium::cell_grid grid = eq->get_cell_grid();
-    if (grid.dims && o.bin_rays != 0 && !o.absorption) {
+    if (grid.dims && o.bin_rays != 0) {
         r->bin_dims = grid.dims;
         r->bin_state = GFB_X;
         for (int i = 0; i < 2; i++) {
@@ -492,7 +498,6 @@ int gfb_rays_wait(gfb_rays *r) {
 }
 int gfb_rays_set_binning(gfb_rays *r, int which_state, double lo, double hi, unsigned cells, size_t rebin_every) {
     if (which_state >= GFB_NUM_STATE) return rays_fail("bad state index");
-    if (which_state >= 0 && r->impl->damping) return rays_fail("binning and absorption=1 cannot be combined");
     if (r->unbin()) return 1;
     if (which_state >= 0 && (cells == 0 || !(hi > lo))) return rays_fail("bad binning grid");
     r->bin_dims = which_state >= 0 ? 1 : 0;
@@ -598,7 +603,7 @@ int gfb_rays_trace_absorb(gfb_rays *r, size_t num_blocks, size_t sub_steps, doub
     const double *zd = static_cast<const double *> (t.context().device_pointer(r->vars[GFB_Z]));
     const double *wd = static_cast<const double *> (t.context().device_pointer(d_power));
     for (size_t b = 0; b < num_blocks; b++) {
-        t.step(sub_steps);
+        if (r->step_binned(sub_steps)) return 1;
         t.damping->run();
         t.deposition->run();
         if (profile && gfb_deposit(ctx, xd, yd, zd, wd, r->n, profile_device, lo, hi, bins)) return 1;
