@@ -261,7 +261,7 @@ def main():
     t_compile = time.perf_counter()
     tracer.compile()
     # (tabulated equilibria: the tracer keeps rays sorted by table cell while stepping -- EFIT (R, Z) cells,
-    #  re-sorted every 1000 steps; VMEC radial cells, every 50 steps -- inside the timed region when due;
+    #  VMEC radial cells; re-sorted after about half a cell of travel, inside the timed region when due;
     #  --options bin_rays=0 switches it off)
     t_ready = time.perf_counter()
     stats = tracer.kernel_stats()

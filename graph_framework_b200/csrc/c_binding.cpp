@@ -456,7 +456,7 @@ gfb_rays *gfb_rays_create(const char *dispersion_name, const char *equilibrium_n
             r->bin_hi[i] = grid.hi[i];
             r->bin_cells[i] = grid.cells[i];
         }
-        r->rebin_every = o.bin_rays > 0 ? static_cast<size_t> (o.bin_rays) : grid.drift_steps;
+        r->rebin_every = o.bin_rays > 0 ? static_cast<size_t> (o.bin_rays) : grid.drift_steps(std::abs(dt));
     }
     return r.release();
 }

@@ -90,7 +90,12 @@ namespace equilibrium {
         int dims = 0;                   ///< 1: uniform in the first coordinate; 2: (R, Z) with R = sqrt(x^2 + y^2)
         double lo[2] = {0.0, 0.0}, hi[2] = {1.0, 1.0};
         unsigned cells[2] = {0, 0};
-        size_t drift_steps = 1000;      ///< hint: steps after which a re-sort pays
+        double cell_length = 0.0;       ///< length a ray travels across one cell (a ray moves at most dt per step, c = 1)
+///  Steps after which a re-sort pays: about half a cell of travel, within [20, 5000].
+        size_t drift_steps(const double dt) const {
+            if (!(cell_length > 0.0) || !(dt > 0.0)) return 1000;
+            return static_cast<size_t> (std::min(5000.0, std::max(20.0, 0.5*cell_length/dt)));
+        }
     };
 
     template<typename T=double, bool SAFE_MATH=false>
@@ -305,7 +310,7 @@ namespace equilibrium {
             g.dims = 2;
             g.lo[0] = tab.rmin; g.hi[0] = tab.rmin + tab.dr*static_cast<double> (num_rows); g.cells[0] = static_cast<unsigned> (num_rows);
             g.lo[1] = tab.zmin; g.hi[1] = tab.zmin + tab.dz*static_cast<double> (tab.num_cols); g.cells[1] = static_cast<unsigned> (tab.num_cols);
-            g.drift_steps = 1000;
+            g.cell_length = std::min(tab.dr, tab.dz);
             return g;
         }
 
@@ -487,7 +492,7 @@ namespace equilibrium {
             const size_t cells = tab.rmnc[0].empty() ? 0 : tab.rmnc[0][0].size();
             g.dims = cells ? 1 : 0;
             g.lo[0] = tab.sminf; g.hi[0] = tab.sminf + tab.ds*static_cast<double> (cells); g.cells[0] = static_cast<unsigned> (cells);
-            g.drift_steps = 50;
+            g.cell_length = 2.0*tab.ds;         // s is normalised flux: a cell is about 2 ds of the minor radius
             return g;
         }
         virtual leaf_ptr get_x(leaf_ptr s, leaf_ptr u, leaf_ptr v) { set_cache(s, u, v); return x_cache; }
