@@ -85,6 +85,7 @@ def _load():
                                 ctypes.POINTER(ctypes.c_uint64), I, SZ]),
         "gfb_unbin_rays": (I, [P, ctypes.POINTER(ctypes.c_uint64), I, SZ]),
         "gfb_is_binned": (I, [P]),
+        "gfb_bin_disorder": (I, [P, ctypes.POINTER(ctypes.c_uint64), I, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_uint), SZ, c_double_p]),
         "gfb_copy_rays_d2h": (I, [P, ctypes.c_uint64, P, SZ]),
         "gfb_rays_device_ptr": (I, [P, I, c_void_pp]),
         "gfb_rays_ctx": (P, [P]),

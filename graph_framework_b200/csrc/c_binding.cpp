@@ -348,6 +348,7 @@ struct gfb_rays {
     double bin_lo[2] = {0.0, 0.0}, bin_hi[2] = {1.0, 1.0};
     unsigned bin_cells[2] = {0, 0};
     size_t rebin_every = 0, steps_since_bin = 0;
+    double resort_threshold = 1.0/32.0;
     std::vector<uint64_t> ray_keys(const bool with_residual) const {
         std::vector<uint64_t> keys;
         for (auto &v : vars) keys.push_back(reinterpret_cast<uint64_t> (v.get()));
@@ -372,13 +373,25 @@ struct gfb_rays {
     int bin() {
         if (!bin_dims || !compiled) return 0;
         gfb_ctx *ctx = impl->context().device();
-        if (gfb_is_binned(ctx) && !(rebin_every && steps_since_bin >= rebin_every)) return 0;
         auto keys = ray_keys(false);
+        const uint64_t xyz[3] = {keys[GFB_X], keys[GFB_Y], keys[GFB_Z]};
+        if (gfb_is_binned(ctx)) {
+            if (!(rebin_every && steps_since_bin >= rebin_every)) return 0;
+//  Due for a check: re-sort only when the order has decayed (a coherent beam keeps its order for
+//  thousands of steps, rays with random directions lose it within tens).  More than one cell
+//  boundary per warp on average counts as decayed.
+            double disorder = 1.0;
+            if (gfb_bin_disorder(ctx, bin_dims == 1 ? &keys[bin_state] : xyz, bin_dims == 1 ? 1 : 3, bin_lo, bin_hi, bin_cells,
+                                 n, &disorder)) return 1;
+            if (disorder < resort_threshold) {
+                steps_since_bin = 0;
+                return 0;
+            }
+        }
         if (bin_dims == 1) {
             if (gfb_bin_rays(ctx, keys[bin_state], bin_lo[0], bin_hi[0], bin_cells[0], keys.data(),
                              static_cast<int> (keys.size()), n)) return 1;
         } else {
-            const uint64_t xyz[3] = {keys[GFB_X], keys[GFB_Y], keys[GFB_Z]};
             if (gfb_bin_rays_rz(ctx, xyz, bin_lo, bin_hi, bin_cells, keys.data(), static_cast<int> (keys.size()), n)) return 1;
         }
         steps_since_bin = 0;

@@ -136,6 +136,17 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const cell_grid grid, co
         }
     }
 }
+//  How far the order has decayed: the number of neighbouring slots whose rays sit in different cells
+//  (occupied cells - 1 right after a sort, ~n for a random order).
+__global__ void __launch_bounds__(256) bin_breaks_kernel(const cell_grid grid, const unsigned n, unsigned *__restrict__ breaks) {
+    unsigned mine = 0;
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x + 1u; i < n; i += gridDim.x*blockDim.x) {
+        mine += grid(i) != grid(i - 1u) ? 1u : 0u;
+    }
+    for (int offset = 16; offset > 0; offset >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, offset);
+    if ((threadIdx.x & 31u) == 0u && mine) atomicAdd(breaks, mine);
+}
+
 //  Exclusive scan of the cell counts by one block (cells <= 2^24); also primes the placement cursors.
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ cursor,
                                                         const unsigned cells) {
@@ -263,6 +274,17 @@ int gfb_k_bin_permutation(const double *const values[3], unsigned n, const doubl
     bin_count_kernel<<<grid ? grid : 1, 256, 0, s>>> (g, n, cell_of, count);
     bin_scan_kernel<<<1, 1024, 0, s>>> (count, cursor, cells);
     bin_place_kernel<<<grid ? grid : 1, 256, 0, s>>> (cell_of, n, cursor, perm);
+    return static_cast<int> (cudaGetLastError());
+}
+int gfb_k_bin_breaks(const double *const values[3], unsigned n, const double lo[2], const double hi[2],
+                     const unsigned cells01[2], unsigned *breaks, int sms, cudaStream_t s) {
+    const unsigned grid = static_cast<unsigned> ((n + 255u)/256u < static_cast<unsigned> (sms)*8u ? (n + 255u)/256u : sms*8);
+    cell_grid g;
+    g.a = values[0]; g.b = values[1]; g.c = values[2];
+    g.lo0 = lo[0]; g.inv0 = cells01[0]/(hi[0] - lo[0]); g.n0 = cells01[0];
+    g.lo1 = lo[1]; g.inv1 = cells01[1] ? cells01[1]/(hi[1] - lo[1]) : 0.0; g.n1 = cells01[1];
+    cudaMemsetAsync(breaks, 0, sizeof(unsigned), s);
+    bin_breaks_kernel<<<grid ? grid : 1, 256, 0, s>>> (g, n, breaks);
     return static_cast<int> (cudaGetLastError());
 }
 int gfb_k_permute(double *dst, const double *src, const unsigned *perm, unsigned n, int scatter, int sms, cudaStream_t s) {

@@ -41,6 +41,8 @@ int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s);
 int gfb_k_bin_permutation(const double *const values[3], unsigned n, const double lo[2], const double hi[2],
                           const unsigned cells01[2], unsigned *work, unsigned *perm, int sms, cudaStream_t s);
 int gfb_k_permute(double *dst, const double *src, const unsigned *perm, unsigned n, int scatter, int sms, cudaStream_t s);
+int gfb_k_bin_breaks(const double *const values[3], unsigned n, const double lo[2], const double hi[2],
+                     const unsigned cells01[2], unsigned *breaks, int sms, cudaStream_t s);
 int gfb_k_compose(unsigned *total, const unsigned *first, const unsigned *second, unsigned n, int sms, cudaStream_t s);
 int gfb_k_fill(double *p, size_t n, double v, int sms, cudaStream_t s);
 }
@@ -870,6 +872,28 @@ int gfb_bin_rays_rz(gfb_ctx *c, const uint64_t *xyz_keys, const double *lo, cons
                     const uint64_t *keys, int num_keys, size_t n) {
     if (!cells[1]) return fail("gfb_bin_rays_rz: needs cells in both directions");
     return bin_rays(c, xyz_keys, 3, lo, hi, cells, keys, num_keys, n);
+}
+int gfb_bin_disorder(gfb_ctx *c, const uint64_t *sort_keys, int num_sort_keys, const double *lo, const double *hi,
+                     const unsigned *cells, size_t n, double *fraction) {
+    if (flush(c)) return 1;
+    if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+    if (num_sort_keys != 1 && num_sort_keys != 3) return fail("gfb_bin_disorder: 1 or 3 sort arrays");
+    const double *values[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < num_sort_keys; i++) {
+        auto it = c->buffers.find(sort_keys[i]);
+        if (it == c->buffers.end() || it->second.bytes < n*sizeof(double)) return fail("gfb_bin_disorder: bad sort key");
+        values[i] = static_cast<const double *> (it->second.dev);
+    }
+    const double lo2[2] = {lo[0], num_sort_keys == 3 ? lo[1] : 0.0}, hi2[2] = {hi[0], num_sort_keys == 3 ? hi[1] : 1.0};
+    const unsigned cells2[2] = {cells[0], num_sort_keys == 3 ? cells[1] : 0u};
+    unsigned *counter = reinterpret_cast<unsigned *> (c->scratch);
+    if (gfb_k_bin_breaks(values, static_cast<unsigned> (n), lo2, hi2, cells2, counter, c->sms, c->stream)) return fail("gfb_bin_disorder: launch failed");
+    c->launches++;
+    unsigned *host = reinterpret_cast<unsigned *> (c->scratch_host);
+    if (check(cudaMemcpyAsync(host, counter, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream), "disorder d2h")) return 1;
+    if (check(cudaStreamSynchronize(c->stream), "disorder sync")) return 1;
+    *fraction = n > 1 ? static_cast<double> (*host)/static_cast<double> (n - 1) : 0.0;
+    return 0;
 }
 int gfb_is_binned(gfb_ctx *c) { return c->binned ? 1 : 0; }
 int gfb_copy_rays_d2h(gfb_ctx *c, uint64_t key, void *destination, size_t n) {

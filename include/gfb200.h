@@ -138,6 +138,11 @@ int gfb_bin_rays_rz(gfb_ctx *ctx, const uint64_t *xyz_keys, const double *lo, co
                     const uint64_t *keys, int num_keys, size_t n);
 int gfb_unbin_rays(gfb_ctx *ctx, const uint64_t *keys, int num_keys, size_t n);
 int gfb_is_binned(gfb_ctx *ctx);
+/* How far the order has decayed: the fraction of neighbouring slots whose rays sit in different cells
+ * (about occupied_cells/n right after a sort, towards 1 for a random order).  1 sort key: the 1-D grid;
+ * 3 sort keys: the (R, Z) grid of gfb_bin_rays_rz.  Synchronises the stream. */
+int gfb_bin_disorder(gfb_ctx *ctx, const uint64_t *sort_keys, int num_sort_keys, const double *lo, const double *hi,
+                     const unsigned *cells, size_t n, double *fraction);
 /* Device -> host copy of one per-ray array of n doubles in the CALLER's order, whether or not the rays
  * are binned at the moment (binned: un-permuted through a scratch buffer; the device order is kept). */
 int gfb_copy_rays_d2h(gfb_ctx *ctx, uint64_t key, void *destination, size_t n);
