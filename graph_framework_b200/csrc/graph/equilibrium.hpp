@@ -91,10 +91,13 @@ namespace equilibrium {
         double lo[2] = {0.0, 0.0}, hi[2] = {1.0, 1.0};
         unsigned cells[2] = {0, 0};
         double cell_length = 0.0;       ///< length a ray travels across one cell (a ray moves at most dt per step, c = 1)
-///  Steps after which a re-sort pays: about half a cell of travel, within [20, 5000].
+///  A re-sort costs about as much as `min_steps`/25 steps of the kernels that use these tables, so
+///  checking the order more often than every min_steps steps cannot pay.
+        size_t min_steps = 20;
+///  Steps after which the order is worth checking: about half a cell of travel, within [min_steps, 5000].
         size_t drift_steps(const double dt) const {
             if (!(cell_length > 0.0) || !(dt > 0.0)) return 1000;
-            return static_cast<size_t> (std::min(5000.0, std::max(20.0, 0.5*cell_length/dt)));
+            return static_cast<size_t> (std::min(5000.0, std::max(static_cast<double> (min_steps), 0.5*cell_length/dt)));
         }
     };
 
@@ -311,6 +314,7 @@ namespace equilibrium {
             g.lo[0] = tab.rmin; g.hi[0] = tab.rmin + tab.dr*static_cast<double> (num_rows); g.cells[0] = static_cast<unsigned> (num_rows);
             g.lo[1] = tab.zmin; g.hi[1] = tab.zmin + tab.dz*static_cast<double> (tab.num_cols); g.cells[1] = static_cast<unsigned> (tab.num_cols);
             g.cell_length = std::min(tab.dr, tab.dz);
+            g.min_steps = 200;                  // EFIT ray steps are cheap (~0.08 us per ray): a sort is worth ~4 of them
             return g;
         }
 

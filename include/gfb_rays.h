@@ -37,7 +37,7 @@ enum { GFB_T = 0, GFB_W, GFB_X, GFB_Y, GFB_Z, GFB_KX, GFB_KY, GFB_KZ, GFB_NUM_ST
  *              absorption=<0|1>  also build the weak-damping and power kernels (gfb_rays_trace_absorb)
  *              bin_rays=<0|steps> rays of tabulated equilibria (efit, vmec) are kept sorted by table cell
  *                                 while stepping (default on; the order is checked after about half a cell of
- *                                 travel, 0.5*cell/dt steps within [20, 5000], and the rays are re-sorted when
+ *                                 travel, 0.5*cell/dt steps within [200 (efit) | 20 (vmec), 5000], and the rays are re-sorted when
  *                                 more than 1/32 of neighbouring rays sit in different cells); 0 = off
  * Mirrors the constructor sequence of xrays_bench.cpp:53-85. */
 gfb_rays *gfb_rays_create(const char *dispersion, const char *equilibrium, const char *table_file,
