@@ -233,6 +233,7 @@ run_options parse_options(const char *options) {
         else if (k == "share_rcp") o.emit.share_reciprocals = v != 0;
         else if (k == "fast_div") o.emit.fast_division = v != 0;
         else if (k == "mode_unroll") o.emit.mode_loop_unroll = static_cast<unsigned> (v);
+        else if (k == "mode_recurrence") o.emit.mode_recurrence = v != 0;
         else if (k == "unroll_stages") o.unroll_stages = v != 0 ? 1 : 0;
         else if (k == "fused_steps") o.fused_steps = static_cast<unsigned> (v);
         else if (k == "absorption") o.absorption = v != 0;

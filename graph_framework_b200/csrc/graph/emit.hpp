@@ -47,6 +47,7 @@ namespace jit {
         std::vector<double> packed;     ///< cells*stride doubles, cell major
         bool raw = false;               ///< packed was filled by the emitter (Fourier tables), do not repack
         int alias_input = -1;           ///< >= 0: no table of its own, the pointer of that kernel input (index_1D/2D)
+        bool mode_table = false;        ///< the small [mode][xm, xn, row start, 0] table of a Fourier loop
         size_t bytes() const { return packed.size()*sizeof(double); }
     };
 
@@ -64,7 +65,8 @@ namespace jit {
     struct fourier_loop {
         const graph::leaf_node *u, *v;
         std::vector<double> xm, xn;
-        size_t mode_group;                                  ///< pointer slot of the [mode][2] table
+        size_t mode_group;                                  ///< pointer slot of the [mode][4] table
+        double xn_step = 0.0;                               ///< xn increment inside a row of equal xm (0: no rows)
         std::vector<fourier_set> sets;
         bool emitted = false;
     };
@@ -97,6 +99,9 @@ namespace jit {
 ///  multiplication by 1/scale in table indices (what -ffast-math does to the reference's kernels).
         bool fast_division = true;
         unsigned mode_loop_unroll = 2;          ///< unroll factor of Fourier mode loops (graph::fourier_series)
+///  Fourier loops: inside a row of modes with equal m and equally spaced n, step the angle by one
+///  rotation (4 FMAs) instead of a sincos per mode; each row starts from a fresh sincos.
+        bool mode_recurrence = true;
         size_t unroll_stages_below = 640;       ///< unroll the RK stage loop for bodies up to this many statements
         unsigned block_size = 128;
 ///  Resident blocks per SM promised to ptxas; 0 = let the device layer pick the highest
@@ -169,15 +174,34 @@ namespace jit {
                     loop.v = fv;
                     loop.xm = n->table->xm;
                     loop.xn = n->table->xn;
+//  Rows: runs of equal xm whose xn advance by one common step (VMEC orders its modes that way).
+                    std::vector<bool> row_start(loop.xm.size(), true);
+                    if (opt.mode_recurrence) {
+                        for (size_t m = 1; m < loop.xm.size() && loop.xn_step == 0.0; m++)
+                            if (loop.xm[m] == loop.xm[m - 1] && loop.xn[m] != loop.xn[m - 1]) loop.xn_step = loop.xn[m] - loop.xn[m - 1];
+                        size_t continued = 0;
+                        for (size_t m = 1; m < loop.xm.size(); m++) {
+                            row_start[m] = !(loop.xn_step != 0.0 && loop.xm[m] == loop.xm[m - 1] &&
+                                             loop.xn[m] - loop.xn[m - 1] == loop.xn_step);
+                            continued += row_start[m] ? 0 : 1;
+                        }
+                        if (3*continued < 2*loop.xm.size()) {       // too few modes would profit
+                            loop.xn_step = 0.0;
+                            row_start.assign(loop.xm.size(), true);
+                        }
+                    }
                     table_group g;
                     g.op = graph::op_t::fourier;
                     g.num_cols = 0;
                     g.cells = loop.xm.size();
-                    g.stride = 2;
+                    g.stride = 4;
                     g.raw = true;
+                    g.mode_table = true;
                     for (size_t m = 0; m < loop.xm.size(); m++) {
                         g.packed.push_back(loop.xm[m]);
                         g.packed.push_back(loop.xn[m]);
+                        g.packed.push_back(row_start[m] ? 1.0 : 0.0);
+                        g.packed.push_back(0.0);
                     }
                     loop.mode_group = info.groups.size();
                     info.groups.push_back(g);
@@ -274,9 +298,9 @@ namespace jit {
             for (auto &g : info.groups) {
                 if (g.alias_input >= 0) continue;
                 if (g.raw) {
-//  Fourier tables keep their layout; the small [mode][2] mode-number table is staged.
+//  Fourier tables keep their layout; the small [mode][4] mode-number table is staged.
                     if (g.packed.size() & 1) g.packed.push_back(0.0);
-                    g.staged = opt.stage_tables && g.stride == 2 && g.bytes() <= opt.stage_limit_bytes &&
+                    g.staged = opt.stage_tables && g.mode_table && g.bytes() <= opt.stage_limit_bytes &&
                                staged_total + g.bytes() <= opt.stage_total_bytes;
                     if (g.staged) {
                         g.smem_offset = offset;
@@ -358,11 +382,28 @@ namespace jit {
                     weights.insert({o.b, o.c, (o.b + o.c + (o.base ? 3u : 0u)) & 3u});
                 }
             }
+            const bool rows = loop.xn_step != 0.0;
+            if (rows) {
+//  Inside a row the angle m u - n v drops by xn_step*v per mode: one rotation instead of a sincos.
+//  The row-start test is uniform across the warp (every lane is at the same mode).
+                out << "            double rs" << id << ", rc" << id << ", sn = 0.0, cs = 1.0;" << std::endl
+                    << "            sincos(" << literal(loop.xn_step) << "*" << vreg << ", &rs" << id << ", &rc" << id << ");" << std::endl;
+            }
             out << "#pragma unroll " << opt.mode_loop_unroll << std::endl
                 << "            for (int m = 0; m < " << loop.xm.size() << "; m++) {" << std::endl
-                << "                const double xm = mn" << id << "[2*m], xn = mn" << id << "[2*m + 1];" << std::endl
-                << "                double sn, cs;" << std::endl
-                << "                sincos(xm*" << ureg << " - xn*" << vreg << ", &sn, &cs);" << std::endl;
+                << "                const double xm = mn" << id << "[4*m], xn = mn" << id << "[4*m + 1];" << std::endl;
+            if (rows) {
+                out << "                if (mn" << id << "[4*m + 2] != 0.0) {" << std::endl
+                    << "                    sincos(xm*" << ureg << " - xn*" << vreg << ", &sn, &cs);" << std::endl
+                    << "                } else {" << std::endl
+                    << "                    const double turned = fma(cs, rc" << id << ", sn*rs" << id << ");" << std::endl
+                    << "                    sn = fma(sn, rc" << id << ", -(cs*rs" << id << "));" << std::endl
+                    << "                    cs = turned;" << std::endl
+                    << "                }" << std::endl;
+            } else {
+                out << "                double sn, cs;" << std::endl
+                    << "                sincos(xm*" << ureg << " - xn*" << vreg << ", &sn, &cs);" << std::endl;
+            }
             for (size_t j = 0; j < loop.sets.size(); j++) {
                 const std::string c = "c" + std::to_string(j);
                 const std::string &x = sreg[j];

@@ -33,7 +33,7 @@ enum { GFB_T = 0, GFB_W, GFB_X, GFB_Y, GFB_Z, GFB_KX, GFB_KY, GFB_KZ, GFB_NUM_ST
  *              graph, the reference's construction) | "split_simplextic" (separable dispersions only)
  * options    : NULL or space separated key=value list:
  *              block=<threads> minblocks=<n> stage_tables=<0|1> share_rcp=<0|1> fast_div=<0|1> unroll_stages=<0|1>
- *              fused_steps=<max steps per launch>
+ *              fused_steps=<max steps per launch> mode_unroll=<n> mode_recurrence=<0|1> (Fourier mode loops)
  *              absorption=<0|1>  also build the weak-damping and power kernels (gfb_rays_trace_absorb)
  *              bin_rays=<0|steps> rays of tabulated equilibria (efit, vmec) are kept sorted by table cell
  *                                 while stepping (default on; the order is checked after about half a cell of
