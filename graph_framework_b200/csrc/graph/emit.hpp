@@ -67,6 +67,9 @@ namespace jit {
         std::vector<double> xm, xn;
         size_t mode_group;                                  ///< pointer slot of the [mode][4] table
         double xn_step = 0.0;                               ///< xn increment inside a row of equal xm (0: no rows)
+        std::vector<bool> row_start;
+        std::vector<std::pair<unsigned, unsigned>> factors; ///< (b, c) with b + c >= 2: xm^b (-xn)^c tabulated per mode
+        size_t stride = 4;                                  ///< doubles per mode: xm, -xn, row start, factors...
         std::vector<fourier_set> sets;
         bool emitted = false;
     };
@@ -190,19 +193,14 @@ namespace jit {
                             row_start.assign(loop.xm.size(), true);
                         }
                     }
-                    table_group g;
+                    loop.row_start = row_start;
+                    table_group g;                  // filled by finish_mode_tables() once every member is known
                     g.op = graph::op_t::fourier;
                     g.num_cols = 0;
                     g.cells = loop.xm.size();
                     g.stride = 4;
                     g.raw = true;
                     g.mode_table = true;
-                    for (size_t m = 0; m < loop.xm.size(); m++) {
-                        g.packed.push_back(loop.xm[m]);
-                        g.packed.push_back(loop.xn[m]);
-                        g.packed.push_back(row_start[m] ? 1.0 : 0.0);
-                        g.packed.push_back(0.0);
-                    }
                     loop.mode_group = info.groups.size();
                     info.groups.push_back(g);
                     floops.push_back(loop);
@@ -290,6 +288,37 @@ namespace jit {
                 slot[n] = {g, m};
             }
             for (size_t i = 0, ie = n->num_args(); i < ie; i++) scan(n->args[i].get());
+        }
+
+//  Per mode: xm, -xn, row-start flag, then xm^b (-xn)^c for every derivative order (b, c) with
+//  b + c >= 2 that a member of the loop needs -- so that a weight is ONE multiply with the trig value.
+        void finish_mode_tables() {
+            for (auto &loop : floops) {
+                std::set<std::pair<unsigned, unsigned>> need;
+                for (auto &set : loop.sets) {
+                    for (auto *m : set.members) {
+                        const graph::fourier_order o = graph::fourier_order::unpack(m->num_cols);
+                        if (o.b + o.c >= 2) need.insert({o.b, o.c});
+                    }
+                }
+                loop.factors.assign(need.begin(), need.end());
+                loop.stride = (3 + loop.factors.size() + 1)/2*2;
+                table_group &g = info.groups[loop.mode_group];
+                g.stride = loop.stride;
+                g.packed.assign(loop.xm.size()*loop.stride, 0.0);
+                for (size_t m = 0; m < loop.xm.size(); m++) {
+                    double *row = &g.packed[m*loop.stride];
+                    row[0] = loop.xm[m];
+                    row[1] = -loop.xn[m];
+                    row[2] = loop.row_start[m] ? 1.0 : 0.0;
+                    for (size_t f = 0; f < loop.factors.size(); f++) {
+                        double v = 1.0;
+                        for (unsigned i = 0; i < loop.factors[f].first; i++) v *= loop.xm[m];
+                        for (unsigned i = 0; i < loop.factors[f].second; i++) v *= -loop.xn[m];
+                        row[3 + f] = v;
+                    }
+                }
+            }
         }
 
         void pack_groups() {
@@ -383,18 +412,30 @@ namespace jit {
                 }
             }
             const bool rows = loop.xn_step != 0.0;
+            const std::string st = std::to_string(loop.stride);
             if (rows) {
 //  Inside a row the angle m u - n v drops by xn_step*v per mode: one rotation instead of a sincos.
 //  The row-start test is uniform across the warp (every lane is at the same mode).
                 out << "            double rs" << id << ", rc" << id << ", sn = 0.0, cs = 1.0;" << std::endl
                     << "            sincos(" << literal(loop.xn_step) << "*" << vreg << ", &rs" << id << ", &rc" << id << ");" << std::endl;
             }
+//  Cubic and its derivatives with the powers of s hoisted out of the mode loop:
+//  P' = c1 + c2 (2 s) + c3 (3 s^2),  P''/2 = c2 + c3 (3 s),  P'''/6 = c3; the factors 2 and 6 are
+//  applied to the accumulated sums after the loop.
+            for (size_t j = 0; j < loop.sets.size(); j++) {
+                bool d1 = false, d2 = false;
+                for (auto &[jj, a] : polys) if (jj == j) { d1 = d1 || a == 1; d2 = d2 || a == 2; }
+                const std::string &x = sreg[j];
+                if (d1) out << "            const double x2_" << id << "_" << j << " = " << x << " + " << x << ", x3q_" << id << "_" << j
+                            << " = 3.0*" << x << "*" << x << ";" << std::endl;
+                if (d2) out << "            const double x3_" << id << "_" << j << " = 3.0*" << x << ";" << std::endl;
+            }
             out << "#pragma unroll " << opt.mode_loop_unroll << std::endl
                 << "            for (int m = 0; m < " << loop.xm.size() << "; m++) {" << std::endl
-                << "                const double xm = mn" << id << "[4*m], xn = mn" << id << "[4*m + 1];" << std::endl;
+                << "                const double xm = mn" << id << "[" << st << "*m], nxn = mn" << id << "[" << st << "*m + 1];" << std::endl;
             if (rows) {
-                out << "                if (mn" << id << "[4*m + 2] != 0.0) {" << std::endl
-                    << "                    sincos(xm*" << ureg << " - xn*" << vreg << ", &sn, &cs);" << std::endl
+                out << "                if (mn" << id << "[" << st << "*m + 2] != 0.0) {" << std::endl
+                    << "                    sincos(fma(nxn, " << vreg << ", xm*" << ureg << "), &sn, &cs);" << std::endl
                     << "                } else {" << std::endl
                     << "                    const double turned = fma(cs, rc" << id << ", sn*rs" << id << ");" << std::endl
                     << "                    sn = fma(sn, rc" << id << ", -(cs*rs" << id << "));" << std::endl
@@ -402,11 +443,12 @@ namespace jit {
                     << "                }" << std::endl;
             } else {
                 out << "                double sn, cs;" << std::endl
-                    << "                sincos(xm*" << ureg << " - xn*" << vreg << ", &sn, &cs);" << std::endl;
+                    << "                sincos(fma(nxn, " << vreg << ", xm*" << ureg << "), &sn, &cs);" << std::endl;
             }
             for (size_t j = 0; j < loop.sets.size(); j++) {
                 const std::string c = "c" + std::to_string(j);
                 const std::string &x = sreg[j];
+                const std::string sj = std::to_string(id) + "_" + std::to_string(j);
                 out << "                const double2 " << c << "lo = __ldg(reinterpret_cast<const double2 *> (fc" << id << "_" << j
                     << " + m*" << loop.sets[j].table->cells*4 << ")), " << c << "hi = __ldg(reinterpret_cast<const double2 *> (fc"
                     << id << "_" << j << " + m*" << loop.sets[j].table->cells*4 << ") + 1);" << std::endl;
@@ -415,20 +457,25 @@ namespace jit {
                     out << "                const double p" << j << "_" << a << " = ";
                     switch (a) {
                         case 0: out << "fma(fma(fma(" << c << "hi.y, " << x << ", " << c << "hi.x), " << x << ", " << c << "lo.y), " << x << ", " << c << "lo.x)"; break;
-                        case 1: out << "fma(fma(3.0*" << c << "hi.y, " << x << ", 2.0*" << c << "hi.x), " << x << ", " << c << "lo.y)"; break;
-                        case 2: out << "fma(6.0*" << c << "hi.y, " << x << ", 2.0*" << c << "hi.x)"; break;
-                        default: out << "6.0*" << c << "hi.y"; break;
+                        case 1: out << "fma(" << c << "hi.y, x3q_" << sj << ", fma(" << c << "hi.x, x2_" << sj << ", " << c << "lo.y))"; break;
+                        case 2: out << "fma(" << c << "hi.y, x3_" << sj << ", " << c << "hi.x)"; break;
+                        default: out << c << "hi.y"; break;
                     }
                     out << ";" << std::endl;
                 }
             }
             for (auto &w : weights) {
                 out << "                const double w" << w[0] << "_" << w[1] << "_" << w[2] << " = ";
-                std::string f;
-                for (unsigned i = 0; i < w[0]; i++) f += "xm*";
-                for (unsigned i = 0; i < w[1]; i++) f += "(-xn)*";
                 static const char *trig[4] = {"cs", "(-sn)", "(-cs)", "sn"};
-                out << f << trig[w[2]] << ";" << std::endl;
+                if (w[0] + w[1] == 0) {
+                    out << trig[w[2]];
+                } else if (w[0] + w[1] == 1) {
+                    out << (w[0] ? "xm*" : "nxn*") << trig[w[2]];
+                } else {
+                    const size_t f = std::find(loop.factors.begin(), loop.factors.end(), std::make_pair(w[0], w[1])) - loop.factors.begin();
+                    out << "mn" << id << "[" << st << "*m + " << 3 + f << "]*" << trig[w[2]];
+                }
+                out << ";" << std::endl;
             }
             for (size_t j = 0; j < loop.sets.size(); j++) {
                 for (auto *m : loop.sets[j].members) {
@@ -439,7 +486,15 @@ namespace jit {
                     info.num_statements++;
                 }
             }
-            out << "            }" << std::endl << "        }" << std::endl;
+            out << "            }" << std::endl;
+            for (auto &set : loop.sets) {
+                for (auto *m : set.members) {
+                    const unsigned a = fourier_order::unpack(m->num_cols).a;
+                    if (a == 2) out << "            " << reg.at(m) << " *= 2.0;" << std::endl;
+                    if (a >= 3) out << "            " << reg.at(m) << " *= 6.0;" << std::endl;
+                }
+            }
+            out << "        }" << std::endl;
         }
 
         const std::string &emit(const graph::leaf_node *n) {
@@ -615,6 +670,7 @@ namespace jit {
                  const std::vector<size_t> &evolved,
                  const int time_idx) {
             for (auto &r : results) scan(r.get());
+            finish_mode_tables();
             pack_groups();
             index_reg.assign(info.groups.size(), "");
             pair_loaded.clear();
