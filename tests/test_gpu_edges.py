@@ -232,3 +232,38 @@ def test_boris_binning_is_invisible_and_exact(lib):
     for a, c in zip(out[0], out[1]):
         for k in a:
             assert np.array_equal(a[k], c[k]), k
+
+
+def test_two_tracers_in_two_host_threads(lib):
+    """The reference's model is one device context per host thread (xrays.cpp:419-527); the xrays
+    driver here uses the same.  Two tracers built, compiled and stepped concurrently from two
+    threads (same device) must give exactly what they give one after the other."""
+    import threading
+    from graph_framework_b200.rays import RayTracer
+    from graph_framework_b200 import workloads
+
+    def run(disp, seed, out, key):
+        n = 30000
+        tr = RayTracer(disp, "efit", n, 2.0e-5)
+        tr.set_state(workloads.efit_ensemble(n, seed=seed))
+        tr.init("kx")
+        tr.compile()
+        tr.step(150)
+        rec = tr.trace(2, 50)
+        out[key] = (tr.get_state(), rec.copy())
+        tr.close()
+
+    serial, threaded = {}, {}
+    run("extra_ordinary_wave", 1, serial, "a")
+    run("ordinary_wave", 2, serial, "b")
+    threads = [threading.Thread(target=run, args=("extra_ordinary_wave", 1, threaded, "a")),
+               threading.Thread(target=run, args=("ordinary_wave", 2, threaded, "b"))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for key in ("a", "b"):
+        assert key in threaded
+        for k in serial[key][0]:
+            assert np.array_equal(serial[key][0][k], threaded[key][0][k]), (key, k)
+        assert np.array_equal(serial[key][1], threaded[key][1]), key
