@@ -255,6 +255,8 @@ struct tracer_base {
     virtual jit::context<> &context() = 0;
     virtual std::vector<leaf_ptr> rhs() = 0;
     virtual workflow::manager<> &work() = 0;
+    virtual workflow::ray_order<> &order() = 0;
+    virtual void set_ray_order(bool on, size_t period) = 0;
 
 //  Absorption attached to the solver's device context (absorption.hpp): state that the
 //  Runge-Kutta kernel leaves in HBM is read in place.
@@ -309,6 +311,8 @@ struct tracer final : public tracer_base {
     leaf_ptr residual() override { return solve.get_residual(); }
     jit::context<> &context() override { return solve.get_work().get_context(); }
     workflow::manager<> &work() override { return solve.get_work(); }
+    workflow::ray_order<> &order() override { return solve.get_order(); }
+    void set_ray_order(bool on, size_t period) override { solve.set_ray_order(on, period); }
     std::vector<leaf_ptr> rhs() override {
         auto &D = solve.get_dispersion();
         return {D.get_dxdt(), D.get_dydt(), D.get_dzdt(), D.get_dkxdt(), D.get_dkydt(), D.get_dkzdt(), D.get_d()};
@@ -342,76 +346,6 @@ struct gfb_rays {
     bool absorption_started = false;
     char profile_tag = 0;             // its address keys the deposition profile buffer
     std::string source;
-//  Binning by table cell: applied before stepping, undone before anything reads or writes rays by
-//  index.  bin_dims = 1: cells of state[bin_state]; 2: (R, Z) cells of (x, y, z).
-    int bin_dims = 0;
-    int bin_state = -1;
-    double bin_lo[2] = {0.0, 0.0}, bin_hi[2] = {1.0, 1.0};
-    unsigned bin_cells[2] = {0, 0};
-    size_t rebin_every = 0, steps_since_bin = 0;
-    double resort_threshold = 1.0/32.0;
-    std::vector<uint64_t> ray_keys(const bool with_residual) const {
-        std::vector<uint64_t> keys;
-        for (auto &v : vars) keys.push_back(reinterpret_cast<uint64_t> (v.get()));
-//  The running absorption state travels with its ray.
-        if (impl->damping) {
-            for (auto v : {impl->kamp_re, impl->kamp_im, impl->x_last, impl->y_last, impl->z_last, impl->power, impl->k_sum}) {
-                keys.push_back(reinterpret_cast<uint64_t> (v.get()));
-            }
-        }
-        if (with_residual) keys.push_back(reinterpret_cast<uint64_t> (impl->residual().get()));
-        return keys;
-    }
-//  Back to the caller's ray order: the state and the residual of the last launch.
-    int unbin() {
-        if (!bin_dims || !compiled) return 0;
-        auto keys = ray_keys(true);
-        return gfb_unbin_rays(impl->context().device(), keys.data(), static_cast<int> (keys.size()), n);
-    }
-//  Before a block of steps: sort the state by cell if it is in the caller's order or the last sort
-//  is `rebin_every` steps old (re-sorting composes permutations, no round trip through the caller's
-//  order).  The residual is rewritten by the launch, so it is not moved here.
-    int bin() {
-        if (!bin_dims || !compiled) return 0;
-        gfb_ctx *ctx = impl->context().device();
-        auto keys = ray_keys(false);
-        const uint64_t xyz[3] = {keys[GFB_X], keys[GFB_Y], keys[GFB_Z]};
-        if (gfb_is_binned(ctx)) {
-            if (!(rebin_every && steps_since_bin >= rebin_every)) return 0;
-//  Due for a check: re-sort only when the order has decayed (a coherent beam keeps its order for
-//  thousands of steps, rays with random directions lose it within tens).  More than one cell
-//  boundary per warp on average counts as decayed.
-            double disorder = 1.0;
-            if (gfb_bin_disorder(ctx, bin_dims == 1 ? &keys[bin_state] : xyz, bin_dims == 1 ? 1 : 3, bin_lo, bin_hi, bin_cells,
-                                 n, &disorder)) return 1;
-            if (disorder < resort_threshold) {
-                steps_since_bin = 0;
-                return 0;
-            }
-        }
-        if (bin_dims == 1) {
-            if (gfb_bin_rays(ctx, keys[bin_state], bin_lo[0], bin_hi[0], bin_cells[0], keys.data(),
-                             static_cast<int> (keys.size()), n)) return 1;
-        } else {
-            if (gfb_bin_rays_rz(ctx, xyz, bin_lo, bin_hi, bin_cells, keys.data(), static_cast<int> (keys.size()), n)) return 1;
-        }
-        steps_since_bin = 0;
-        return 0;
-    }
-//  num_steps steps in pieces that end where the next re-sort is due.
-    int step_binned(const size_t num_steps) {
-        size_t left = num_steps;
-        while (left) {
-            if (bin()) return 1;
-            size_t piece = left;
-            if (bin_dims && rebin_every) piece = std::min(left, rebin_every - std::min(steps_since_bin, rebin_every - 1));
-            impl->step(piece);
-            if (bin_dims && rebin_every && gfb_flush(impl->context().device())) return 1;
-            steps_since_bin += piece;
-            left -= piece;
-        }
-        return 0;
-    }
 };
 
 namespace {
@@ -459,19 +393,9 @@ gfb_rays *gfb_rays_create(const char *dispersion_name, const char *equilibrium_n
     }
     r->impl.reset(t);
     if (o.absorption) t->attach_absorption(eq, num_rays);
-//  Tabulated equilibria: keep rays sorted by table cell while stepping (options: bin_rays=0 off,
-//  bin_rays=<steps> re-sort period).
-    const equilibrium::cell_grid grid = eq->get_cell_grid();
-    if (grid.dims && o.bin_rays != 0) {
-        r->bin_dims = grid.dims;
-        r->bin_state = GFB_X;
-        for (int i = 0; i < 2; i++) {
-            r->bin_lo[i] = grid.lo[i];
-            r->bin_hi[i] = grid.hi[i];
-            r->bin_cells[i] = grid.cells[i];
-        }
-        r->rebin_every = o.bin_rays > 0 ? static_cast<size_t> (o.bin_rays) : grid.drift_steps(std::abs(dt));
-    }
+//  Tabulated equilibria: the solver keeps rays sorted by table cell while stepping (binning.hpp);
+//  options: bin_rays=0 off, bin_rays=<steps> how often the order is checked.
+    if (o.bin_rays >= 0) t->set_ray_order(o.bin_rays != 0, o.bin_rays > 0 ? static_cast<size_t> (o.bin_rays) : 0);
     return r.release();
 }
 void gfb_rays_destroy(gfb_rays *r) { delete r; }
@@ -480,10 +404,7 @@ int gfb_rays_set_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]) {
     for (int i = 0; i < GFB_NUM_STATE; i++) {
         if (state[i]) r->vars[i]->set(std::vector<double> (state[i], state[i] + r->n));
     }
-    if (r->compiled) {
-        if (r->unbin()) return 1;
-        r->impl->sync_device();
-    }
+    if (r->compiled) r->impl->sync_device();        // restores the caller's ray order first
     return 0;
 }
 int gfb_rays_init(gfb_rays *r, const char *var, double tolerance, size_t max_iterations, int mode) {
@@ -499,11 +420,14 @@ int gfb_rays_init(gfb_rays *r, const char *var, double tolerance, size_t max_ite
 int gfb_rays_compile(gfb_rays *r) {
     r->impl->compile();
     r->compiled = true;
+    tracer_base &t = *r->impl;
+//  The running absorption state travels with its ray when the order changes.
+    if (t.damping) t.order().add_arrays({t.kamp_re, t.kamp_im, t.x_last, t.y_last, t.z_last, t.power, t.k_sum});
     return 0;
 }
 int gfb_rays_step(gfb_rays *r, size_t num_steps) {
     if (!r->compiled) return rays_fail("step before compile");
-    if (r->step_binned(num_steps)) return 1;
+    r->impl->step(num_steps);
     return gfb_flush(r->impl->context().device());
 }
 int gfb_rays_wait(gfb_rays *r) {
@@ -511,16 +435,22 @@ int gfb_rays_wait(gfb_rays *r) {
     return 0;
 }
 int gfb_rays_set_binning(gfb_rays *r, int which_state, double lo, double hi, unsigned cells, size_t rebin_every) {
+    if (!r->compiled) return rays_fail("set_binning before compile");
     if (which_state >= GFB_NUM_STATE) return rays_fail("bad state index");
-    if (r->unbin()) return 1;
-    if (which_state >= 0 && (cells == 0 || !(hi > lo))) return rays_fail("bad binning grid");
-    r->bin_dims = which_state >= 0 ? 1 : 0;
-    r->bin_state = which_state;
-    r->bin_lo[0] = lo;
-    r->bin_hi[0] = hi;
-    r->bin_cells[0] = cells;
-    r->bin_cells[1] = 0;
-    r->rebin_every = rebin_every;
+    tracer_base &t = *r->impl;
+    if (which_state < 0) {
+        t.order().disable();
+        return 0;
+    }
+    if (cells == 0 || !(hi > lo)) return rays_fail("bad binning grid");
+    equilibrium::cell_grid grid;
+    grid.dims = 1;
+    grid.lo[0] = lo;
+    grid.hi[0] = hi;
+    grid.cells[0] = cells;
+    std::vector<leaf_ptr> arrays = r->vars;
+    if (t.damping) for (auto v : {t.kamp_re, t.kamp_im, t.x_last, t.y_last, t.z_last, t.power, t.k_sum}) arrays.push_back(v);
+    t.order().configure(t.work(), grid, {r->vars[which_state]}, arrays, {t.residual()}, r->n, rebin_every);
     return 0;
 }
 int gfb_rays_get_state(gfb_rays *r, double *const state[GFB_NUM_STATE], double *residual) {
@@ -544,7 +474,7 @@ int gfb_rays_get_state(gfb_rays *r, double *const state[GFB_NUM_STATE], double *
 }
 int gfb_rays_put_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]) {
     if (!r->compiled) return gfb_rays_set_state(r, state);
-    if (r->unbin()) return 1;
+    r->impl->order().restore();
     for (int i = 0; i < GFB_NUM_STATE; i++) {
         if (state[i]) r->impl->context().copy_to_device(r->vars[i], const_cast<double *> (state[i]));
     }
@@ -553,7 +483,7 @@ int gfb_rays_put_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]) {
 int gfb_rays_step_host(gfb_rays *r, size_t num_steps, const double *const state_in[GFB_NUM_STATE],
                        double *const state_out[GFB_NUM_STATE], double *residual_out, int chunks) {
     if (!r->compiled) return rays_fail("step_host before compile");
-    if (r->unbin()) return 1;
+    r->impl->order().restore();
 //  Pointer slots of solver_kernel: the 8 inputs in solver order (= GFB_T..GFB_KZ), then the residual.
     const void *src[GFB_NUM_STATE + 1];
     void *dst[GFB_NUM_STATE + 1];
@@ -573,7 +503,7 @@ int gfb_rays_trace(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *out
     keys.push_back(reinterpret_cast<uint64_t> (r->impl->residual().get()));
     gfb_ctx *ctx = r->impl->context().device();
     for (size_t b = 0; b < num_blocks; b++) {
-        if (r->step_binned(sub_steps)) return 1;
+        r->impl->step(sub_steps);
 //  Records are in the caller's ray order: while the rays are binned the snapshot un-permutes them
 //  on its way to the staging buffer (state and residual are both in the order of the last launch).
         if (gfb_snapshot_async(ctx, keys.data(), static_cast<int> (keys.size()), sizeof(double)*r->n,
@@ -617,7 +547,7 @@ int gfb_rays_trace_absorb(gfb_rays *r, size_t num_blocks, size_t sub_steps, doub
     const double *zd = static_cast<const double *> (t.context().device_pointer(r->vars[GFB_Z]));
     const double *wd = static_cast<const double *> (t.context().device_pointer(d_power));
     for (size_t b = 0; b < num_blocks; b++) {
-        if (r->step_binned(sub_steps)) return 1;
+        t.step(sub_steps);
         t.damping->run();
         t.deposition->run();
         if (profile && gfb_deposit(ctx, xd, yd, zd, wd, r->n, profile_device, lo, hi, bins)) return 1;
@@ -632,7 +562,7 @@ int gfb_rays_trace_absorb(gfb_rays *r, size_t num_blocks, size_t sub_steps, doub
 }
 int gfb_rays_device_ptr(gfb_rays *r, int which, void **device_ptr) {
     if (!r->compiled) return rays_fail("device_ptr before compile");
-    if (r->unbin()) return 1;
+    r->impl->order().restore();
     if (which < 0 || which > GFB_NUM_STATE) return rays_fail("bad state index");
     *device_ptr = r->impl->context().device_pointer(which == GFB_NUM_STATE ? r->impl->residual() : r->vars[which]);
     return 0;
@@ -684,29 +614,12 @@ struct gfb_boris {
     std::unique_ptr<workflow::manager<>> work;
     double b0 = 0.0, larmor = 0.0;
     bool compiled = false;
-//  Particles kept sorted by the (R, Z) cell of the field tables (gfb_boris_set_binning).
-    bool binning = false;
-    double bin_lo[2] = {0.0, 0.0}, bin_hi[2] = {1.0, 1.0};
-    unsigned bin_cells[2] = {0, 0};
-    size_t rebin_every = 0, steps_since_bin = 0;
-    std::vector<uint64_t> keys() const {
-        std::vector<uint64_t> k;
-        for (auto &v : vars) k.push_back(reinterpret_cast<uint64_t> (v.get()));
-        return k;
-    }
-    int unbin() {
-        if (!binning || !compiled) return 0;
-        auto k = keys();
-        return gfb_unbin_rays(work->get_context().device(), k.data(), static_cast<int> (k.size()), n);
-    }
-    int bin() {
-        if (!binning || !compiled) return 0;
-        gfb_ctx *ctx = work->get_context().device();
-        if (gfb_is_binned(ctx) && !(rebin_every && steps_since_bin >= rebin_every)) return 0;
-        auto k = keys();
-        if (gfb_bin_rays_rz(ctx, k.data(), bin_lo, bin_hi, bin_cells, k.data(), static_cast<int> (k.size()), n)) return 1;
-        steps_since_bin = 0;
-        return 0;
+//  Particles are kept sorted by the (R, Z) cell of the field tables (binning.hpp).
+    equilibrium::cell_grid grid;
+    size_t order_period = 1000;
+    workflow::ray_order<> order;
+    void setup_order() {
+        if (grid.dims == 2) order.configure(*work, grid, {vars[0], vars[1], vars[2]}, vars, {}, n, order_period);
     }
 };
 
@@ -772,35 +685,29 @@ gfb_boris *gfb_boris_create(const char *equilibrium_name, const char *table_file
         {u_next->get_x(), ux}, {u_next->get_y(), uy}, {u_next->get_z(), uz}, {gamma_next, gamma}
     }, graph::shared_random_state<> (), "step", num_particles);
 //  Particles of one (R, Z) cell share the coefficient rows of the field tables: keep them sorted by
-//  cell while stepping (options: bin_rays=0 off, bin_rays=<steps> re-sort period).
-    const equilibrium::cell_grid grid = eq->get_cell_grid();
-    if (grid.dims == 2 && o.bin_rays != 0) {
-        b->binning = true;
-        for (int i = 0; i < 2; i++) {
-            b->bin_lo[i] = grid.lo[i];
-            b->bin_hi[i] = grid.hi[i];
-            b->bin_cells[i] = grid.cells[i];
-        }
-        b->rebin_every = o.bin_rays > 0 ? static_cast<size_t> (o.bin_rays) : 1000;
-    }
+//  cell while stepping (options: bin_rays=0 off, bin_rays=<steps> how often the order is checked).
+    if (o.bin_rays != 0) b->grid = eq->get_cell_grid();
+    if (o.bin_rays > 0) b->order_period = static_cast<size_t> (o.bin_rays);
     return b.release();
 }
 void gfb_boris_destroy(gfb_boris *b) { delete b; }
 int gfb_boris_set_binning(gfb_boris *b, const double *lo, const double *hi, const unsigned *cells, size_t rebin_every) {
-    if (b->unbin()) return 1;
-    b->binning = cells && cells[0] && cells[1];
-    if (b->binning) {
+    b->order.disable();
+    b->grid = equilibrium::cell_grid();
+    if (cells && cells[0] && cells[1]) {
+        b->grid.dims = 2;
         for (int i = 0; i < 2; i++) {
-            b->bin_lo[i] = lo[i];
-            b->bin_hi[i] = hi[i];
-            b->bin_cells[i] = cells[i];
+            b->grid.lo[i] = lo[i];
+            b->grid.hi[i] = hi[i];
+            b->grid.cells[i] = cells[i];
         }
     }
-    b->rebin_every = rebin_every;
+    b->order_period = rebin_every;
+    if (b->compiled) b->setup_order();
     return 0;
 }
 int gfb_boris_set_state(gfb_boris *b, const double *const state[6]) {
-    if (b->unbin()) return 1;
+    b->order.restore();
     for (int i = 0; i < 6; i++) {
         if (!state[i]) continue;
         b->vars[i]->set(std::vector<double> (state[i], state[i] + b->n));
@@ -813,25 +720,27 @@ int gfb_boris_compile(gfb_boris *b) {
     b->work->compile();
     b->work->pre_run();
     b->compiled = true;
+    b->setup_order();
     return 0;
 }
 int gfb_boris_step(gfb_boris *b, size_t num_steps) {
     if (!b->compiled) return rays_fail("step before compile");
     size_t left = num_steps;
     while (left) {
-        if (b->bin()) return 1;
-        size_t piece = left;
-        if (b->binning && b->rebin_every) piece = std::min(left, b->rebin_every - std::min(b->steps_since_bin, b->rebin_every - 1));
+        const size_t piece = b->order.prepare(left);
         for (size_t i = 0; i < piece; i++) b->work->run();
         if (gfb_flush(b->work->get_context().device())) return 1;
-        b->steps_since_bin += piece;
+        b->order.advanced(piece);
         left -= piece;
     }
     return 0;
 }
 int gfb_boris_get_state(gfb_boris *b, double *const state[7]) {
-    if (b->unbin()) return 1;
-    for (int i = 0; i < 7; i++) if (state[i]) b->work->copy_to_host(b->vars[i], state[i]);
+    for (int i = 0; i < 7; i++) {
+        if (!state[i]) continue;
+        if (b->order.active()) b->order.copy_to_host(b->vars[i], state[i]);     // caller's order, device order kept
+        else b->work->copy_to_host(b->vars[i], state[i]);
+    }
     return 0;
 }
 int gfb_boris_info(gfb_boris *b, double *b0, double *larmor_radius) {

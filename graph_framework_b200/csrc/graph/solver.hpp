@@ -17,9 +17,17 @@
 #define gfb_graph_solver_hpp
 
 #include "dispersion.hpp"
+#include "binning.hpp"
 
 namespace solver {
     using graph::leaf_ptr;
+
+///  Whether solvers keep their rays sorted by table cell while stepping (binning.hpp); per host
+///  thread, on unless the environment says GFB_BIN_RAYS=0.
+    inline bool &bin_rays() {
+        static thread_local bool on = !(std::getenv("GFB_BIN_RAYS") && std::string(std::getenv("GFB_BIN_RAYS")) == "0");
+        return on;
+    }
 
     template<dispersion::function DISPERSION_FUNCTION>
     class solver_interface {
@@ -34,6 +42,20 @@ namespace solver {
         workflow::manager<T, SAFE_MATH> work;
         const size_t index;
         newton_mode init_mode;
+        equilibrium::cell_grid table_grid;
+        workflow::ray_order<T, SAFE_MATH> order;
+        bool order_wanted = bin_rays();
+        size_t order_period = 0;        ///< 0: from the cell size and the step
+
+///  Step size when it is a compile-time constant (how often the ray order is worth checking).
+        virtual double step_size() const { return 0.0; }
+///  After work.compile(): rays of tabulated equilibria are kept sorted by table cell.
+        void setup_order() {
+            if (!table_grid.dims || !order_wanted) return;
+            std::vector<leaf_ptr> sort_by = table_grid.dims == 1 ? std::vector<leaf_ptr> {x} : std::vector<leaf_ptr> {x, y, z};
+            order.configure(work, table_grid, sort_by, inputs(), {residual}, t->size(),
+                            order_period ? order_period : table_grid.drift_steps(step_size()));
+        }
 
         graph::input_nodes<T, SAFE_MATH> inputs() {
 //  Argument order of solver.hpp:304-314.
@@ -49,11 +71,18 @@ namespace solver {
                          equilibrium::shared<T, SAFE_MATH> &eq,
                          const std::string &filename="", const size_t num_rays=0, const size_t index=0) :
         w(w), kx(kx), ky(ky), kz(kz), x(x), y(y), z(z), t(t),
-        D(w, kx, ky, kz, x, y, z, t, eq), work(index), index(index), init_mode(newton_mode::per_ray) {
+        D(w, kx, ky, kz, x, y, z, t, eq), work(index), index(index), init_mode(newton_mode::per_ray),
+        table_grid(eq->get_cell_grid()) {
             (void)filename; (void)num_rays;     // trajectory files are outside this back end
         }
         virtual ~solver_interface() {}
 
+///  Before compile(): keep the rays sorted by table cell while stepping (default: yes for
+///  tabulated equilibria, see solver::bin_rays()); `period` overrides how often the order is checked.
+        void set_ray_order(const bool on, const size_t period=0) {
+            order_wanted = on;
+            order_period = period;
+        }
 ///  Choose between the device-resident per-ray Newton solve (default) and the
 ///  reference's host-driven ensemble-maximum loop.
         void set_newton_mode(const newton_mode m) { init_mode = m; }
@@ -78,18 +107,33 @@ namespace solver {
             work.add_item(inputs(), {residual}, setters, graph::shared_random_state<T, SAFE_MATH> (),
                           "solver_kernel", t->size());
             work.compile();
+            setup_order();
         }
 
         void sync_device() {
+            order.restore();
             for (auto v : inputs()) work.copy_to_device(v, v->data());
         }
         void sync_host() {
-            for (auto v : inputs()) work.copy_to_host(v, v->data());
+            for (auto v : inputs()) {
+                if (order.active()) order.copy_to_host(v, v->data());
+                else work.copy_to_host(v, v->data());
+            }
         }
-        void step() { work.run(); }
-        void step(const size_t n) { for (size_t i = 0; i < n; i++) work.run(); }
-        T check_residual(const size_t i) { return work.check_value(i, residual); }
-        void print(const size_t i) { work.print(i, {t, residual, w, x, y, z, kx, ky, kz}); }
+        void step() { step(1); }
+///  n steps; consecutive launches are fused by the device layer.  With a sorted ray order the
+///  block is cut where the order is due for a check.
+        void step(const size_t n) {
+            size_t left = n;
+            while (left) {
+                const size_t piece = order.prepare(left);
+                for (size_t i = 0; i < piece; i++) work.run();
+                order.advanced(piece);
+                left -= piece;
+            }
+        }
+        T check_residual(const size_t i) { order.restore(); return work.check_value(i, residual); }
+        void print(const size_t i) { order.restore(); work.print(i, {t, residual, w, x, y, z, kx, ky, kz}); }
         void wait() { work.wait(); }
 ///  The reference writes a NetCDF record here (solver.hpp:418-424); this back
 ///  end only provides the synchronisation point.
@@ -97,6 +141,9 @@ namespace solver {
 
         leaf_ptr get_residual() { return residual; }
         workflow::manager<T, SAFE_MATH> &get_work() { return work; }
+///  The ray order policy (binning.hpp).  Code that reads device buffers of the rays by index through
+///  get_work() must call get_order().restore() first.
+        workflow::ray_order<T, SAFE_MATH> &get_order() { return order; }
         dispersion::dispersion_interface<DISPERSION_FUNCTION> &get_dispersion() { return D; }
         std::vector<leaf_ptr> state() { return inputs(); }
     };
@@ -113,6 +160,7 @@ namespace solver {
         typedef typename DISPERSION_FUNCTION::base T;
         static constexpr bool SAFE_MATH = DISPERSION_FUNCTION::safe_math;
         leaf_ptr dt;
+        virtual double step_size() const { return dt->is_constant() ? std::abs(dt->value) : 0.0; }
     public:
         rk2(leaf_ptr w, leaf_ptr kx, leaf_ptr ky, leaf_ptr kz, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr t,
             leaf_ptr dt, equilibrium::shared<T, SAFE_MATH> &eq,
@@ -146,6 +194,7 @@ namespace solver {
                      this->D.get_dxdt(), this->D.get_dydt(), this->D.get_dzdt()},
                     this->t, dt, this->residual, "solver_kernel", this->t->size());
                 this->work.compile();
+                this->setup_order();
             } else {
                 solver_interface<DISPERSION_FUNCTION>::compile();
             }
@@ -161,6 +210,7 @@ namespace solver {
         typedef typename DISPERSION_FUNCTION::base T;
         static constexpr bool SAFE_MATH = DISPERSION_FUNCTION::safe_math;
         leaf_ptr dt;
+        virtual double step_size() const { return dt->is_constant() ? std::abs(dt->value) : 0.0; }
     public:
         rk4(leaf_ptr w, leaf_ptr kx, leaf_ptr ky, leaf_ptr kz, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr t,
             leaf_ptr dt, equilibrium::shared<T, SAFE_MATH> &eq,
@@ -208,6 +258,7 @@ namespace solver {
                      this->D.get_dxdt(), this->D.get_dydt(), this->D.get_dzdt()},
                     this->t, dt, this->residual, "solver_kernel", this->t->size());
                 this->work.compile();
+                this->setup_order();
             } else {
                 solver_interface<DISPERSION_FUNCTION>::compile();
             }
@@ -257,7 +308,7 @@ namespace solver {
             };
             this->work.add_item(inputs, {this->residual}, setters, graph::shared_random_state<T, SAFE_MATH> (),
                                 "solver_kernel", this->t->size());
-            this->work.compile();
+            this->work.compile();               // rays stay in the caller's order: dt and lambda are per-ray state too
         }
         leaf_ptr get_dt() { return dt_var; }
     };
