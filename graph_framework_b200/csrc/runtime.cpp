@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <csignal>
 #include <cstdio>
 #include <cstdlib>
@@ -594,14 +595,33 @@ int gfb_kernel_run_from_host(gfb_kernel *k, unsigned steps, int num_ray_slots,
     }
     const unsigned long long total = k->args.n;
     if (chunks < 1) chunks = 1;
-//  Chunk boundaries on whole waves (blocks/SM x SMs x block) so only the last piece has a tail.
-    unsigned long long per = (total + chunks - 1)/chunks;
+//  Chunk boundaries on whole waves (blocks/SM x SMs x block) so only the last piece has a tail.  The
+//  first upload and the last read-back cannot overlap any kernel, so with three or more chunks the first
+//  piece is a single wave and the last one is the (partial) tail wave; the pieces between share the rest.
     const unsigned long long wave = static_cast<unsigned long long> (k->block)*c->sms*(c->min_blocks > 0 ? c->min_blocks : 1);
-    per = (per + wave - 1)/wave*wave;
+    const unsigned long long waves = (total + wave - 1)/wave;
+    std::vector<std::pair<unsigned long long, unsigned long long>> pieces;       // offset, count
+    if (chunks >= 3 && waves >= 2ull*static_cast<unsigned long long> (chunks)) {
+        const unsigned long long middle_waves = waves - 2;
+        const unsigned long long per_middle = (middle_waves + chunks - 3)/(chunks - 2);
+        unsigned long long off = 0;
+        pieces.push_back({off, wave});
+        off += wave;
+        for (unsigned long long done = 0; done < middle_waves; done += per_middle) {
+            const unsigned long long cnt = std::min(per_middle, middle_waves - done)*wave;
+            pieces.push_back({off, cnt});
+            off += cnt;
+        }
+        pieces.push_back({off, total - off});
+    } else {
+        unsigned long long per = (total + chunks - 1)/chunks;
+        per = (per + wave - 1)/wave*wave;
+        for (unsigned long long off = 0; off < total; off += per) pieces.push_back({off, std::min(per, total - off)});
+    }
     std::vector<cudaEvent_t> uploaded, computed;
     int rc = 0;
-    for (unsigned long long off = 0; off < total && !rc; off += per) {
-        const unsigned long long cnt = total - off < per ? total - off : per;
+    for (size_t piece_index = 0; piece_index < pieces.size() && !rc; piece_index++) {
+        const unsigned long long off = pieces[piece_index].first, cnt = pieces[piece_index].second;
         cudaEvent_t up, done;
         cudaEventCreateWithFlags(&up, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&done, cudaEventDisableTiming);

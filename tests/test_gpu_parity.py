@@ -319,18 +319,20 @@ def test_pipelined_host_stepping_is_bit_identical(lib):
     from graph_framework_b200.rays import RayTracer
     g = golden("ref_trace_extra_ordinary_wave_efit_rk4")
     base = unpack(g["per_step"][0][:8])
-    reps = 700                                  # ragged: 22400 rays, chunks do not divide evenly
-    start = {k: np.tile(v, reps) for k, v in base.items()}
-    n = start["w"].size
-    tr = RayTracer("extra_ordinary_wave", "efit", n, float(g["dt"]))
-    tr.set_state(start)
-    tr.init("")
-    tr.compile()
-    tr.step(25)
-    ref = tr.get_state()
-    for chunks in (1, 3, 8):
-        out = {k: np.empty(n) for k in ORDER + ("residual",)}
-        tr.step_host(25, start, out, chunks=chunks)
-        for k in ORDER + ("residual",):
-            assert np.array_equal(out[k], ref[k]), (chunks, k)
-    tr.close()
+    # ragged sizes: 22400 rays (less than one wave of blocks: equal pieces) and 400032 rays (7.04 waves:
+    # one-wave first piece, tail-wave last piece, the rest shared by the pieces between)
+    for reps, chunk_counts in ((700, (1, 3, 8)), (12501, (3,))):
+        start = {k: np.tile(v, reps) for k, v in base.items()}
+        n = start["w"].size
+        tr = RayTracer("extra_ordinary_wave", "efit", n, float(g["dt"]))
+        tr.set_state(start)
+        tr.init("")
+        tr.compile()
+        tr.step(25)
+        ref = tr.get_state()
+        for chunks in chunk_counts:
+            out = {k: np.empty(n) for k in ORDER + ("residual",)}
+            tr.step_host(25, start, out, chunks=chunks)
+            for k in ORDER + ("residual",):
+                assert np.array_equal(out[k], ref[k]), (reps, chunks, k)
+        tr.close()
