@@ -216,7 +216,7 @@ def main():
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
     ap.add_argument("--ref-rays", type=int, default=20000, help="rays of the bounded CPU sample")
     ap.add_argument("--options", default="", help="emit/launch options passed to gfb_rays_create")
-    ap.add_argument("--chunks", type=int, default=4, help="pieces of the ensemble pipelined by the e2e call")
+    ap.add_argument("--chunks", type=int, default=5, help="pieces of the ensemble pipelined by the e2e call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
