@@ -89,6 +89,8 @@ int gfb_kernel_launch(gfb_kernel *kernel, unsigned steps);
  * read-back of different pieces overlap on three streams (two copy engines + SMs).
  * host_src / host_dst: one pointer per per-ray slot (the first num_ray_slots pointer slots of the
  * kernel: inputs then outputs), NULL = no transfer for that slot.  Pinned memory recommended.
+ * Pieces end on whole waves of thread blocks; with 3 or more chunks the first piece is one wave and
+ * the last one the tail wave, because the first upload and the last read-back overlap nothing.
  * Returns after everything has completed. */
 int gfb_kernel_run_from_host(gfb_kernel *kernel, unsigned steps, int num_ray_slots,
                              const void *const *host_src, void *const *host_dst, int chunks);
