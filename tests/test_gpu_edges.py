@@ -267,3 +267,55 @@ def test_two_tracers_in_two_host_threads(lib):
         for k in serial[key][0]:
             assert np.array_equal(serial[key][0][k], threaded[key][0][k]), (key, k)
         assert np.array_equal(serial[key][1], threaded[key][1]), key
+
+
+def test_rebinning_composes_permutations(lib):
+    """Sorting rays that are already sorted (after they moved) folds the new permutation into the one
+    in force: gfb_unbin_rays still restores the caller's order in one pass, and gfb_bin_disorder
+    reports the decay that triggers the re-sort."""
+    n, cells = 50021, 29
+    rng = np.random.default_rng(33)
+    key = rng.uniform(0.0, 1.0, n)
+    tag = np.arange(n, dtype=np.float64)
+    ctx = lib.gfb_ctx_create(0)
+    for k, a in ((21, key), (22, tag)):
+        assert lib.gfb_buffer(ctx, k, a.nbytes, a.ctypes.data_as(ctypes.c_void_p), None) == 0
+    keys = (ctypes.c_uint64*2)(21, 22)
+    sort_key = (ctypes.c_uint64*1)(21)
+    lo, hi = np.array([0.0, 0.0]), np.array([1.0, 1.0])
+    grid = (ctypes.c_uint*2)(cells, 0)
+
+    def disorder():
+        f = ctypes.c_double(0.0)
+        assert lib.gfb_bin_disorder(ctx, sort_key, 1, lo.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                    hi.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), grid, n, ctypes.byref(f)) == 0
+        return f.value
+
+    def fetch(k):
+        out = np.empty(n)
+        assert lib.gfb_copy_d2h(ctx, k, out.ctypes.data_as(ctypes.c_void_p), 0) == 0
+        return out
+
+    assert disorder() > 0.9                                            # random order: almost every neighbour differs
+    assert lib.gfb_bin_rays(ctx, 21, 0.0, 1.0, cells, keys, 2, n) == 0
+    assert disorder() < 2.0*cells/n                                    # sorted: one boundary per occupied cell
+    first = fetch(22).astype(np.int64)
+    # the rays "move": new key values, written in the CURRENT device order
+    moved = np.clip(fetch(21) + rng.normal(0.0, 0.05, n), 0.0, 1.0)
+    assert lib.gfb_copy_h2d(ctx, 21, moved.ctypes.data_as(ctypes.c_void_p), 0) == 0
+    assert disorder() > 1.0/32.0
+    assert lib.gfb_bin_rays(ctx, 21, 0.0, 1.0, cells, keys, 2, n) == 0      # re-sort, permutations composed
+    total = fetch(22).astype(np.int64)
+    assert np.array_equal(np.sort(total), np.arange(n))
+    now = fetch(21)
+    assert np.all(np.diff(np.clip(now*cells, 0, cells - 1).astype(int)) >= 0)
+    # ray r = first[i] carried moved[i]; after the re-sort slot j holds ray total[j]
+    carried = np.empty(n)
+    carried[first] = moved
+    assert np.array_equal(now, carried[total])
+    host = np.empty(n)
+    assert lib.gfb_copy_rays_d2h(ctx, 21, host.ctypes.data_as(ctypes.c_void_p), n) == 0     # caller's order, device untouched
+    assert np.array_equal(host, carried) and lib.gfb_is_binned(ctx) == 1
+    assert lib.gfb_unbin_rays(ctx, keys, 2, n) == 0
+    assert np.array_equal(fetch(22), tag) and np.array_equal(fetch(21), carried)
+    lib.gfb_ctx_destroy(ctx)
