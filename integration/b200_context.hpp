@@ -40,6 +40,7 @@
 
 #include "random.hpp"
 #include "../include/gfb200.h"
+#include "text_passes.hpp"
 
 namespace gpu {
     template<jit::float_scalar T, bool SAFE_MATH=false>
@@ -60,73 +61,6 @@ namespace gpu {
             }
         }
         static uint64_t key(const void *p) { return reinterpret_cast<uint64_t> (p); }
-
-///  The reference's nodes write one operation per statement (`const double r<id> = a/b;`).  An IEEE
-///  FP64 division costs ~10 FP64-pipe instructions plus a guarded slow path on the GPU, and the
-///  reference's EFIT kernels divide 336-696 times per step by only ~80 distinct denominators
-///  (SURVEY.md App. A.1).  This pass rewrites the kernel TEXT before NVRTC sees it:
-///      a/b            ->  a*i<b>   with  const double i<b> = gfb::rcp(b);  once per denominator
-///      a/(double)c    ->  a*(1.0/(double)c)
-///      pow(a, (double)1.5)  ->  a*sqrt(a)
-///  gfb::rcp is the hardware seed refined to <= 1 ulp (skeleton.cuh).  The reference compiles its own
-///  kernels with -ffast-math (cpu_context.hpp:155-157), i.e. with reciprocal-math, so the arithmetic
-///  stays inside what the reference defines.  GFB_B200_IEEE_DIVIDE=1 keeps the text as emitted.
-        static std::string share_reciprocals(const std::string &source) {
-            if (std::getenv("GFB_B200_IEEE_DIVIDE")) return source;
-            auto is_register = [] (const std::string &t) {
-                if (t.size() < 2 || (t[0] != 'r' && t[0] != 'v' && t[0] != 'o')) return false;
-                for (const char ch : t) if (!std::isalnum(static_cast<unsigned char> (ch)) && ch != '_') return false;
-                return true;
-            };
-            std::istringstream in(source);
-            std::ostringstream out;
-            std::unordered_map<std::string, std::string> inverse;
-            std::string line;
-            const std::string head = "const double ";
-            while (std::getline(in, line)) {
-                if (line.find("extern \"C\"") != std::string::npos) inverse.clear();       // registers are per kernel
-                const size_t at = line.find(head);
-                const size_t eq = line.find(" = ");
-                if (line.size() > 400 || at == std::string::npos || eq == std::string::npos || line.back() != ';' ||
-                    line.find_first_not_of(' ') != at) {
-                    out << line << '\n';
-                    continue;
-                }
-                const std::string indent = line.substr(0, at);
-                const std::string name = line.substr(at + head.size(), eq - at - head.size());
-                const std::string rhs = line.substr(eq + 3, line.size() - eq - 4);
-                const size_t slash = rhs.find('/');
-                if (slash != std::string::npos && rhs.find('/', slash + 1) == std::string::npos &&
-                    rhs.find_first_of(" ,?") == std::string::npos) {
-                    const std::string num = rhs.substr(0, slash), den = rhs.substr(slash + 1);
-                    if (is_register(den)) {
-                        auto found = inverse.find(den);
-                        if (found == inverse.end()) {
-                            const std::string iname = "i" + den;
-                            out << indent << head << iname << " = gfb::rcp(" << den << ");\n";
-                            found = inverse.emplace(den, iname).first;
-                        }
-                        out << indent << head << name << " = " << num << "*" << found->second << ";\n";
-                        continue;
-                    }
-                    if (den.rfind("(double)", 0) == 0 && den.find('(', 8) == std::string::npos) {
-                        out << indent << head << name << " = " << num << "*(1.0/" << den << ");\n";
-                        continue;
-                    }
-                }
-                const std::string pow_head = "pow(", pow_tail = ", (double)1.5)";
-                if (rhs.rfind(pow_head, 0) == 0 && rhs.size() > pow_head.size() + pow_tail.size() &&
-                    rhs.compare(rhs.size() - pow_tail.size(), pow_tail.size(), pow_tail) == 0) {
-                    const std::string base = rhs.substr(pow_head.size(), rhs.size() - pow_head.size() - pow_tail.size());
-                    if (is_register(base)) {
-                        out << indent << head << name << " = " << base << "*sqrt(" << base << ");\n";
-                        continue;
-                    }
-                }
-                out << line << '\n';
-            }
-            return out.str();
-        }
 
     public:
 ///  cuda_context.hpp:111.
@@ -155,7 +89,7 @@ namespace gpu {
             (void)add_reduction;
             std::vector<const char *> cnames;
             for (auto &n : names) cnames.push_back(n.c_str());
-            const std::string text = share_reciprocals(kernel_source);
+            const std::string text = gfb_text::share_reciprocals(kernel_source);
             check(gfb_compile(ctx, text.c_str(), cnames.data(), static_cast<int> (cnames.size()),
                               "--device-as-default-execution-space"), "compile");
         }

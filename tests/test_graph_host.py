@@ -182,3 +182,40 @@ def test_index_nodes(g):
         assert np.array_equal(i2.evaluate(), [expect])
     g.set_variable(grid, np.arange(9.0)*2.0)                     # the array is a variable: new contents, same node
     assert np.array_equal(i2.evaluate(), [12.0])
+
+
+def test_reference_kernel_text_pass(tmp_path):
+    """integration/text_passes.hpp (applied by b200_context to kernels written by the reference's own
+    front end): one reciprocal per distinct denominator, constants folded, pow(x, 1.5) -> x sqrt(x);
+    table index expressions, multi-operator lines and long table literals pass through untouched;
+    reciprocals are not shared across kernels; GFB_B200_IEEE_DIVIDE=1 switches the pass off."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "text_pass_case")
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "text_pass_case.cpp"), "-o", exe], check=True)
+    src = "\n".join([
+        "const double a1[] = {" + ", ".join(["1.5"]*300) + "};",
+        'extern "C" __global__ void k1() {',
+        "        const double r1 = r2/r3;",
+        "        const double r4 = r5/r3;",
+        "        const double r6 = r1/(double)2.5;",
+        "        const double r7 = pow(r3, (double)1.5);",
+        "        const double r8 = a1[(unsigned char)min<double>(max<double>((r1 - 0.5)/0.25,0),63)];",
+        "        const double r9 = r1*r4 + r6/r3;",
+        "}",
+        'extern "C" __global__ void k2() {',
+        "        const double r10 = r11/r3;",
+        "}", ""])
+    out = subprocess.run([exe], input=src, capture_output=True, text=True, check=True).stdout
+    lines = out.splitlines()
+    assert lines[0] == src.splitlines()[0]
+    assert out.count("gfb::rcp(r3)") == 2                               # once per kernel
+    assert "const double r1 = r2*ir3;" in out and "const double r4 = r5*ir3;" in out
+    assert "const double r6 = r1*(1.0/(double)2.5);" in out
+    assert "const double r7 = r3*sqrt(r3);" in out
+    assert src.splitlines()[6] in out and src.splitlines()[7] in out  # index expression, compound line
+    assert lines.index("        const double ir3 = gfb::rcp(r3);") < lines.index("        const double r1 = r2*ir3;")
+    same = subprocess.run([exe], input=src, capture_output=True, text=True, check=True,
+                          env=dict(os.environ, GFB_B200_IEEE_DIVIDE="1")).stdout
+    assert same == src
