@@ -532,11 +532,6 @@ int gfb_kernel_create(gfb_ctx *c, const char *name, const uint64_t *ptr_keys, in
         k->slot_keys.push_back(ptr_keys[i]);
     }
     k->args.n = num_rays;
-//  Small ensembles: a block of `block_size` rays would leave SMs idle (10^4 rays in blocks of 128 are 79
-//  blocks for 148 SMs).  Halve the block, down to one warp, until there are two blocks per SM.
-    while (block_size >= 64 && (num_rays + block_size - 1)/block_size < 2ull*static_cast<unsigned long long> (c->sms)) {
-        block_size = (block_size/2 + 31)/32*32;
-    }
     k->block = block_size;
     k->grid = static_cast<unsigned> ((num_rays + block_size - 1)/block_size);
     if (k->grid == 0) k->grid = 1;
