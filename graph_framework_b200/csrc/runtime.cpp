@@ -31,6 +31,7 @@
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 extern "C" {
@@ -405,13 +406,10 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
     const bool pinned = user.find("-DGFB_MIN_BLOCKS") != std::string::npos ||
                         std::string(source).find("GFB_MIN_BLOCKS)") == std::string::npos;
     struct variant { CUmodule module = nullptr; int regs = 0; int local = 0; };
-    auto build = [&] (const int mb, variant &v) -> int {
-        const std::string opts = (pinned || mb == 0) ? user : user + " -DGFB_MIN_BLOCKS=" + std::to_string(mb);
-        std::vector<char> image;
-        if (nvrtc_compile(c->source, opts.c_str(), image, c->log)) {
-            std::fprintf(stderr, "%s\n", last_error.c_str());
-            return 1;
-        }
+    auto options_for = [&] (const int mb) {
+        return (pinned || mb == 0) ? user : user + " -DGFB_MIN_BLOCKS=" + std::to_string(mb);
+    };
+    auto load = [&] (const int mb, const std::vector<char> &image, variant &v) -> int {
         if (check_cu(driver.ModuleLoadData(&v.module, image.data()), "cuModuleLoadData")) return 1;
         for (int i = 0; i < num_names; i++) {
             CUfunction f;
@@ -424,7 +422,14 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
         return 0;
     };
     variant natural;
-    if (build(1, natural)) return 1;
+    {
+        std::vector<char> image;
+        if (nvrtc_compile(c->source, options_for(1).c_str(), image, c->log)) {
+            std::fprintf(stderr, "%s\n", last_error.c_str());
+            return 1;
+        }
+        if (load(1, image, natural)) return 1;
+    }
     c->module = natural.module;
     c->min_blocks = 0;
     if (pinned) return 0;
@@ -432,13 +437,33 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
     int m0 = regs8 > 0 ? 65536/(128*regs8) : 1;
     m0 = m0 < 1 ? 1 : (m0 > 8 ? 8 : m0);
     c->min_blocks = m0;
-    for (int mb = (m0 + 2 > 8 ? 8 : m0 + 2); mb > m0; mb--) {
+//  The candidates are independent NVRTC runs: compile them side by side, then take the first
+//  (highest) one that qualifies.
+    std::vector<int> candidates;
+    for (int mb = (m0 + 2 > 8 ? 8 : m0 + 2); mb > m0; mb--) candidates.push_back(mb);
+    std::vector<std::vector<char>> images(candidates.size());
+    std::vector<std::string> logs(candidates.size()), errors(candidates.size());
+    std::vector<int> status(candidates.size(), 0);
+    std::vector<std::thread> workers;
+    for (size_t i = 0; i < candidates.size(); i++) {
+        workers.emplace_back([&, i] {
+            status[i] = nvrtc_compile(c->source, options_for(candidates[i]).c_str(), images[i], logs[i]);
+            if (status[i]) errors[i] = last_error;      // last_error is per thread
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (size_t i = 0; i < candidates.size(); i++) {
+        if (status[i]) {
+            std::fprintf(stderr, "%s\n", errors[i].c_str());
+            return fail(errors[i]);
+        }
         variant v;
-        if (build(mb, v)) return 1;
+        if (load(candidates[i], images[i], v)) return 1;
         if (v.local - natural.local <= 128) {
             driver.ModuleUnload(natural.module);
             c->module = v.module;
-            c->min_blocks = mb;
+            c->min_blocks = candidates[i];
+            c->log = logs[i];
             return 0;
         }
         driver.ModuleUnload(v.module);
