@@ -20,6 +20,8 @@ namespace gfb_text {
 ///      a/b            ->  a*i<b>   with  const double i<b> = gfb::rcp(b);  once per denominator
 ///      a/(double)c    ->  a*(1.0/(double)c)
 ///      pow(a, (double)1.5)  ->  a*sqrt(a)
+///      sqrt(a)        ->  gfb::sqrt_from_rsqrt(a, gfb::rsqrt(a))   (refined hardware seed, IEEE at 0 and inf)
+///      (x - o)/s  inside a table index  ->  (x - o)*(1.0/s)         (what the full back end does too)
 ///  gfb::rcp is the hardware seed refined to <= 1 ulp (skeleton.cuh).  The reference compiles its own
 ///  kernels with -ffast-math (cpu_context.hpp:155-157), i.e. with reciprocal-math, so the arithmetic
 ///  stays inside what the reference defines.  GFB_B200_IEEE_DIVIDE=1 keeps the text as emitted.
@@ -71,7 +73,37 @@ namespace gfb_text {
                 rhs.compare(rhs.size() - pow_tail.size(), pow_tail.size(), pow_tail) == 0) {
                 const std::string base = rhs.substr(pow_head.size(), rhs.size() - pow_head.size() - pow_tail.size());
                 if (is_register(base)) {
-                    out << indent << head << name << " = " << base << "*sqrt(" << base << ");\n";
+                    out << indent << head << name << " = " << base << "*gfb::sqrt_from_rsqrt(" << base << ", gfb::rsqrt(" << base << "));\n";
+                    continue;
+                }
+            }
+            const std::string sqrt_head = "sqrt(";
+            if (rhs.rfind(sqrt_head, 0) == 0 && rhs.back() == ')' &&
+                is_register(rhs.substr(sqrt_head.size(), rhs.size() - sqrt_head.size() - 1))) {
+                const std::string arg = rhs.substr(sqrt_head.size(), rhs.size() - sqrt_head.size() - 1);
+                out << indent << head << name << " = gfb::sqrt_from_rsqrt(" << arg << ", gfb::rsqrt(" << arg << "));\n";
+                continue;
+            }
+//  Table look-ups: `...max<double>((x - offset)/scale,0)...` with a literal scale.
+            if (rhs.find("max<double>((") != std::string::npos) {
+                std::string edited = rhs;
+                size_t pos = 0;
+                bool changed = false;
+                while ((pos = edited.find(")/", pos)) != std::string::npos) {
+                    size_t end = pos + 2;
+                    while (end < edited.size() && (std::isdigit(static_cast<unsigned char> (edited[end])) || edited[end] == '.' ||
+                                                   edited[end] == 'e' || edited[end] == 'E' || edited[end] == '-' || edited[end] == '+')) end++;
+                    if (end > pos + 2 && end < edited.size() && edited[end] == ',') {
+                        const std::string with = ")*(1.0/" + edited.substr(pos + 2, end - pos - 2) + ")";
+                        edited.replace(pos, end - pos, with);
+                        pos += with.size();
+                        changed = true;
+                    } else {
+                        pos += 2;
+                    }
+                }
+                if (changed) {
+                    out << indent << head << name << " = " << edited << ";\n";
                     continue;
                 }
             }

@@ -186,8 +186,9 @@ def test_index_nodes(g):
 
 def test_reference_kernel_text_pass(tmp_path):
     """integration/text_passes.hpp (applied by b200_context to kernels written by the reference's own
-    front end): one reciprocal per distinct denominator, constants folded, pow(x, 1.5) -> x sqrt(x);
-    table index expressions, multi-operator lines and long table literals pass through untouched;
+    front end): one reciprocal per distinct denominator, constants folded, pow(x, 1.5) -> x sqrt(x) with
+    the refined rsqrt, table indices multiply by the inverse cell size; multi-operator lines and long
+    table literals pass through untouched;
     reciprocals are not shared across kernels; GFB_B200_IEEE_DIVIDE=1 switches the pass off."""
     import os
     import subprocess
@@ -213,8 +214,9 @@ def test_reference_kernel_text_pass(tmp_path):
     assert out.count("gfb::rcp(r3)") == 2                               # once per kernel
     assert "const double r1 = r2*ir3;" in out and "const double r4 = r5*ir3;" in out
     assert "const double r6 = r1*(1.0/(double)2.5);" in out
-    assert "const double r7 = r3*sqrt(r3);" in out
-    assert src.splitlines()[6] in out and src.splitlines()[7] in out  # index expression, compound line
+    assert "const double r7 = r3*gfb::sqrt_from_rsqrt(r3, gfb::rsqrt(r3));" in out
+    assert "max<double>((r1 - 0.5)*(1.0/0.25),0),63)];" in out          # table index: multiply by the inverse cell size
+    assert src.splitlines()[7] in out                                  # compound line untouched
     assert lines.index("        const double ir3 = gfb::rcp(r3);") < lines.index("        const double r1 = r2*ir3;")
     same = subprocess.run([exe], input=src, capture_output=True, text=True, check=True,
                           env=dict(os.environ, GFB_B200_IEEE_DIVIDE="1")).stdout
