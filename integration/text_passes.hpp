@@ -27,6 +27,7 @@ namespace gfb_text {
 ///  stays inside what the reference defines.  GFB_B200_IEEE_DIVIDE=1 keeps the text as emitted.
     inline std::string share_reciprocals(const std::string &source) {
         if (std::getenv("GFB_B200_IEEE_DIVIDE")) return source;
+        const bool divides_only = std::getenv("GFB_B200_DIVIDES_ONLY") != nullptr;      // A/B switch for measurements
         auto is_register = [] (const std::string &t) {
             if (t.size() < 2 || (t[0] != 'r' && t[0] != 'v' && t[0] != 'o')) return false;
             for (const char ch : t) if (!std::isalnum(static_cast<unsigned char> (ch)) && ch != '_') return false;
@@ -78,14 +79,14 @@ namespace gfb_text {
                 }
             }
             const std::string sqrt_head = "sqrt(";
-            if (rhs.rfind(sqrt_head, 0) == 0 && rhs.back() == ')' &&
+            if (!divides_only && rhs.rfind(sqrt_head, 0) == 0 && rhs.back() == ')' &&
                 is_register(rhs.substr(sqrt_head.size(), rhs.size() - sqrt_head.size() - 1))) {
                 const std::string arg = rhs.substr(sqrt_head.size(), rhs.size() - sqrt_head.size() - 1);
                 out << indent << head << name << " = gfb::sqrt_from_rsqrt(" << arg << ", gfb::rsqrt(" << arg << "));\n";
                 continue;
             }
 //  Table look-ups: `...max<double>((x - offset)/scale,0)...` with a literal scale.
-            if (rhs.find("max<double>((") != std::string::npos) {
+            if (!divides_only && rhs.find("max<double>((") != std::string::npos) {
                 std::string edited = rhs;
                 size_t pos = 0;
                 bool changed = false;
