@@ -40,6 +40,7 @@ namespace absorption {
     class weak_damping final : public method<T, SAFE_MATH> {
     private:
         leaf_ptr kamp_re, kamp_im, w, kx, ky, kz, x, y, z, t;
+        leaf_ptr re_next, im_next;
         std::unique_ptr<workflow::manager<T, SAFE_MATH>> own;
         workflow::manager<T, SAFE_MATH> &work;
         size_t item;
@@ -54,8 +55,8 @@ namespace absorption {
                                          std::vector<leaf_ptr> {Dc->df(kx), Dc->df(ky), Dc->df(kz)};
             auto slope = k_unit->dot(grad[0]*eq->get_esup1(x, y, z) + grad[1]*eq->get_esup2(x, y, z) +
                                      grad[2]*eq->get_esup3(x, y, z));
-            auto re_next = k_vec->length() - Dw.re/slope;
-            auto im_next = -1.0*(Dw.im/slope);
+            re_next = k_vec->length() - Dw.re/slope;
+            im_next = -1.0*(Dw.im/slope);
 //  Argument order of absorption.hpp:414-424 with kamp split in two.
             graph::input_nodes<T, SAFE_MATH> inputs = {kamp_re, kamp_im, kx, ky, kz, x, y, z, t, w};
             graph::map_nodes<T, SAFE_MATH> setters = {{re_next, kamp_re}, {im_next, kamp_im}};
@@ -95,6 +96,9 @@ namespace absorption {
         }
         void wait() { work.wait(); }
         workflow::manager<T, SAFE_MATH> &get_work() { return work; }
+///  The expressions the kernel assigns to (Re, Im) k_amp, e.g. for host evaluation.
+        leaf_ptr get_real_expression() { return re_next; }
+        leaf_ptr get_imaginary_expression() { return im_next; }
     };
 
 //------------------------------------------------------------------------------

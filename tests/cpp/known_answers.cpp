@@ -252,6 +252,46 @@ static void solves_every_unknown(const char *what, const double tolerance, const
     EXPECT(ok, what);
 }
 
+// absorption::weak_damping with the reference's calling sequence (own device context, sync_device,
+// run, sync_host; absorption.hpp:466-483): the kernel against the host evaluation of the same
+// expression (jit_test.cpp style), on rays that straddle the electron cyclotron resonance of the
+// EFIT case, plus the analytic limits far from it (no damping, Re k_amp = |k|).
+static void absorption_standalone() {
+    const size_t n = 96;
+    ray r(n);
+    auto kamp_re = graph::variable(n, "kamp_re"), kamp_im = graph::variable(n, "kamp_im");
+    std::vector<double> xs(n), ws(n), kys(n);
+    for (size_t i = 0; i < n; i++) {
+        xs[i] = 1.7 + 0.7*static_cast<double> (i)/static_cast<double> (n - 1);
+        ws[i] = 690.0 + static_cast<double> (i%7)*3.0;
+        kys[i] = -100.0 + static_cast<double> (i%5)*4.0;
+    }
+    r.w->set(ws); r.kx->set(-600.0); r.ky->set(kys); r.kz->set(7.0);
+    r.x->set(xs); r.y->set(0.02); r.z->set(0.03); r.t->set(0.0);
+    auto eq = equilibrium::make_efit<> (EFIT_FILE);
+    absorption::weak_damping<> damping(kamp_re, kamp_im, r.w, r.kx, r.ky, r.kz, r.x, r.y, r.z, r.t, eq);
+    damping.compile();
+    damping.sync_device();
+    damping.run();
+    damping.sync_host();
+    const auto im_host = damping.get_imaginary_expression()->evaluate();
+    const auto re_host = damping.get_real_expression()->evaluate();
+    double worst_im = 0.0, worst_re = 0.0, largest = 0.0;
+    size_t undamped = 0;
+    for (size_t i = 0; i < n; i++) {
+        const double im = kamp_im->data()[i], re = kamp_re->data()[i];
+        largest = std::max(largest, std::abs(im));
+        worst_im = std::max(worst_im, std::abs(im - im_host.at(i))/std::max(std::abs(im_host.at(i)), 1.0E-6));
+        if (std::abs(im_host.at(i)) > 1.0E-3) worst_re = std::max(worst_re, std::abs(re - re_host.at(i))/std::abs(re_host.at(i)));
+        const double klen = std::sqrt(600.0*600.0 + kys[i]*kys[i] + 49.0);
+        if (im == 0.0 && std::abs(re - klen) < 1.0E-9*klen) undamped++;
+    }
+    EXPECT(worst_im < 1.0E-8, "weak_damping kernel == host evaluation (Im k_amp)");
+    EXPECT(worst_re < 1.0E-10, "weak_damping kernel == host evaluation (Re k_amp)");
+    EXPECT(largest > 1.0, "rays at the resonance are damped");
+    EXPECT(undamped > 5, "far from the resonance: Im k_amp = 0 and Re k_amp = |k|");
+}
+
 int main() {
     const double tolerance = 1.6E-21;       // physics_test.cpp:652, the reference's CUDA branch
     invariant();
@@ -265,6 +305,7 @@ int main() {
     cold_plasma_cutoffs();
     efit_reflects();
     adaptive();
+    absorption_standalone();
     keeps_dispersion<solver::rk2<dispersion::simple<>>> ("rk2 simple keeps D^2 < 1e-30", 1.0E-30, 0.5, 0.25, 1.0);
     keeps_dispersion<solver::rk4<dispersion::simple<>>> ("rk4 simple keeps D^2 < 1e-30", 1.0E-30, 0.5, 0.25, 1.0);
     keeps_dispersion<solver::rk2<dispersion::gaussian_well<>>> ("rk2 gaussian_well keeps D^2 < 1e-30", 1.0E-30, 0.5, 0.25, 0.00001);
