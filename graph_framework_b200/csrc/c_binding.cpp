@@ -216,6 +216,7 @@ struct run_options {
     unsigned fused_steps = 0;
     bool absorption = false;
     int bin_rays = -1;              // -1: on when the equilibrium has tables; 0 off; > 0 re-sort period in steps
+    int reference_defects = -1;     // -1: dispersion::reference_defects() as it stands; 0 true derivatives; 1 the reference's
 };
 run_options parse_options(const char *options) {
     run_options o;
@@ -238,6 +239,7 @@ run_options parse_options(const char *options) {
         else if (k == "fused_steps") o.fused_steps = static_cast<unsigned> (v);
         else if (k == "absorption") o.absorption = v != 0;
         else if (k == "bin_rays") o.bin_rays = static_cast<int> (v);
+        else if (k == "reference_defects") o.reference_defects = v != 0 ? 1 : 0;
     }
     return o;
 }
@@ -377,6 +379,8 @@ gfb_rays *gfb_rays_create(const char *dispersion_name, const char *equilibrium_n
     const run_options o = parse_options(options);
     const std::string d = dispersion_name, s = solver_name;
     tracer_base *t = nullptr;
+    const bool defects_before = dispersion::reference_defects();
+    if (o.reference_defects >= 0) dispersion::reference_defects() = o.reference_defects != 0;
     if (d == "cold_plasma") t = make_tracer<dispersion::cold_plasma<>> (s, r->vars, dtc, eq, num_rays, device, o);
     else if (d == "ordinary_wave") t = make_tracer<dispersion::ordinary_wave<>> (s, r->vars, dtc, eq, num_rays, device, o);
     else if (d == "extra_ordinary_wave") t = make_tracer<dispersion::extra_ordinary_wave<>> (s, r->vars, dtc, eq, num_rays, device, o);
@@ -387,6 +391,7 @@ gfb_rays *gfb_rays_create(const char *dispersion_name, const char *equilibrium_n
     else if (d == "gaussian_well") t = make_tracer<dispersion::gaussian_well<>> (s, r->vars, dtc, eq, num_rays, device, o);
     else if (d == "ion_cyclotron") t = make_tracer<dispersion::ion_cyclotron<>> (s, r->vars, dtc, eq, num_rays, device, o);
     else if (d == "stiff") t = make_tracer<dispersion::stiff<>> (s, r->vars, dtc, eq, num_rays, device, o);
+    dispersion::reference_defects() = defects_before;
     if (!t) {
         rays_fail(std::string("unknown dispersion/solver ") + d + "/" + s);
         return nullptr;

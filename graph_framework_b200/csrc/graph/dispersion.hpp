@@ -35,6 +35,13 @@ namespace dispersion {
         virtual ~dispersion_function() {}
         virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr t,
                            equilibrium::shared<T, SAFE_MATH> &eq) = 0;
+///  Reference compatibility (see reference_defects()): the term the reference's symbolic
+///  dD/d(coordinate `axis`) carries on top of the true derivative; null when there is none.
+        virtual leaf_ptr reference_defect(leaf_ptr, vector_ptr, leaf_ptr, leaf_ptr, leaf_ptr, leaf_ptr,
+                                          equilibrium::shared<T, SAFE_MATH> &, int &axis) {
+            axis = -1;
+            return leaf_ptr();
+        }
         typedef T base;
         static constexpr bool safe_math = SAFE_MATH;
     };
@@ -188,9 +195,13 @@ namespace dispersion {
 ///  Cold plasma determinant with electrons and every ion species of the equilibrium.
     template<typename T=double, bool SAFE_MATH=false>
     class cold_plasma : public physics<T, SAFE_MATH> {
-    public:
-        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
-                           equilibrium::shared<T, SAFE_MATH> &eq) {
+    protected:
+///  The named sub-expressions of the determinant (nodes are interned: building them twice costs nothing).
+        struct elements {
+            leaf_ptr w2, b_sq, npara2, nperp2, m11, m12, m13, m22, m33;
+        };
+        elements build(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z,
+                       equilibrium::shared<T, SAFE_MATH> &eq) {
             auto wpe2 = build_plasma_frequency(eq->get_electron_density(x, y, z), this->q, this->me, this->c, this->epsilon0);
             auto b_vec = eq->get_magnetic_field(x, y, z);
             auto b_len = b_vec->length();
@@ -221,12 +232,47 @@ namespace dispersion {
             auto nperp = b_hat->cross(n)->length();
             auto nperp2 = nperp*nperp;
 
-            auto m11 = e11 - npara2;
-            auto m12 = e12;
-            auto m13 = npara*nperp;
-            auto m22 = e11 - npara2 - nperp2;
-            auto m33 = e33 - nperp2;
-            return (m11*m22 - m12*m12)*m33 - m22*(m13*m13);
+            elements e;
+            e.w2 = w2;
+            e.b_sq = b_vec->dot(b_vec);
+            e.npara2 = npara2;
+            e.nperp2 = nperp2;
+            e.m11 = e11 - npara2;
+            e.m12 = e12;
+            e.m13 = npara*nperp;
+            e.m22 = e11 - npara2 - nperp2;
+            e.m33 = e33 - nperp2;
+            return e;
+        }
+    public:
+        virtual leaf_ptr D(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                           equilibrium::shared<T, SAFE_MATH> &eq) {
+            const elements e = build(w, k_vec, x, y, z, eq);
+            return (e.m11*e.m22 - e.m12*e.m12)*e.m33 - e.m22*(e.m13*e.m13);
+        }
+
+///  What the reference's symbolic dD/d(axis) contains on top of the true derivative.
+///
+///  The reference's expression reducer rewrites ((a b)^2 c)/(d^2 b^4) as a^2 c/d^4 (it should be
+///  a^2 c/(d^2 b^2); four variables reproduce it, oracle/ref_driver.cpp `reducer`).  n_par^2 and
+///  n_perp^2 are N^2/(B.B w^2); in the quotient rule of their derivative along a coordinate on which
+///  B.B depends through a common factor s (the 1/R of the EFIT field components, coordinate z), the
+///  term -n^2 d(B.B)/(B.B) comes out multiplied by w^2/((B.B)^2 s).  The faulty form survives in the
+///  copies of n_par^2 and n_perp^2 inside m11 and m22; m33 and m13 reduce along another path and are
+///  right.  With K = -(d(B.B)/B.B) (w^2/((B.B)^2 s) - 1):
+///      extra = K ((n_par^2 + n_perp^2) m13^2 - (n_par^2 m22 + m11 (n_par^2 + n_perp^2)) m33).
+///  Checked against the reference's own kernels: dkz/dt agrees to 4e-15 (median) on the 64 + 16 states
+///  of tests/golden/ref_rhs_cold_plasma_efit.npz and ref_defect_cold_plasma_efit.npz.
+        virtual leaf_ptr reference_defect(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z, leaf_ptr,
+                                          equilibrium::shared<T, SAFE_MATH> &eq, int &axis) {
+            const auto defect = eq->get_reducer_defect(x, y, z);
+            axis = defect.axis;
+            if (axis < 0) return leaf_ptr();
+            const elements e = build(w, k_vec, x, y, z, eq);
+            leaf_ptr coordinate = axis == 0 ? x : (axis == 1 ? y : z);
+            auto K = -1.0*(e.b_sq->df(coordinate)/e.b_sq)*(e.w2/(e.b_sq*e.b_sq*defect.scale) - 1.0);
+            auto n2 = e.npara2 + e.nperp2;
+            return K*(n2*(e.m13*e.m13) - (e.npara2*e.m22 + e.m11*n2)*e.m33);
         }
     };
 
@@ -350,6 +396,15 @@ namespace dispersion {
         return on;
     }
 
+///  Whether the ray equations reproduce the reference where its symbolic derivative is defective
+///  (cold_plasma in the EFIT field: dD/dz, see cold_plasma::reference_defect).  Default: yes -- results
+///  identical to the reference's; false gives the true derivative.  GFB_TRUE_DERIVATIVES=1 in the
+///  environment or the tracer option reference_defects=0 switch it off.
+    inline bool &reference_defects() {
+        static thread_local bool on = std::getenv("GFB_TRUE_DERIVATIVES") == nullptr;
+        return on;
+    }
+
 ///  Whether dispersion_interface differentiates D with one reverse sweep (graph::gradient)
 ///  instead of seven forward df() calls.
     inline bool &reverse_mode() {
@@ -396,6 +451,16 @@ namespace dispersion {
                 dDdx = D->df(x);
                 dDdy = D->df(y);
                 dDdz = D->df(z);
+            }
+
+            if (reference_defects()) {
+                int axis = -1;
+                auto extra = DISPERSION_FUNCTION().reference_defect(w, k_vec, x, y, z, t, eq, axis);
+                if (extra.get()) {
+                    if (axis == 0) dDdx = dDdx + extra;
+                    if (axis == 1) dDdy = dDdy + extra;
+                    if (axis == 2) dDdz = dDdz + extra;
+                }
             }
 
             if (graph::pseudo_variable_cast(x).get()) {

@@ -131,6 +131,13 @@ namespace equilibrium {
         virtual leaf_ptr get_z(leaf_ptr, leaf_ptr, leaf_ptr x3) { return x3; }
 ///  Extension (no reference counterpart): see cell_grid.
         virtual cell_grid get_cell_grid() const { return cell_grid(); }
+///  Reference compatibility (dispersion::cold_plasma::reference_defect): the coordinate along which
+///  the reference's reducer mis-cancels the derivative of B.B in this field, and the factor involved.
+        struct reducer_defect {
+            int axis = -1;              ///< 0, 1, 2 = x, y, z; -1: none known
+            leaf_ptr scale;
+        };
+        virtual reducer_defect get_reducer_defect(leaf_ptr, leaf_ptr, leaf_ptr) { return reducer_defect(); }
     };
 
     template<typename T=double, bool SAFE_MATH=false>
@@ -305,6 +312,16 @@ namespace equilibrium {
         virtual leaf_ptr get_ion_temperature(const size_t, leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return ti_cache; }
         virtual vector_ptr get_magnetic_field(leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return b_cache; }
         leaf_ptr get_psi(leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return psi_cache; }
+///  Every field component carries 1/R (equilibrium.hpp:1363-1381): B.B = G/R^2, and the reducer's
+///  faulty cancellation along z leaves R^8 behind (measured: exact to 10 digits on every state).
+        virtual typename generic<T, SAFE_MATH>::reducer_defect get_reducer_defect(leaf_ptr x, leaf_ptr y, leaf_ptr) {
+            typename generic<T, SAFE_MATH>::reducer_defect d;
+            auto r2 = x*x + y*y;
+            auto r4 = r2*r2;
+            d.axis = 2;
+            d.scale = r4*r4;
+            return d;
+        }
 ///  The psi(R, Z) tables: numr x numz cells.  A ray at the speed of light crosses one cell in
 ///  dr/dt steps; the hint assumes the reference's example step (2e-5).
         virtual cell_grid get_cell_grid() const {

@@ -63,6 +63,17 @@ def trace_cases():
              per_step=per_step, long=long)
 
 
+def interior_case():
+    """cold_plasma + EFIT started INSIDE the plasma (the efit_example rays of trace_cases start at
+    R = 2.5 in vacuum, where cold-plasma D is doubly degenerate and the reference's dkz/dt is a
+    ratio of two rounding-level numbers): Newton for kx, 5 single steps, 200 steps in two blocks."""
+    n, dt = 32, 2.0e-5
+    s = workloads.interior_states(n, seed=9)
+    per_step = reference.trace("cold_plasma", "efit", s, dt, 5, save_every=1, init="kx", solver="rk4")
+    long = reference.trace("cold_plasma", "efit", s, dt, 200, save_every=100, init="kx", solver="rk4")
+    save("ref_trace_cold_plasma_efit_interior_rk4", state=workloads.pack(s), dt=np.array(dt), per_step=per_step, long=long)
+
+
 def bench_case():
     # xrays_bench initial conditions (every ray identical), xrays_bench.cpp:62-79
     s = workloads.bench_rays(8)
@@ -85,6 +96,16 @@ def vmec_case():
     for disp in ("ordinary_wave", "cold_plasma"):
         out = reference.rhs(disp, "vmec", s)
         save("ref_rhs_%s_vmec" % disp, state=workloads.pack(s), rhs=out)
+
+
+def vmec_trace_case(disp="ordinary_wave"):
+    """VMEC trajectory from the reference: Newton solve for k_s, then 20 single RK4 steps, every
+    state recorded (records 0..3 feed the per-step tests, record 20 the block test).  One run costs
+    the reference ~10 min of graph building plus the g++ compile of its 54 k-statement kernel."""
+    n, dt = 16, 1.0e-4
+    s = workloads.vmec_states(n, seed=8)
+    rec = reference.trace(disp, "vmec", s, dt, 20, save_every=1, init="kx", solver="rk4")
+    save("ref_trace_%s_vmec_rk4" % disp, state=workloads.pack(s), dt=np.array(dt), per_step=rec)
 
 
 def defect_case():
@@ -122,13 +143,15 @@ def absorb_case():
 if __name__ == "__main__":
     if not reference.available():
         raise SystemExit("oracle/_ref/ref_driver missing: run `make -C oracle ref` first")
-    which = sys.argv[1:] or ["rhs", "trace", "bench", "korc", "defect"]
+    which = sys.argv[1:] or ["rhs", "trace", "bench", "korc", "defect", "interior"]
     if "rhs" in which:
         rhs_cases()
     if "trace" in which:
         trace_cases()
     if "bench" in which:
         bench_case()
+    if "interior" in which:
+        interior_case()
     if "korc" in which:
         korc_case()
     if "defect" in which:
@@ -137,3 +160,7 @@ if __name__ == "__main__":
         vmec_case()
     if "absorb" in which:
         absorb_case()
+    if "vmec_trace" in which:
+        vmec_trace_case("ordinary_wave")
+    if "vmec_trace_cold" in which:
+        vmec_trace_case("cold_plasma")

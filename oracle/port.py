@@ -218,8 +218,49 @@ def dispersion(name, eq, w, kx, ky, kz, x, y, z, t):
 ORDER = ("t", "w", "x", "y", "z", "kx", "ky", "kz")
 
 
-def rhs(name, eq, s):
-    """dispersion.hpp:1387-1433 for Cartesian equilibria: returns dict with dxdt..dkzdt and D."""
+def cold_plasma_reference_defect(eq, s):
+    """What the reference's symbolic dD/dz carries on top of the true derivative for cold_plasma in
+    the EFIT field.  Its reducer rewrites ((a b)^2 c)/(d^2 b^4) as a^2 c/d^4 (arithmetic.hpp divide /
+    multiply reductions; reproduced with four plain variables by `ref_driver reducer`), which hits the
+    quotient-rule term of d(n_par^2)/dz and d(n_perp^2)/dz inside m11 and m22 (dispersion.hpp:994-1003):
+        extra = K ((p + q) m13^2 - (p m22 + m11 (p + q)) m33),   p = n_par^2, q = n_perp^2,
+        K = -(d(B.B)/dz / B.B) (w^2/((B.B)^2 R^8) - 1).
+    Pinned to the reference's own kernels in tests/test_oracle.py."""
+    def elements(x, y, z, w, kx, ky, kz):
+        f = eq.fields(x, y, z)
+        b = f["b"]
+        g = _dot(b, b)
+        bl = np.sqrt(g)
+        bh = (b[0]/bl, b[1]/bl, b[2]/bl)
+        n = (kx/w, ky/w, kz/w)
+        w2 = w*w
+        wpe2 = f["ne"]*Q*Q/(EPSILON0*ME*C*C)
+        ec = -Q*bl/(ME*C)
+        denome = 1.0 - ec*ec/w2
+        e11 = 1.0 - (wpe2/w2)/denome
+        e33 = wpe2
+        wpi2 = f["ni"]*Q*Q/(EPSILON0*MI*C*C)
+        ic = Q*bl/(MI*C)
+        denomi = 1.0 - ic*ic/w2
+        e11 = e11 - (wpi2/w2)/denomi
+        e33 = 1.0 - (e33 + wpi2)/w2
+        npara = _dot(bh, n)
+        cr = _cross(bh, n)
+        p, q = npara*npara, _dot(cr, cr)
+        return g, p, q, e11 - p, e11 - p - q, e33 - q
+    c = {k: np.asarray(s[k], dtype=np.complex128) for k in ORDER}
+    g_z = elements(c["x"], c["y"], c["z"] + 1j*H, c["w"], c["kx"], c["ky"], c["kz"])[0].imag/H
+    g, p, q, m11, m22, m33 = (v.real for v in elements(c["x"], c["y"], c["z"], c["w"], c["kx"], c["ky"], c["kz"]))
+    r2 = np.asarray(s["x"], dtype=np.float64)**2 + np.asarray(s["y"], dtype=np.float64)**2
+    w = np.asarray(s["w"], dtype=np.float64)
+    K = -(g_z/g)*(w*w/(g*g*r2**4) - 1.0)
+    return K*((p + q)*(p*q) - (p*m22 + m11*(p + q))*m33)
+
+
+def rhs(name, eq, s, reference_defects=True):
+    """dispersion.hpp:1387-1433 for Cartesian equilibria: returns dict with dxdt..dkzdt and D.
+    reference_defects: reproduce the reference's effective dD/dz for cold_plasma + EFIT (see
+    cold_plasma_reference_defect) instead of the true derivative."""
     base = {k: np.asarray(s[k], dtype=np.complex128) for k in ORDER}
 
     def d(var):
@@ -229,26 +270,29 @@ def rhs(name, eq, s):
 
     D = dispersion(name, eq, base["w"], base["kx"], base["ky"], base["kz"], base["x"], base["y"], base["z"], base["t"]).real
     dDdw = d("w")
+    dDdz = d("z")
+    if reference_defects and name == "cold_plasma" and isinstance(eq, Efit):
+        dDdz = dDdz + cold_plasma_reference_defect(eq, s)
     return {"dxdt": -d("kx")/dDdw, "dydt": -d("ky")/dDdw, "dzdt": -d("kz")/dDdw,
-            "dkxdt": d("x")/dDdw, "dkydt": d("y")/dDdw, "dkzdt": d("z")/dDdw, "D": D}
+            "dkxdt": d("x")/dDdw, "dkydt": d("y")/dDdw, "dkzdt": dDdz/dDdw, "D": D}
 
 
 EVOLVED = (("kx", "dkxdt"), ("ky", "dkydt"), ("kz", "dkzdt"), ("x", "dxdt"), ("y", "dydt"), ("z", "dzdt"))
 
 
-def rk4_step(name, eq, s, dt):
+def rk4_step(name, eq, s, dt, reference_defects=True):
     """solver.hpp:811-869.  Returns (new state, residual = D^2 at the old state)."""
     s = {k: np.asarray(s[k], dtype=np.float64) for k in ORDER}
-    f1 = rhs(name, eq, s)
+    f1 = rhs(name, eq, s, reference_defects)
     k1 = {v: dt*f1[r] for v, r in EVOLVED}
     s2 = dict(s, t=s["t"] + dt/2.0, **{v: s[v] + k1[v]/2.0 for v, _ in EVOLVED})
-    f2 = rhs(name, eq, s2)
+    f2 = rhs(name, eq, s2, reference_defects)
     k2 = {v: dt*f2[r] for v, r in EVOLVED}
     s3 = dict(s, t=s["t"] + dt/2.0, **{v: s[v] + k2[v]/2.0 for v, _ in EVOLVED})
-    f3 = rhs(name, eq, s3)
+    f3 = rhs(name, eq, s3, reference_defects)
     k3 = {v: dt*f3[r] for v, r in EVOLVED}
     s4 = dict(s, t=s["t"] + dt, **{v: s[v] + k3[v] for v, _ in EVOLVED})
-    f4 = rhs(name, eq, s4)
+    f4 = rhs(name, eq, s4, reference_defects)
     k4 = {v: dt*f4[r] for v, r in EVOLVED}
     out = dict(s, t=s["t"] + dt)
     for v, _ in EVOLVED:
@@ -270,11 +314,10 @@ def rk2_step(name, eq, s, dt):
     return out, f1["D"]**2
 
 
-def trace(name, eq, s, dt, nsteps, order=4):
-    step = rk4_step if order == 4 else rk2_step
+def trace(name, eq, s, dt, nsteps, order=4, reference_defects=True):
     res = None
     for _ in range(nsteps):
-        s, res = step(name, eq, s, dt)
+        s, res = rk4_step(name, eq, s, dt, reference_defects) if order == 4 else rk2_step(name, eq, s, dt)
     return s, res
 
 

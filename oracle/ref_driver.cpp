@@ -31,6 +31,11 @@
 //                does; power/d_power follow the bin_power stage (xrays.cpp:674-793, T = double) fed
 //                with Im kamp (reference_imag_variable, xrays.cpp:743).  Record 0 holds power = 1,
 //                d_power = 0 (the state before the first bin_power kernel).
+//   ref_driver reducer
+//       the reference's reducer defect behind its wrong cold-plasma dD/dz, with four plain variables:
+//       ((A W)^2 B)/(C^2 W^4) built from graph nodes, evaluated by the reference's host evaluate(), next
+//       to the same arithmetic in plain doubles; plus the cut-down expression of the ray equations
+//       d/dz [ (z Q - x S)^2 / ((1 + z^2) W^2) ]  against a central difference.  Prints one JSON line.
 //   ref_driver erfi <N> <in.bin> <out.bin>
 //       in: N doubles x; out: 2 arrays special::w_im(x), Re special::erfi(x + 0i) (special_functions.hpp)
 #include <chrono>
@@ -462,6 +467,35 @@ static int erfi_values(int argc, char **argv) {
     if (DNAME == "cold_plasma" && SNAME == "rk2") return FN<solver::rk2<dispersion::cold_plasma<T>>> (argc, argv);          \
     if (DNAME == "simple" && SNAME == "rk2") return FN<solver::rk2<dispersion::simple<T>>> (argc, argv);
 
+//  Minimal reproduction of the reducer rule at fault.
+static int reducer_defect() {
+    auto A = graph::variable<T> (1, "A"), B = graph::variable<T> (1, "B"), C = graph::variable<T> (1, "C"), W = graph::variable<T> (1, "W");
+    const double a = 1.3, b = 0.7, c = 2.2, w = 500.0;
+    graph::variable_cast(A)->set(a); graph::variable_cast(B)->set(b); graph::variable_cast(C)->set(c); graph::variable_cast(W)->set(w);
+    auto two = graph::constant<T> (2.0), four = graph::constant<T> (4.0);
+    auto f = (graph::pow(A*W, two)*B)/(graph::pow(C, two)*graph::pow(W, four));
+    const double from_graph = f->evaluate().at(0);
+    const double direct = (a*w)*(a*w)*b/(c*c*w*w*w*w);
+    const double what_it_became = a*a*b/(c*c*c*c);
+
+    auto x = graph::variable<T> (1, "x"), z = graph::variable<T> (1, "z"), Q = graph::variable<T> (1, "Q"), S = graph::variable<T> (1, "S");
+    graph::variable_cast(x)->set(1.5); graph::variable_cast(z)->set(0.2); graph::variable_cast(Q)->set(-20.0); graph::variable_cast(S)->set(30.0);
+    auto n = z*Q - x*S;
+    auto h = (n*n)/((1.0 + z*z)*(W*W));
+    const double symbolic = h->df(z)->evaluate().at(0);
+    const double step = 1.0e-6;
+    graph::variable_cast(z)->set(0.2 + step);
+    const double hp = h->evaluate().at(0);
+    graph::variable_cast(z)->set(0.2 - step);
+    const double hm = h->evaluate().at(0);
+    std::printf("{\"expression\": \"((A W)^2 B)/(C^2 W^4)\", \"A\": %.17g, \"B\": %.17g, \"C\": %.17g, \"W\": %.17g, "
+                "\"reference_graph\": %.17g, \"direct\": %.17g, \"a2b_over_c4\": %.17g, "
+                "\"derivative_expression\": \"d/dz (z Q - x S)^2/((1 + z^2) W^2) at x=1.5 z=0.2 Q=-20 S=30 W=500\", "
+                "\"reference_df\": %.17g, \"central_difference\": %.17g}\n",
+                a, b, c, w, from_graph, direct, what_it_became, symbolic, (hp - hm)/(2.0*step));
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { std::cerr << "usage: see header of oracle/ref_driver.cpp" << std::endl; return 2; }
     const std::string mode = argv[1];
@@ -486,6 +520,8 @@ int main(int argc, char **argv) {
 #endif
     } else if (mode == "erfi" && argc == 5) {
         return erfi_values(argc, argv);
+    } else if (mode == "reducer") {
+        return reducer_defect();
     }
     std::cerr << "bad arguments; see header of oracle/ref_driver.cpp" << std::endl;
     return 2;

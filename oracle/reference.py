@@ -108,3 +108,9 @@ def erfi(x):
         _run(["erfi", arr.size, fin, fout])
         out = np.fromfile(fout).reshape(2, arr.size)
     return out[0], out[1]
+
+
+def reducer_defect():
+    """The four-variable reproduction of the reducer rule behind the reference's wrong cold-plasma
+    dD/dz (ref_driver reducer); tests/golden/ref_reducer_defect.json is its committed output."""
+    return json.loads(_run(["reducer"]).strip().splitlines()[-1])

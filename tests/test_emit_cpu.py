@@ -31,10 +31,13 @@ def emit_tool(lib):
     return EMIT
 
 
-def emit(tool, disp, eq, kind, tag, dt=None):
+def emit(tool, disp, eq, kind, tag, dt=None, true_derivatives=False):
     cu = os.path.join(BUILD, "emit_%s.cu" % tag)
     tab = os.path.join(BUILD, "emit_%s.tab" % tag)
     env = dict(os.environ)
+    env.pop("GFB_TRUE_DERIVATIVES", None)
+    if true_derivatives:
+        env["GFB_TRUE_DERIVATIVES"] = "1"       # dispersion::reference_defects() = false
     if dt is not None:
         env["GFB_DT"] = repr(float(dt))
     out = subprocess.run([tool, disp, eq, kind, cu, tab], check=True, capture_output=True, text=True, cwd=ROOT, env=env).stdout
@@ -62,8 +65,10 @@ RHS_CASES = [("ordinary_wave", "efit"), ("extra_ordinary_wave", "efit"), ("cold_
              ("cold_plasma", "slab"), ("cold_plasma", "slab_density"), ("ordinary_wave", "slab_density"),
              ("bohm_gross", "no_magnetic_field"), ("simple", "slab"), ("ordinary_wave", "vmec"), ("cold_plasma", "vmec")]
 #  cold_plasma in a field that depends on the coordinate: the reference's symbolic dD/dx_i is defective
-#  (tests/test_oracle.py::test_reference_dkz_defect); those components are not compared with it.
-REFERENCE_DEFECT = {("cold_plasma", "efit"): ("dkzdt",), ("cold_plasma", "vmec"): ("dkxdt", "dkydt", "dkzdt")}
+#  (tests/test_oracle.py::test_reference_dkz_defect).  For EFIT the defect has a closed form and is
+#  reproduced by default (dispersion::cold_plasma::reference_defect); for VMEC those components are
+#  not compared with the reference.
+REFERENCE_DEFECT = {("cold_plasma", "vmec"): ("dkxdt", "dkydt", "dkzdt")}
 
 
 @pytest.mark.parametrize("disp,eq", RHS_CASES)
@@ -83,15 +88,51 @@ def test_emitted_rhs_matches_reference(emit_tool, disp, eq):
         assert_rhs_close(out[i], g["rhs"][i], (disp, eq, k))
 
 
-TRACE_CASES = [("extra_ordinary_wave", "efit", "rk4"), ("ordinary_wave", "efit", "rk4"),
-               ("cold_plasma", "slab_density", "rk4"), ("cold_plasma", "slab", "rk2")]
+def test_emitted_rhs_true_derivatives_match_port(emit_tool):
+    """reference_defects() = false: cold plasma + EFIT with the true dD/dz, against the numpy
+    restatement (complex-step derivatives, independent of both symbolic differentiators)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import port
+    from graph_framework_b200.tools.gfbt import read_gfbt
+    g = golden("ref_rhs_cold_plasma_efit")
+    n = g["state"].shape[1]
+    tag = "rhs_cold_plasma_efit_true"
+    cu, tab, info = emit(emit_tool, "cold_plasma", "efit", "rhs", tag, true_derivatives=True)
+    out = run_harness(cu, tab, "rhs_kernel", g["state"], n, 1, 8, 7, tag)[8:]
+    eq = port.Efit(read_gfbt(os.path.join(ROOT, "tests", "golden", "efit.gfbt")))
+    with np.errstate(all="ignore"):
+        ref = port.rhs("cold_plasma", eq, dict(zip(port.ORDER, g["state"])), reference_defects=False)
+        quirk = port.rhs("cold_plasma", eq, dict(zip(port.ORDER, g["state"])))
+    for i, k in enumerate(("dxdt", "dydt", "dzdt", "dkxdt", "dkydt", "dkzdt", "D")):
+        assert_rhs_close(out[i], ref[k], ("cold_plasma", "efit", k, "true derivatives vs port"))
+    # the port's own restatement of the defect equals the reference's kernels
+    assert_rhs_close(quirk["dkzdt"], g["rhs"][5], "port with the reference's defect vs reference")
+    assert np.median(np.abs(ref["dkzdt"] - g["rhs"][5])/np.abs(g["rhs"][5])) > 0.1     # and the defect is not small
 
 
-@pytest.mark.parametrize("disp,eq,solver", TRACE_CASES)
-def test_emitted_runge_kutta_steps_match_reference(emit_tool, disp, eq, solver):
+#  (dispersion, equilibrium, solver, golden tag).  cold_plasma + EFIT: "efit_interior" starts inside the
+#  plasma; "efit" are the efit_example rays, which start at R = 2.5 in VACUUM where cold-plasma D is
+#  doubly degenerate (D ~ (1 - n^2)^2): there the reference's dkz/dt is its reducer defect times
+#  (n^2 - 1) ~ 3e-9, a difference of O(1) numbers known to ~1e-7 relative to ANY evaluation order, so
+#  kz of that case is held to 1e-6 per step and everything else to 1e-12.
+TRACE_CASES = [("extra_ordinary_wave", "efit", "rk4", "efit"), ("ordinary_wave", "efit", "rk4", "efit"),
+               ("cold_plasma", "efit", "rk4", "efit_interior"), ("cold_plasma", "efit", "rk4", "efit"),
+               ("cold_plasma", "slab_density", "rk4", "slab_density"), ("cold_plasma", "slab", "rk2", "slab")]
+ILL_CONDITIONED = {("cold_plasma", "efit"): {7: 1.0e-6}}
+#  The residual is D^2 at a Newton root, i.e. the square of D's rounding noise.  For cold plasma + EFIT
+#  that noise is ~1e-11 (psi ~ 0.3 is a sum of folded-spline terms up to 4e7, conftest.assert_rhs_close),
+#  so |D| is compared with that absolute floor; elsewhere the floor is 1e-14.
+RESIDUAL_FLOOR = {("cold_plasma", "efit"): 1.0e-10, ("cold_plasma", "efit_interior"): 1.0e-10}
+
+
+@pytest.mark.parametrize("disp,eq,solver,tag", TRACE_CASES)
+def test_emitted_runge_kutta_steps_match_reference(emit_tool, disp, eq, solver, tag):
     """Skeleton RK stage/step loops + emitted body, one step at a time from the reference's own
     pre-step states (1e-12) and 5 fused steps (1e-11)."""
-    g = golden("ref_trace_%s_%s_%s" % (disp, eq, solver))
+    golden_tag = tag
+    g = golden("ref_trace_%s_%s_%s" % (disp, tag, solver))
+    loose = ILL_CONDITIONED.get((disp, tag), {})
     rec = g["per_step"]
     n = rec.shape[2]
     tag = "rk_%s_%s_%s" % (disp, eq, solver)
@@ -101,23 +142,28 @@ def test_emitted_runge_kutta_steps_match_reference(emit_tool, disp, eq, solver):
         for i in range(9):
             ref = rec[step + 1][i]
             if i == 8:
-                assert np.max(np.abs(out[i] - ref)) <= 1.0e-12*np.max(np.abs(ref)) + 1.0e-28
+                d_got, d_ref = np.sqrt(out[i]), np.sqrt(ref)
+                assert np.max(np.abs(d_got - d_ref)) <= 1.0e-12*np.max(d_ref) + RESIDUAL_FLOOR.get((disp, golden_tag), 1.0e-14)
             else:
-                assert rel_dev(out[i], ref) < 1.0e-12, (step, i, rel_dev(out[i], ref))
+                assert rel_dev(out[i], ref) < loose.get(i, 1.0e-12), (step, i, rel_dev(out[i], ref))
     out = run_harness(cu, tab, "solver_kernel", rec[0][:8], n, rec.shape[0] - 1, 8, 1, tag)
     for i in range(8):
-        assert rel_dev(out[i], rec[-1][i]) < 1.0e-11, (i, rel_dev(out[i], rec[-1][i]))
+        assert rel_dev(out[i], rec[-1][i]) < 10.0*loose.get(i, 1.0e-12), (i, rel_dev(out[i], rec[-1][i]))
 
 
-@pytest.mark.parametrize("disp,eq", [("extra_ordinary_wave", "efit"), ("cold_plasma", "slab_density")])
-def test_emitted_newton_matches_reference(emit_tool, disp, eq):
+@pytest.mark.parametrize("disp,eq,tag", [("extra_ordinary_wave", "efit", "efit"), ("cold_plasma", "slab_density", "slab_density"),
+                                         ("cold_plasma", "efit", "efit_interior"), ("cold_plasma", "efit", "efit")])
+def test_emitted_newton_matches_reference(emit_tool, disp, eq, tag):
     """Device-resident per-ray Newton skeleton vs the reference's converged kx."""
-    g = golden("ref_trace_%s_%s_rk4" % (disp, eq))
+    g = golden("ref_trace_%s_%s_rk4" % (disp, tag))
     n = g["state"].shape[1]
-    tag = "newton_%s_%s" % (disp, eq)
-    cu, tab, info = emit(emit_tool, disp, eq, "newton", tag)
-    out = run_harness(cu, tab, "loss_kernel", g["state"], n, 1000, 8, 1, tag, scalar=1.0e-30)
-    assert rel_dev(out[5], g["per_step"][0][5]) < 1.0e-12
+    name = "newton_%s_%s" % (disp, eq)
+    cu, tab, info = emit(emit_tool, disp, eq, "newton", name)
+    out = run_harness(cu, tab, "loss_kernel", g["state"], n, 1000, 8, 1, name, scalar=1.0e-30)
+    print(disp, tag, "kx deviation", rel_dev(out[5], g["per_step"][0][5]), "max D^2", np.max(out[8]))
+    # cold plasma + EFIT: the root is only defined to |noise of D|/|dD/dkx| (a double root in vacuum)
+    tol = {("cold_plasma", "efit_interior"): 1.0e-10, ("cold_plasma", "efit"): 1.0e-7}.get((disp, tag), 1.0e-12)
+    assert rel_dev(out[5], g["per_step"][0][5]) < tol
     assert np.max(out[8]) < 1.0e-20          # D^2 at the last evaluated iterate
 
 

@@ -5,9 +5,12 @@ Golden vectors in tests/golden/ref_*.npz were produced by the UNMODIFIED referen
   * right-hand side and one step from identical pre-step state: 1e-12 relative (north star),
     with an absolute floor of 1e-9 x the ensemble scale for components that are ~0;
   * trajectories: stated per test.
-cold_plasma + EFIT: the reference's symbolic dD/dz is defective (tests/test_oracle.py documents it
-with the reference's own finite differences), so dkz/dt -- and anything downstream of it -- is
-compared with the independent numpy restatement (oracle/port.py) instead.
+cold_plasma + EFIT: the reference's symbolic dD/dz is defective (a reducer rule,
+tests/test_oracle.py::test_reference_reducer_defect_is_pinned).  Its effect has a closed form
+(dispersion::cold_plasma::reference_defect) and is reproduced by default, so this case is compared with
+the REFERENCE like every other; with the option reference_defects=0 the true derivative is used and
+compared with the independent numpy restatement (oracle/port.py).  For VMEC no closed form is known: there
+dk/dt of cold plasma is compared with the reference's own D through finite differences elsewhere.
 """
 import numpy as np
 import pytest
@@ -28,7 +31,7 @@ RHS_CASES = [("ordinary_wave", "efit"), ("extra_ordinary_wave", "efit"), ("cold_
              ("cold_plasma", "slab"), ("cold_plasma", "slab_density"), ("ordinary_wave", "slab_density"),
              ("bohm_gross", "no_magnetic_field"), ("simple", "slab"), ("cold_plasma", "gaussian_density"),
              ("ordinary_wave", "vmec"), ("cold_plasma", "vmec")]
-REFERENCE_DEFECT = {("cold_plasma", "efit"): ("dkzdt",), ("cold_plasma", "vmec"): ("dkxdt", "dkydt", "dkzdt")}
+REFERENCE_DEFECT = {("cold_plasma", "vmec"): ("dkxdt", "dkydt", "dkzdt")}
 
 
 @pytest.mark.parametrize("disp,eq", RHS_CASES)
@@ -48,31 +51,47 @@ def test_rhs_matches_reference(lib, disp, eq):
         assert_rhs_close(got[k], g["rhs"][i], (disp, eq, k))
 
 
-def test_rhs_cold_plasma_efit_dkz_matches_port(lib, efit_tables):
+@pytest.mark.parametrize("defects", [True, False])
+def test_rhs_cold_plasma_efit_matches_port_in_both_modes(lib, efit_tables, defects):
+    """reference_defects=1 (default): the reference's effective dD/dz; =0: the true derivative.  Both
+    against the numpy restatement, whose derivatives are complex-step."""
     from graph_framework_b200.rays import RayTracer
     from oracle import port
     g = golden("ref_rhs_cold_plasma_efit")
     state = unpack(g["state"])
-    tr = RayTracer("cold_plasma", "efit", state["w"].size, 1.0e-3)
+    tr = RayTracer("cold_plasma", "efit", state["w"].size, 1.0e-3, options="reference_defects=%d" % defects)
     tr.set_state(state)
     got = tr.rhs()
     tr.close()
-    ref = port.rhs("cold_plasma", port.Efit(efit_tables), state)
+    with np.errstate(all="ignore"):
+        ref = port.rhs("cold_plasma", port.Efit(efit_tables), state, reference_defects=defects)
     for k in RHS:
-        assert_rhs_close(got[k], ref[k], ("cold_plasma", "efit", k, "vs port"))
+        assert_rhs_close(got[k], ref[k], ("cold_plasma", "efit", k, "vs port", defects))
+    if not defects:
+        assert np.median(np.abs(got["dkzdt"] - g["rhs"][5])/np.abs(g["rhs"][5])) > 0.1
 
 
-TRACE_CASES = [("extra_ordinary_wave", "efit", "rk4"), ("ordinary_wave", "efit", "rk4"),
-               ("cold_plasma", "slab_density", "rk4"), ("ordinary_wave", "slab_density", "rk4"),
-               ("cold_plasma", "slab", "rk2"), ("simple", "slab", "rk4")]
+#  (dispersion, equilibrium, solver, golden tag).  cold_plasma + EFIT: "efit_interior" starts inside the
+#  plasma; "efit" are the efit_example rays, which start at R = 2.5 in VACUUM where cold-plasma D is doubly
+#  degenerate (D ~ (1 - n^2)^2): there the reference's dkz/dt is its reducer defect times (n^2 - 1) ~ 3e-9, a
+#  difference of O(1) numbers known to ~1e-7 relative to ANY evaluation order, so kz of that case is held
+#  to 1e-6 per step and everything else to 1e-12.
+TRACE_CASES = [("extra_ordinary_wave", "efit", "rk4", "efit"), ("ordinary_wave", "efit", "rk4", "efit"),
+               ("cold_plasma", "efit", "rk4", "efit_interior"), ("cold_plasma", "efit", "rk4", "efit"),
+               ("cold_plasma", "slab_density", "rk4", "slab_density"), ("ordinary_wave", "slab_density", "rk4", "slab_density"),
+               ("cold_plasma", "slab", "rk2", "slab"), ("simple", "slab", "rk4", "slab")]
+ILL_CONDITIONED = {("cold_plasma", "efit"): {"kz": 1.0e-6}}
+#  The residual is D^2 at a Newton root = the square of D's rounding noise; for cold plasma + EFIT that
+#  noise is ~1e-11 (folded spline coefficients up to 4e7, conftest.assert_rhs_close), elsewhere < 1e-14.
+RESIDUAL_FLOOR = {("cold_plasma", "efit"): 1.0e-10, ("cold_plasma", "efit_interior"): 1.0e-10}
 
 
-@pytest.mark.parametrize("disp,eq,solver", TRACE_CASES)
+@pytest.mark.parametrize("disp,eq,solver,tag", TRACE_CASES)
 @pytest.mark.parametrize("mode", ["per_ray", "ensemble"])
-def test_newton_init_matches_reference(lib, disp, eq, solver, mode):
+def test_newton_init_matches_reference(lib, disp, eq, solver, tag, mode):
     """dispersion_test.cpp:25-64 analogue: Newton solve for kx; compare the converged wavenumber."""
     from graph_framework_b200.rays import RayTracer
-    g = golden("ref_trace_%s_%s_%s" % (disp, eq, solver))
+    g = golden("ref_trace_%s_%s_%s" % (disp, tag, solver))
     state = unpack(g["state"])
     n = state["w"].size
     tr = RayTracer(disp, eq, n, float(g["dt"]), solver=solver)
@@ -81,16 +100,20 @@ def test_newton_init_matches_reference(lib, disp, eq, solver, mode):
     got = tr.get_state(residual=False)
     tr.close()
     ref = g["per_step"][0]
-    # Newton stops on a residual of 1e-30 in D^2: converged roots agree to ~1e-14 relative.
-    assert rel_dev(got["kx"], ref[5]) < 1.0e-12, rel_dev(got["kx"], ref[5])
+    # Newton stops on a residual of 1e-30 in D^2: converged roots agree to ~1e-14 relative.  Cold plasma +
+    # EFIT: D is flat near its root in vacuum (double root) and noisy inside (RESIDUAL_FLOOR): the root is
+    # defined to |D noise|/|dD/dkx|: observed 8e-12 inside the plasma, 7e-9 on the vacuum double root.
+    tol = {("cold_plasma", "efit_interior"): 1.0e-10, ("cold_plasma", "efit"): 1.0e-7}.get((disp, tag), 1.0e-12)
+    assert rel_dev(got["kx"], ref[5]) < tol, rel_dev(got["kx"], ref[5])
 
 
-@pytest.mark.parametrize("disp,eq,solver", TRACE_CASES)
-def test_one_step_from_identical_state(lib, disp, eq, solver):
+@pytest.mark.parametrize("disp,eq,solver,tag", TRACE_CASES)
+def test_one_step_from_identical_state(lib, disp, eq, solver, tag):
     """Per-step parity: copy the reference's pre-step state to the device, one step, compare
     all outputs and the residual (D^2 at the pre-step state, solver.hpp:316-319)."""
     from graph_framework_b200.rays import RayTracer
-    g = golden("ref_trace_%s_%s_%s" % (disp, eq, solver))
+    g = golden("ref_trace_%s_%s_%s" % (disp, tag, solver))
+    loose = ILL_CONDITIONED.get((disp, tag), {})
     rec = g["per_step"]
     n = rec.shape[2]
     tr = RayTracer(disp, eq, n, float(g["dt"]), solver=solver)
@@ -102,19 +125,22 @@ def test_one_step_from_identical_state(lib, disp, eq, solver):
         tr.step(1)
         got = tr.get_state()
         for i, k in enumerate(ORDER):
-            assert rel_dev(got[k], rec[step + 1][i]) < 1.0e-12, (step, k, rel_dev(got[k], rec[step + 1][i]))
-        res_ref = rec[step + 1][8]
-        assert np.max(np.abs(got["residual"] - res_ref)) <= 1.0e-12*max(np.max(np.abs(res_ref)), 1.0e-300) + 1.0e-28
+            assert rel_dev(got[k], rec[step + 1][i]) < loose.get(k, 1.0e-12), (step, k, rel_dev(got[k], rec[step + 1][i]))
+        d_ref = np.sqrt(rec[step + 1][8])
+        assert np.max(np.abs(np.sqrt(got["residual"]) - d_ref)) <= 1.0e-12*np.max(d_ref) + RESIDUAL_FLOOR.get((disp, tag), 1.0e-14)
     tr.close()
 
 
-@pytest.mark.parametrize("disp,eq,solver", TRACE_CASES)
+@pytest.mark.parametrize("disp,eq,solver,tag", TRACE_CASES)
 @pytest.mark.parametrize("graph_stages", [False, True])
-def test_trajectory_matches_reference(lib, disp, eq, solver, graph_stages):
+def test_trajectory_matches_reference(lib, disp, eq, solver, tag, graph_stages):
     """200 fused steps (two launches of 100) from the reference's post-Newton state; stated
-    end-of-trajectory tolerance 1e-9 relative (observed ~1e-12; errors grow along the ray)."""
+    end-of-trajectory tolerance 1e-9 relative (observed ~1e-12; errors grow along the ray).  The vacuum-start
+    cold-plasma case is ill-conditioned in kz step after step (ILL_CONDITIONED) and is left to the per-step test."""
     from graph_framework_b200.rays import RayTracer
-    g = golden("ref_trace_%s_%s_%s" % (disp, eq, solver))
+    if (disp, tag) in ILL_CONDITIONED:
+        pytest.skip("kz of the reference itself is rounding-dominated along this trajectory; per-step test covers it")
+    g = golden("ref_trace_%s_%s_%s" % (disp, tag, solver))
     rec = g["long"]
     n = rec.shape[2]
     tr = RayTracer(disp, eq, n, float(g["dt"]), solver=solver + ("_graph" if graph_stages else ""))
@@ -173,21 +199,25 @@ def test_xrays_bench_case(lib):
         assert rel_dev(got[k], rec[-1][i]) < 1.0e-9, (k, rel_dev(got[k], rec[-1][i]))
 
 
-def test_cold_plasma_efit_trajectory_matches_port(lib, efit_tables):
+@pytest.mark.parametrize("defects", [True, False])
+def test_cold_plasma_efit_trajectory_matches_port(lib, efit_tables, defects):
+    """20 steps inside the plasma in both derivative modes against the numpy restatement (the default
+    mode is also held to the reference itself by the TRACE_CASES tests above)."""
     from graph_framework_b200.rays import RayTracer
     from oracle import port
-    g = golden("ref_trace_cold_plasma_efit_rk4")
+    g = golden("ref_trace_cold_plasma_efit_interior_rk4")
     start = unpack(g["per_step"][0][:8])
     n = start["w"].size
     dt = float(g["dt"])
-    tr = RayTracer("cold_plasma", "efit", n, dt)
+    tr = RayTracer("cold_plasma", "efit", n, dt, options="reference_defects=%d" % defects)
     tr.set_state(start)
     tr.init("")
     tr.compile()
     tr.step(20)
     got = tr.get_state()
     tr.close()
-    ref, res = port.trace("cold_plasma", port.Efit(efit_tables), start, dt, 20)
+    with np.errstate(all="ignore"):
+        ref, res = port.trace("cold_plasma", port.Efit(efit_tables), start, dt, 20, reference_defects=defects)
     for k in ORDER:
         assert rel_dev(got[k], ref[k]) < 1.0e-10, (k, rel_dev(got[k], ref[k]))
 

@@ -121,9 +121,48 @@ def test_reference_dkz_defect(efit):
     assert np.max(np.abs(ref_dkx[inside] - fd_dkx[inside])/np.abs(fd_dkx[inside])) < 1.0e-4
     assert np.median(np.abs(ref_dkz[inside] - fd_dkz[inside])/np.abs(fd_dkz[inside])) > 1.0       # the defect
     with np.errstate(all="ignore"):
-        mine = port.rhs("cold_plasma", efit, unpack(g["state"]))
+        mine = port.rhs("cold_plasma", efit, unpack(g["state"]), reference_defects=False)
     assert np.max(np.abs(mine["dkzdt"][inside] - fd_dkz[inside])/np.maximum(np.abs(fd_dkz[inside]), 1e-3*np.max(np.abs(fd_dkz)))) < 1.0e-3
     assert np.max(rel_devs(mine["dkxdt"], ref_dkx)) < 1.0e-6
+
+
+def test_reference_reducer_defect_is_pinned(efit):
+    """Root cause of the dkz defect, localised: the reference's reducer turns ((A W)^2 B)/(C^2 W^4)
+    into A^2 B/C^4 (fixture written by `ref_driver reducer`; re-run here when oracle/_ref exists).
+    The port's closed form for what that does to cold_plasma + EFIT (cold_plasma_reference_defect)
+    reproduces the reference's own dkz/dt on 80 states."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from oracle import port, reference
+    with open(os.path.join(GOLDEN, "ref_reducer_defect.json")) as f:
+        fix = json.load(f)
+    runs = [fix] + ([reference.reducer_defect()] if reference.available() else [])
+    for r in runs:
+        assert abs(r["reference_graph"] - r["a2b_over_c4"]) < 1.0e-15*abs(r["a2b_over_c4"])       # what it became
+        assert abs(r["reference_graph"]/r["direct"]) > 1.0e4                                        # not what it is
+        assert abs(r["reference_df"]/r["central_difference"]) > 1.0e4
+    for name in ("ref_rhs_cold_plasma_efit", "ref_defect_cold_plasma_efit"):
+        g = golden(name)
+        with np.errstate(all="ignore"):
+            mine = port.rhs("cold_plasma", efit, unpack(g["state"]))
+            true = port.rhs("cold_plasma", efit, unpack(g["state"]), reference_defects=False)
+        d = rel_devs(mine["dkzdt"], g["rhs"][5])
+        assert np.median(d) < 1.0e-13 and np.max(d) < 1.0e-8, (name, np.median(d), np.max(d))
+        assert np.median(rel_devs(true["dkzdt"], g["rhs"][5])) > 0.1
+
+
+def test_port_steps_cold_plasma_like_the_reference(efit):
+    """With the defect restated, the port follows the reference's cold-plasma + EFIT trajectory inside the
+    plasma step by step (1e-12), which nothing could before."""
+    from oracle import port
+    g = golden("ref_trace_cold_plasma_efit_interior_rk4")
+    rec = g["per_step"]
+    with np.errstate(all="ignore"):
+        for step in range(rec.shape[0] - 1):
+            out, res = port.rk4_step("cold_plasma", efit, unpack(rec[step][:8]), float(g["dt"]))
+            for i, k in enumerate(port.ORDER):
+                assert rel_dev(out[k], rec[step + 1][i]) < 1.0e-12, (step, k)
 
 
 def test_port_deposit_matches_numpy_histogram():
