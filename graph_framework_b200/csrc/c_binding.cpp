@@ -15,6 +15,17 @@
 
 using graph::leaf_ptr;
 
+//  The node caches of the front end are per thread and keep every interned node -- and through
+//  the variable nodes the n-double host copies of the ray arrays -- alive.  Handles are counted per
+//  thread; when the last one created on a thread is destroyed there, the caches are dropped.
+namespace {
+thread_local long live_handles = 0;
+void handle_created() { live_handles++; }
+void handle_destroyed() {
+    if (live_handles > 0 && --live_handles == 0) graph::clear_caches();
+}
+}
+
 //******************************************************************************
 //  graph_c_binding
 //******************************************************************************
@@ -65,9 +76,14 @@ graph_c_context *graph_construct_context(const enum graph_type type, const bool 
     auto c = new c_context;
     c->type = type;
     c->safe_math = use_safe_math;
+    handle_created();
     return c;
 }
-void graph_destroy_context(graph_c_context *c) { delete cast(c); }
+void graph_destroy_context(graph_c_context *c) {
+    if (!c) return;
+    delete cast(c);
+    handle_destroyed();
+}
 
 graph_node graph_variable(graph_c_context *c, const size_t size, const char *symbol) {
     return cast(c)->keep(graph::variable(size, symbol));
@@ -401,9 +417,14 @@ gfb_rays *gfb_rays_create(const char *dispersion_name, const char *equilibrium_n
 //  Tabulated equilibria: the solver keeps rays sorted by table cell while stepping (binning.hpp);
 //  options: bin_rays=0 off, bin_rays=<steps> how often the order is checked.
     if (o.bin_rays >= 0) t->set_ray_order(o.bin_rays != 0, o.bin_rays > 0 ? static_cast<size_t> (o.bin_rays) : 0);
+    handle_created();
     return r.release();
 }
-void gfb_rays_destroy(gfb_rays *r) { delete r; }
+void gfb_rays_destroy(gfb_rays *r) {
+    if (!r) return;
+    delete r;
+    handle_destroyed();
+}
 
 int gfb_rays_set_state(gfb_rays *r, const double *const state[GFB_NUM_STATE]) {
     for (int i = 0; i < GFB_NUM_STATE; i++) {
@@ -693,9 +714,14 @@ gfb_boris *gfb_boris_create(const char *equilibrium_name, const char *table_file
 //  cell while stepping (options: bin_rays=0 off, bin_rays=<steps> how often the order is checked).
     if (o.bin_rays != 0) b->grid = eq->get_cell_grid();
     if (o.bin_rays > 0) b->order_period = static_cast<size_t> (o.bin_rays);
+    handle_created();
     return b.release();
 }
-void gfb_boris_destroy(gfb_boris *b) { delete b; }
+void gfb_boris_destroy(gfb_boris *b) {
+    if (!b) return;
+    delete b;
+    handle_destroyed();
+}
 int gfb_boris_set_binning(gfb_boris *b, const double *lo, const double *hi, const unsigned *cells, size_t rebin_every) {
     b->order.disable();
     b->grid = equilibrium::cell_grid();
@@ -712,6 +738,13 @@ int gfb_boris_set_binning(gfb_boris *b, const double *lo, const double *hi, cons
     return 0;
 }
 int gfb_boris_set_state(gfb_boris *b, const double *const state[6]) {
+//  After compile every call re-runs initialize_gamma (u <- gamma u), so the momenta must all be the
+//  caller's physical u/c again: a partial update would scale the untouched components twice.
+    if (b->compiled) {
+        for (int i = 0; i < 6; i++) {
+            if (!state[i]) return rays_fail("gfb_boris_set_state: after compile all six arrays x, y, z, ux, uy, uz are required");
+        }
+    }
     b->order.restore();
     for (int i = 0; i < 6; i++) {
         if (!state[i]) continue;

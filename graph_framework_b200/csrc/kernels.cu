@@ -19,18 +19,20 @@ __device__ __forceinline__ unsigned long long ordered(const double d) {
 
 __global__ void __launch_bounds__(256) max_kernel(const double *__restrict__ in, const unsigned long long n,
                                                   unsigned long long *__restrict__ result) {
-    double m = -1.7976931348623157e308;
-    bool any_nan = false;
+//  NaN elements are ignored, like the reference's max() (CUDA max = fmax, cuda_context.hpp:973-985):
+//  one bad ray must not end a convergence loop for all the others (workflow.hpp:179-205).  Key 0 =
+//  "no number seen" (all NaN, or n == 0) and decodes to NaN.
+    double m = __longlong_as_double(0xfff0000000000000ll);        // -inf
+    bool seen = false;
     for (unsigned long long i = static_cast<unsigned long long> (blockIdx.x)*blockDim.x + threadIdx.x; i < n;
          i += static_cast<unsigned long long> (gridDim.x)*blockDim.x) {
         const double v = __ldg(in + i);
-        any_nan = any_nan || (v != v);
-        m = fmax(m, v);
+        if (v == v) {
+            m = fmax(m, v);
+            seen = true;
+        }
     }
-    if (any_nan) {
-        m = __longlong_as_double(0x7ff8000000000000ll);
-    }
-    unsigned long long key = any_nan ? 0xffffffffffffffffull : ordered(m);
+    unsigned long long key = seen ? ordered(m) : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long other = __shfl_down_sync(0xffffffffu, key, o);
@@ -239,7 +241,7 @@ int gfb_k_max(const double *in, unsigned long long n, unsigned long long *result
     return static_cast<int> (cudaGetLastError());
 }
 double gfb_k_unorder(unsigned long long key) {
-    if (key == 0xffffffffffffffffull) {
+    if (key == 0ull) {                      // nothing but NaN (or nothing at all)
         const unsigned long long nan_bits = 0x7ff8000000000000ull;
         double d;
         __builtin_memcpy(&d, &nan_bits, 8);

@@ -643,6 +643,15 @@ int gfb_kernel_run_from_host(gfb_kernel *k, unsigned steps, int num_ray_slots,
         per = (per + wave - 1)/wave*wave;
         for (unsigned long long off = 0; off < total; off += per) pieces.push_back({off, std::min(per, total - off)});
     }
+//  The uploads overwrite arrays that work already queued on the compute stream may still read or
+//  write (an earlier step, the scatter that restores the caller's ray order): order them after it.
+    {
+        cudaEvent_t quiet;
+        cudaEventCreateWithFlags(&quiet, cudaEventDisableTiming);
+        cudaEventRecord(quiet, c->stream);
+        cudaStreamWaitEvent(c->upload_stream, quiet, 0);
+        cudaEventDestroy(quiet);
+    }
     std::vector<cudaEvent_t> uploaded, computed;
     int rc = 0;
     for (size_t piece_index = 0; piece_index < pieces.size() && !rc; piece_index++) {

@@ -15,7 +15,8 @@ hold kamp (imaginary part), power and d_power, and bins.gfbt holds bins = sum(d_
 the bin edges xbins/ybins/zbins (bin.py:20-33, 106; options --num_x --min_x --max_x ... as bin.py).
 Differences: the random stream is numpy's (seeded with the shard index; the reference uses
 std::mt19937_64), equilibrium files are GFBT (tools/gfbt.py converts netCDF), results are
-result<shard>.gfbt with one (time, num_rays) variable per quantity; the root_find absorption model
+result<shard>.gfbt with one (time, num_rays) variable per quantity, num_times/sub_steps + 1 records of
+which record 0 is the initial state, as in the reference's files; the root_find absorption model
 (complex root search) is not part of this back end.
 """
 import argparse
@@ -99,16 +100,22 @@ def trace_shard(args, shard, n, device, report):
     t1 = time.perf_counter()
     blocks = max(args.num_times//args.sub_steps, 1)
     profile = None
+#  Record 0 is the state before the first step (xrays.cpp:246-258 writes num_steps + 1 records and the
+#  power stage takes record 0 as X_last): residual 0, kamp 0, power 1, d_power 0.
+    start = tr.get_state(residual=False)
+    first = [start[k] for k in STATE] + [np.zeros(n)]
     if absorb:
         bins = (args.num_x, args.num_y, args.num_z)
         records, absorbed, profile = tr.trace_absorb(blocks, args.sub_steps, bins=bins,
                                                      lo=(args.min_x, args.min_y, args.min_z),
                                                      hi=(args.max_x, args.max_y, args.max_z))
         records = np.concatenate([records, absorbed], axis=1)
+        first += [np.zeros(n), np.ones(n), np.zeros(n)]
         names = ("t", "w", "x", "y", "z", "kx", "ky", "kz", "residual", "kamp", "power", "d_power")
     else:
         records = tr.trace(blocks, args.sub_steps)
         names = ("t", "w", "x", "y", "z", "kx", "ky", "kz", "residual")
+    records = np.concatenate([np.stack(first)[None], records], axis=0)
     t2 = time.perf_counter()
     write_trajectory("%s%d.gfbt" % (args.output, shard), records, names)
     tr.close()

@@ -105,7 +105,9 @@ int gfb_set_max_fused_steps(gfb_ctx *ctx, unsigned steps);
 int gfb_flush(gfb_ctx *ctx);
 
 /* cuda_context::create_max_call  (cuda_context.hpp:540-576) + create_reduction (:954-995):
- * maximum of n doubles of a buffer, returned to the host. */
+ * maximum of n doubles of a buffer, returned to the host.  NaN elements are IGNORED, as by the
+ * reference's max() (= fmax): a convergence loop on this value keeps iterating for the good rays.
+ * The result is NaN only when every element is NaN or n == 0. */
 int gfb_max(gfb_ctx *ctx, uint64_t key, size_t n, double *result);
 /* cuda_context::wait  (cuda_context.hpp:581-584). */
 int gfb_wait(gfb_ctx *ctx);

@@ -108,6 +108,31 @@ def vmec_trace_case(disp="ordinary_wave"):
     save("ref_trace_%s_vmec_rk4" % disp, state=workloads.pack(s), dt=np.array(dt), per_step=rec)
 
 
+def vmec_fd_case():
+    """cold_plasma + VMEC: the reference's symbolic dk/dt is defective on all three components (the
+    same reducer rule as for EFIT, no closed form known here), so this back end's dk/dt is pinned to the
+    reference's OWN D instead: D at the base states and at +-h, +-2h along s, u, v and w (4th-order central
+    differences), all in ONE reference run (the VMEC graph build dominates its cost)."""
+    n, h = 16, 1.0e-5
+    s = workloads.vmec_states(n, seed=8)
+    batch = {k: [np.asarray(s[k], dtype=np.float64)] for k in workloads.ORDER}
+    order = []
+    for var in ("x", "y", "z", "w"):
+        for mult in (-2.0, -1.0, 1.0, 2.0):
+            order.append((var, mult))
+            for k in workloads.ORDER:
+                batch[k].append(s[k] + (mult*h if k == var else 0.0))
+    stacked = {k: np.concatenate(v) for k, v in batch.items()}
+    out = reference.rhs("cold_plasma", "vmec", stacked)
+    D = out[6].reshape(len(order) + 1, n)
+    fd = {}
+    for j, var in enumerate(("x", "y", "z", "w")):
+        m2, m1, p1, p2 = (D[1 + 4*j + i] for i in range(4))
+        fd[var] = (m2 - 8.0*m1 + 8.0*p1 - p2)/(12.0*h)
+    save("ref_fd_cold_plasma_vmec", state=workloads.pack(s), h=np.array(h), D=D[0], rhs=out[:, :n],
+         dDdx=fd["x"], dDdy=fd["y"], dDdz=fd["z"], dDdw=fd["w"])
+
+
 def defect_case():
     """Evidence for the reference's symbolic dD/dz defect (cold_plasma in a z-dependent field):
     its own D at z +- h and w +- h next to its own symbolic dkz/dt."""
@@ -160,6 +185,8 @@ if __name__ == "__main__":
         vmec_case()
     if "absorb" in which:
         absorb_case()
+    if "vmec_fd" in which:
+        vmec_fd_case()
     if "vmec_trace" in which:
         vmec_trace_case("ordinary_wave")
     if "vmec_trace_cold" in which:

@@ -104,7 +104,8 @@ def test_xrays_driver_with_absorption(lib, tmp_path):
                      "--num_z=1", "--min_z=-1", "--max_z=1", "--output=" + prefix])
     assert rc == 0
     out = read_gfbt(prefix + "0.gfbt")
-    assert out["power"].shape == (30, 2000) and out["d_power"].shape == (30, 2000) and out["kamp"].shape == (30, 2000)
+    assert out["power"].shape == (31, 2000) and out["d_power"].shape == (31, 2000) and out["kamp"].shape == (31, 2000)
+    assert np.all(out["power"][0] == 1.0) and np.all(out["d_power"][0] == 0.0)       # record 0: before the first step
     binned = read_gfbt(str(tmp_path / "bins.gfbt"))
     assert binned["bins"].shape == (16, 1, 1) and binned["xbins"].shape == (17,)
     assert abs(binned["bins"].sum()*2000 - out["d_power"].sum()) < 1.0e-6*out["d_power"].sum()

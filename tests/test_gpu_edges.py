@@ -139,8 +139,9 @@ def test_xrays_driver_efit_example(lib, tmp_path):
                      "--use_cyl_xy", "--seed", "--devices=1", "--output=" + prefix])
     assert rc == 0
     out = read_gfbt(prefix + "0.gfbt")
-    assert out["x"].shape == (10, 5000)
-    assert np.allclose(out["t"][:, 0], 2.0e-5*100*np.arange(1, 11), rtol=1e-12)
+    assert out["x"].shape == (11, 5000)                     # num_times/sub_steps + 1: record 0 is the initial state (xrays.cpp:246-258)
+    assert np.allclose(out["t"][:, 0], 2.0e-5*100*np.arange(0, 11), rtol=1e-12)
+    assert np.allclose(np.sqrt(out["x"][0]**2 + out["y"][0]**2), 2.5, rtol=1e-14) and np.all(out["residual"][0] == 0.0)
     assert np.isfinite(out["kx"]).all() and np.max(out["residual"][-1]) < 1.0e-18
     r = np.sqrt(out["x"]**2 + out["y"]**2)
     assert np.all(r[-1] < r[0])                    # launched inward from R = 2.5
