@@ -254,7 +254,7 @@ namespace dispersion {
 ///  What the reference's symbolic dD/d(axis) contains on top of the true derivative.
 ///
 ///  The reference's expression reducer rewrites ((a b)^2 c)/(d^2 b^4) as a^2 c/d^4 (it should be
-///  a^2 c/(d^2 b^2); four variables reproduce it, oracle/ref_driver.cpp `reducer`).  n_par^2 and
+///  a^2 c/(d^2 b^2); four plain variables reproduce it).  n_par^2 and
 ///  n_perp^2 are N^2/(B.B w^2); in the quotient rule of their derivative along a coordinate on which
 ///  B.B depends through a common factor s (the 1/R of the EFIT field components, coordinate z), the
 ///  term -n^2 d(B.B)/(B.B) comes out multiplied by w^2/((B.B)^2 s).  The faulty form survives in the
