@@ -1,21 +1,30 @@
 #!/usr/bin/env python3
-"""Headline benchmark: FP64 RK4 ray-steps/s of the EFIT ray step on B200.
+"""Headline benchmark: FP64 RK4 ray-steps/s of the EFIT ray step on B200, with every BASELINE.json
+configuration timed briefly beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ...]
+                    [--scaling weak|strong] [--no-extras]
 
-One bench "step" = one block of SUB_STEPS (100, the reference's sub_steps between outputs,
-graph_driver/efit_example.sh) RK4 steps over every ray: one fused launch of the hot-path kernel.
+One bench "step" = one output block: SUB_STEPS (100, the reference's sub_steps between outputs,
+graph_driver/efit_example.sh) RK4 steps over every ray = one fused launch of the hot-path kernel.
 `value` is ray-steps/s with the ensemble resident in HBM, timed with CUDA events on the launching
-stream (max over ranks).  `e2e` is the same quantity through the public API with host buffers:
-every step uploads the 8 state arrays from pinned host memory, runs the block and reads state +
-residual back.  Rays are sharded over ranks with no data-path collective (weak scaling: the
-per-GPU ensemble is fixed).
+stream (max over ranks).  `e2e` is the same quantity through the public API with host buffers: every
+step uploads the state arrays from pinned host memory, runs the block and reads the result back.
+Rays are sharded over ranks with no data-path collective; the one collective of the path -- the sum
+of the binned power-deposition profile, BASELINE configs[2] -- is in workload `efit_absorb`.
+
+The headline workload (default efit_xmode = BASELINE configs[1]) fills the top-level keys; unless
+--no-extras is given the other configurations are timed for 3 steps each into extra.workloads:
+efit_cold (the north-star roofline kernel), efit_absorb (configs[2]), vmec_omode (configs[3]) and
+boris (configs[4]).  --scaling strong shards the BASELINE totals (10^6 / 10^7 / 10^8) over the ranks.
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref/ref_driver: the
 unmodified reference graph/solver code, kernels compiled by g++ -O3 -ffast-math) on all host
 threads on a bounded sample of the same workload.
 """
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -27,21 +36,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SUB_STEPS = 100
-#  From the committed ncu --set full captures of exactly this command (profiles/r1_ncu_*.txt):
-#  DRAM bytes read + written per launch, and the share of cycles the FP64 pipe was busy.
-NCU = {
-    "efit_xmode": {"traffic": 64113152 + 16543488, "fp64_pipe_active_pct": 75.6, "source": "profiles/r1_ncu_efit_xmode_solver_kernel.txt"},
-    "efit_cold": {"traffic": 64047360 + 9921792, "fp64_pipe_active_pct": 73.9, "source": "profiles/r1_ncu_efit_cold_solver_kernel.txt"},
-}
 WORKLOADS = {
-    # name: (dispersion, equilibrium, default rays per GPU, dt)
-    "efit_xmode": ("extra_ordinary_wave", "efit", 1000000, 2.0e-5),     # BASELINE configs[1]
-    "efit_cold": ("cold_plasma", "efit", 1000000, 2.0e-5),              # north-star roofline kernel
-    "efit_omode": ("ordinary_wave", "efit", 1000000, 2.0e-5),
-    "slab_omode": ("ordinary_wave", "slab_density", 1000000, 1.0e-3),   # analytic variant of configs[0]
-    "vmec_omode": ("ordinary_wave", "vmec", 1250000, 1.0e-4),           # configs[3]: 10^7 rays / 8 GPUs
-    "vmec_cold": ("cold_plasma", "vmec", 1250000, 1.0e-4),
+    # name: (dispersion, equilibrium, rays per GPU (weak), dt, BASELINE total (strong))
+    "efit_xmode": ("extra_ordinary_wave", "efit", 1000000, 2.0e-5, 1000000),    # BASELINE configs[1]
+    "efit_cold": ("cold_plasma", "efit", 1000000, 2.0e-5, 1000000),             # north-star roofline kernel
+    "efit_omode": ("ordinary_wave", "efit", 1000000, 2.0e-5, 1000000),
+    "slab_omode": ("ordinary_wave", "slab_density", 1000000, 1.0e-3, 10000),    # analytic variant of configs[0]
+    "vmec_omode": ("ordinary_wave", "vmec", 1250000, 1.0e-4, 10000000),         # configs[3]: 10^7 rays / 8 GPUs
+    "vmec_cold": ("cold_plasma", "vmec", 1250000, 1.0e-4, 10000000),
 }
+#  configs[2]: O-mode rays that cross the electron-cyclotron resonance within the timed blocks (dt 5e-4:
+#  0.05 of travel per block, resonance 0.44 from the launch point), device Newton, weak damping + power +
+#  deposition on a 64 x 64 x 128 grid over the EFIT box, one FP64 all-reduce of the profile per block.
+ABSORB = {"dispersion": "ordinary_wave", "equilibrium": "efit", "rays": 1000000, "dt": 5.0e-4, "total": 1000000,
+          "bins": (64, 64, 128), "lo": (0.84, -1.7, -1.6), "hi": (2.54, 1.7, 1.6)}
+BORIS = {"particles": 20000000, "total": 100000000, "dt": 0.5}                  # configs[4]
+EXTRAS = ("efit_cold", "efit_absorb", "vmec_omode", "boris")
+EXTRA_STEPS, EXTRA_WARMUP = 3, 3
 
 
 def generator(eq):
@@ -76,6 +87,7 @@ class ClockSampler:
             self.thread.start()
         except OSError:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -111,16 +123,546 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ---------------------------------------------------------------------------------------------
+#  Roofline bookkeeping
+# ---------------------------------------------------------------------------------------------
+def kernel_text_sha(ctx):
+    """sha256 of the CUDA text NVRTC compiled for this context (skeleton + emitted bodies): what a
+    committed ncu capture must have been taken from for its counters to describe this binary."""
+    from graph_framework_b200 import _lib
+    return hashlib.sha256(_lib.lib.gfb_source(ctx)).hexdigest()
+
+
+def ncu_capture(workload, sha):
+    """The committed ncu --set full capture of this workload's kernel (profiles/r*_ncu_<workload>.json,
+    written on the GPU box by tools/capture_ncu.sh): newest round first.  `stale` = the kernel text
+    benchmarked now is not the text the capture was taken from."""
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_%s.json" % workload)), reverse=True)
+    for path in found:
+        try:
+            with open(path) as f:
+                cap = json.load(f)
+        except (OSError, ValueError):
+            continue
+        cap["file"] = os.path.relpath(path, ROOT)
+        cap["stale"] = cap.get("kernel_text_sha256") != sha
+        return cap
+    return None
+
+
+def fp64_roofline(workload, ctx, units_per_launch, unit_steps, launch_ms, algorithmic_flop, peaks, bytes_per_launch):
+    """units_per_launch: rays (particles) one launch advances; unit_steps: steps per launch.
+    frac = EXECUTED FP64 flops / peak (<= 1 by construction): executed = (2 DFMA + DADD + DMUL thread
+    instructions) per unit-step from the committed ncu capture of the same kernel text x the measured rate.
+    work_rate_vs_reference_flops = the reference kernel's flop count per unit-step (BASELINE.md section 2,
+    SURVEY.md 8d) x the measured rate / peak: how fast the REFERENCE's arithmetic is being retired; it
+    exceeds frac (and may exceed 1) because this back end executes fewer flops for the same step."""
+    rate = units_per_launch*unit_steps/(launch_ms*1.0e-3)           # unit-steps per second on this GPU
+    peak = peaks["nominal_tflops"]
+    sha = kernel_text_sha(ctx)
+    cap = ncu_capture(workload, sha)
+    out = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak,
+           "peak_source": "FP64 pipe: %d SMs x 64 lanes x 2 x %.3f GHz (device attributes); MEASURED_PEAKS.json has no FP64 figure. "
+                          "The live DFMA probe (gfb_measure_fp64_peak) reads %.2f with the FP64 pipe %s busy under ncu, i.e. the same pipe peak"
+                          % (peaks["sms"], peaks["clock_ghz"], peaks["probe_tflops"],
+                             "92.0 % (profiles/r2_ncu_fp64_peak.json)"),
+           "probe_tflops": peaks["probe_tflops"],
+           "algorithmic_flop_per_unit_step": algorithmic_flop,
+           "algorithmic_tflops_reference_count": algorithmic_flop*rate/1.0e12 if algorithmic_flop else None,
+           "work_rate_vs_reference_flops": algorithmic_flop*rate/1.0e12/peak if algorithmic_flop else None,
+           "kernel_text_sha256": sha,
+           "hbm": {"algorithmic_bytes_per_launch": bytes_per_launch,
+                   "achieved_gbs": bytes_per_launch/(launch_ms*1.0e-3)/1.0e9, "peak_gbs": peaks.get("hbm_gbs")}}
+    if cap and cap.get("fp64_flop_per_unit_step"):
+        executed = cap["fp64_flop_per_unit_step"]
+        out.update({"achieved": executed*rate/1.0e12, "frac": executed*rate/1.0e12/peak,
+                    "executed_flop_per_unit_step": executed,
+                    "fp64_instructions_per_unit_step": cap.get("fp64_inst_per_unit_step"),
+                    "fp64_pipe_active_pct_ncu": cap.get("fp64_pipe_active_pct"),
+                    "traffic": cap.get("dram_bytes_per_launch"),
+                    "ncu": {"file": cap["file"], "captured_at_git_sha": cap.get("git_sha"), "stale": cap["stale"],
+                            "units_per_launch": cap.get("units_per_launch"), "unit_steps": cap.get("unit_steps")}})
+    else:
+        out.update({"achieved": out["algorithmic_tflops_reference_count"], "frac": None, "traffic": None,
+                    "ncu": None, "note": "no committed ncu capture for this workload: achieved is the reference-count work rate"})
+    return out
+
+
+def device_peaks(tracer_like):
+    """Nominal FP64 pipe peak from the device attributes + the live DFMA probe + MEASURED_PEAKS.json."""
+    import torch
+    props = torch.cuda.get_device_properties(torch.cuda.current_device())
+    clock_khz = getattr(props, "clock_rate", None)
+    if not clock_khz:
+        clock_khz = 1965000
+    sms = props.multi_processor_count
+    peaks = {"sms": sms, "clock_ghz": clock_khz/1.0e6, "nominal_tflops": sms*64*2*clock_khz*1.0e3/1.0e12,
+             "probe_tflops": tracer_like.fp64_peak()}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks["hbm_gbs"] = json.load(f).get("hbm_gbs")
+    except (OSError, ValueError):
+        peaks["hbm_gbs"] = None
+    return peaks
+
+
+class Ranks:
+    """RANK / WORLD_SIZE plumbing and the max-over-ranks reduction of a device time."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dist = None
+
+    def init(self):
+        import torch
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        import torch
+        if self.dist:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, value):
+        if not self.dist:
+            return value
+        import torch
+        t = torch.tensor([value], dtype=torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def finish(self):
+        if self.dist:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def shard(total, ranks):
+    from graph_framework_b200 import parallel
+    return parallel.my_shard(total, ranks.rank, ranks.world)[1]
+
+
+# ---------------------------------------------------------------------------------------------
+#  Ray workloads (EFIT / VMEC / slab step kernels)
+# ---------------------------------------------------------------------------------------------
+def run_rays(name, args, ranks, steps, warmup, with_e2e=True, cpu_baseline=True, rays_override=0):
+    import numpy as np
+    import torch
+    from graph_framework_b200 import workloads, _lib
+    from graph_framework_b200.rays import RayTracer, STATE
+
+    disp, eq, per_gpu, dt, total = WORKLOADS[name]
+    strong = args.scaling == "strong"
+    if rays_override:
+        rays = rays_override
+    elif strong:
+        rays = shard(total, ranks)
+    else:
+        rays = per_gpu
+    gen = generator(eq)
+    state0 = gen(rays, seed=ranks.rank)
+
+    t_setup = time.perf_counter()
+    tracer = RayTracer(disp, eq, rays, dt, solver="rk4", device=ranks.local_rank,
+                       options=("fused_steps=%d " % SUB_STEPS) + args.options)
+    tracer.set_state(state0)
+    t_init = time.perf_counter()
+    tracer.init("kx")                                      # device-resident per-ray Newton
+    t_compile = time.perf_counter()
+    tracer.compile()
+    # (tabulated equilibria: the tracer keeps rays sorted by table cell while stepping -- EFIT (R, Z) cells,
+    #  VMEC radial cells; re-sorted after about half a cell of travel, inside the timed region when due;
+    #  --options bin_rays=0 switches it off)
+    t_ready = time.perf_counter()
+    stats = tracer.kernel_stats()
+    peaks = device_peaks(tracer)
+
+    # ---- kernel-resident measurement -------------------------------------------------
+    sampler = ClockSampler(ranks.local_rank).start()
+    for _ in range(warmup):
+        tracer.step(SUB_STEPS)
+    tracer.wait()
+    ranks.barrier()
+    sampler.mark()                                         # clocks are kept from here to the end of the e2e region
+    launches0 = tracer.launch_count()
+    kernel_ms = 0.0
+    for _ in range(steps):
+        tracer.flush_l2()                                  # untimed: evict state + tables from L2
+        tracer.timer_start()
+        tracer.step(SUB_STEPS)
+        kernel_ms += tracer.timer_stop()
+    tracer.wait()
+    launches = tracer.launch_count() - launches0           # solver_kernel launches (+ re-sorts when due); L2 fills not counted
+    ranks.barrier()
+    kernel_ms_max = ranks.max(kernel_ms)
+
+    # ---- end to end through the public API with host buffers -------------------------
+    e2e = None
+    finite = True
+    if with_e2e:
+        host = {k: torch.empty(rays, dtype=torch.float64).pin_memory() for k in STATE + ("residual",)}
+        host_out = {k: v.numpy() for k, v in host.items()}
+        tracer.get_state(out=host_out)
+        host_in = {k: torch.empty(rays, dtype=torch.float64).pin_memory() for k in STATE}
+        for k in STATE:
+            host_in[k].copy_(host[k])
+        host_np = {k: host_in[k].numpy() for k in STATE}
+        e2e_steps = max(2, min(steps, 10))
+        for _ in range(2):
+            out = tracer.step_host(SUB_STEPS, host_np, host_out, chunks=args.chunks)
+        ranks.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            # one public-API call: H2D of the 8 state arrays from pinned memory, SUB_STEPS fused steps,
+            # D2H of the 8 arrays + residual into pinned memory; pieces of the ensemble are pipelined
+            out = tracer.step_host(SUB_STEPS, host_np, host_out, chunks=args.chunks)
+        torch.cuda.synchronize()
+        e2e_s = ranks.max(time.perf_counter() - t0)
+        finite = bool(np.isfinite(out["x"]).all())
+        copied = (8*8 + 9*8)*rays
+        e2e = {"value": rays*ranks.world*SUB_STEPS*e2e_steps/e2e_s if not strong else total*SUB_STEPS*e2e_steps/e2e_s,
+               "unit": "ray-steps/s", "h2d_bytes_per_step": 8*8*rays, "d2h_bytes_per_step": 9*8*rays,
+               "steps": e2e_steps, "finite": finite,
+               "host_copy_gbs_per_rank": copied*e2e_steps/e2e_s/1.0e9,
+               "api": "RayTracer.step_host (gfb_rays_step_host): upload, %d fused steps, read-back; %d pipelined chunks"
+                      % (SUB_STEPS, args.chunks)}
+    clocks = sampler.stop()
+
+    total_rays = total if strong else rays*ranks.world
+    result = None
+    if ranks.rank == 0:
+        flop = workloads.FLOP_PER_RAY_STEP.get((disp, eq))
+        result = {
+            "metric": "ray-steps/sec (FP64 RK4)", "value": total_rays*SUB_STEPS*steps/(kernel_ms_max*1.0e-3),
+            "unit": "ray-steps/s", "n_gpus": ranks.world, "steps": steps, "warmup": warmup,
+            "ms_per_step": kernel_ms_max/steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s + %s, RK4 FP64, %d RK4 steps per bench step (one fused launch)"
+                                   % (name, disp, eq, SUB_STEPS),
+                       "rays_per_gpu": rays, "rays_total": total_rays, "dt": dt, "newton_init": "device-resident per-ray",
+                       "l2": "flushed between timed steps (256 MiB fill, untimed)", "options": args.options},
+            "roofline": fp64_roofline(name, tracer.ctx, rays, SUB_STEPS, kernel_ms/steps, flop, peaks,
+                                      workloads.STATE_BYTES_PER_RAY*rays),
+            "e2e": e2e, "gpu_launches": launches,
+            "kernel": dict(stats, block=128, min_blocks_per_sm=int(_lib.lib.gfb_compiled_min_blocks(tracer.ctx))),
+            "clocks": clocks,
+            "phases_s": {"setup": t_init - t_setup, "newton_init": t_compile - t_init, "jit": t_ready - t_compile},
+        }
+        if cpu_baseline and ranks.world == 1:                # reported baseline, rank 0 at N = 1 only
+            result["cpu_baseline"] = reference_rays_baseline(disp, eq, dt, gen, args.ref_rays)
+    tracer.close()
+    return result
+
+
+def reference_rays_baseline(disp, eq, dt, gen, n_ref):
+    try:
+        from oracle import reference
+        if eq == "vmec":
+            return {"value": None, "unit": "ray-steps/s", "cores": 0, "kind": "reference",
+                    "sample": "not timed here: the reference needs ~8 min of graph building + compiling per VMEC kernel "
+                              "(oracle/make_golden.py vmec_trace); its stepping rate is 4.6e3 ray-steps/s per thread (SURVEY.md section 6)"}
+        if not reference.available():
+            return {"value": None, "unit": "ray-steps/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/ref_driver not present"}
+        cores = nproc()
+        r = reference.bench(disp, eq, n_ref, dt, SUB_STEPS, cores, gen(n_ref, seed=0))
+        return {"value": r["ray_steps_per_s"], "unit": "ray-steps/s", "cores": cores, "kind": "reference",
+                "sample": "%d rays x %d RK4 steps, unmodified reference graph+solver, kernel compiled by g++ -O3 -ffast-math, %d threads; "
+                          "stepping phase only (setup %.1fs, init %.1fs, JIT %.1fs excluded)"
+                          % (n_ref, SUB_STEPS, cores, r["setup_s"], r["init_s"], r["compile_s"])}
+    except Exception as e:      # the baseline must never take the headline down
+        return {"value": None, "unit": "ray-steps/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+
+
+# ---------------------------------------------------------------------------------------------
+#  configs[2]: trace + absorption + deposition, the profile summed over GPUs once per output block
+# ---------------------------------------------------------------------------------------------
+def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
+    import numpy as np
+    import torch
+    from graph_framework_b200 import workloads
+    from graph_framework_b200.rays import RayTracer, STATE, pinned_empty
+
+    cfg = ABSORB
+    strong = args.scaling == "strong"
+    rays = shard(cfg["total"], ranks) if strong else cfg["rays"]
+    total_rays = cfg["total"] if strong else rays*ranks.world
+    bins, lo, hi = cfg["bins"], cfg["lo"], cfg["hi"]
+    state0 = workloads.efit_ensemble(rays, seed=ranks.rank)
+    tracer = RayTracer(cfg["dispersion"], cfg["equilibrium"], rays, cfg["dt"], device=ranks.local_rank,
+                       options=("fused_steps=%d absorption=1 " % SUB_STEPS) + args.options)
+    tracer.set_state(state0)
+    tracer.init("kx")
+    tracer.compile()
+    start = tracer.get_state(residual=False)
+    peaks = device_peaks(tracer)
+    #  All torch work (zeroing, NCCL) is issued on the tracer's own stream: one timeline, no host waits.
+    stream = torch.cuda.ExternalStream(tracer.stream(), device=torch.device("cuda", ranks.local_rank))
+    increment = torch.zeros(bins, dtype=torch.float64, device="cuda")       # d_power of one block, this rank
+    profile = torch.zeros(bins, dtype=torch.float64, device="cuda")         # running sum over blocks and ranks
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def block(timed):
+        with torch.cuda.stream(stream):
+            increment.zero_()
+            if timed:
+                ev[0].record(stream)
+            tracer.deposit_block(SUB_STEPS, increment.data_ptr(), lo, hi, bins)
+            if timed:
+                ev[1].record(stream)
+            if ranks.dist:
+                ranks.dist.all_reduce(increment, op=ranks.dist.ReduceOp.SUM)       # NCCL, FP64, over NVLink
+            profile.add_(increment)
+            if timed:
+                ev[2].record(stream)
+
+    sampler = ClockSampler(ranks.local_rank).start()
+    for _ in range(warmup):
+        block(False)
+    tracer.wait()
+    ranks.barrier()
+    sampler.mark()
+    launches0 = tracer.launch_count()
+    total_ms = compute_ms = 0.0
+    deposited = []
+    for _ in range(steps):
+        block(True)
+        ev[2].synchronize()
+        compute_ms += ev[0].elapsed_time(ev[1])
+        total_ms += ev[0].elapsed_time(ev[2])
+        deposited.append(float(increment.sum().item()))
+    launches = tracer.launch_count() - launches0
+    ranks.barrier()
+    total_ms_max = ranks.max(total_ms)
+    compute_ms_max = ranks.max(compute_ms)
+
+    # ---- parity of the reduced profile: one more block of the production path, ALL rays -----------
+    parity = None
+    if check:
+        block(False)
+        tracer.wait()
+        torch.cuda.synchronize()
+        pos = tracer.get_state(residual=False)                  # caller's ray order
+        absorbed = tracer.get_absorbed()                        # Im k_amp, power, d_power of that block, same order
+        from oracle import port
+        mine = port.deposit(pos["x"], pos["y"], pos["z"], absorbed["d_power"], lo, hi, bins)
+        summed = torch.from_numpy(mine).cuda()
+        if ranks.dist:
+            ranks.dist.all_reduce(summed, op=ranks.dist.ReduceOp.SUM)
+        oracle_sum = summed.cpu().numpy()
+        reduced = increment.cpu().numpy()
+        scale = max(float(np.max(np.abs(oracle_sum))), 1.0e-300)
+        dev = float(np.max(np.abs(reduced - oracle_sum))/scale)
+        parity = {"rays_checked_per_rank": rays, "max_abs_dev_over_max_bin": dev, "tolerance": 1.0e-12, "ok": dev < 1.0e-12,
+                  "oracle": "oracle.port.deposit (numpy restatement of utilities/bin.py:53-106) of every rank's rays and d_power of the block, summed over ranks",
+                  "block_power": float(oracle_sum.sum()), "nonzero_bins": int((reduced != 0).sum()),
+                  "rays_depositing": int((absorbed["d_power"] != 0).sum()),
+                  "profile_total_all_blocks": float(profile.sum().item()),
+                  "median_transmitted_power": float(np.nanmedian(absorbed["power"]))}
+
+    # ---- end to end: host state in, reduced profile out ------------------------------------------
+    e2e = None
+    if with_e2e:
+        host_in = {k: pinned_empty(rays) for k in STATE}
+        for k in STATE:
+            host_in[k][:] = start[k]
+        host_profile = torch.empty(bins, dtype=torch.float64).pin_memory()
+        e2e_steps = max(2, min(steps, 5))
+
+        def e2e_step():
+            tracer.put_state(host_in)                              # H2D of the 8 state arrays
+            tracer.absorption_reset()
+            block(False)
+            with torch.cuda.stream(stream):
+                host_profile.copy_(increment, non_blocking=True)   # D2H of the reduced profile of the block
+            stream.synchronize()
+        e2e_step()
+        ranks.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = ranks.max(time.perf_counter() - t0)
+        e2e = {"value": total_rays*SUB_STEPS*e2e_steps/e2e_s, "unit": "ray-steps/s", "h2d_bytes_per_step": 8*8*rays,
+               "d2h_bytes_per_step": int(np.prod(bins))*8, "steps": e2e_steps,
+               "api": "RayTracer.put_state + deposit_block + NCCL all-reduce + profile read-back"}
+    clocks = sampler.stop()
+
+    result = None
+    if ranks.rank == 0:
+        cells = int(np.prod(bins))
+        result = {
+            "metric": "ray-steps/sec (FP64 RK4 + absorption + deposition + all-reduce)",
+            "value": total_rays*SUB_STEPS*steps/(total_ms_max*1.0e-3), "unit": "ray-steps/s", "n_gpus": ranks.world,
+            "steps": steps, "warmup": warmup, "ms_per_step": total_ms_max/steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "efit_absorb (BASELINE configs[2]): %s + %s, device Newton, %d RK4 steps, weak damping, power, "
+                                   "deposition on %dx%dx%d bins, one NCCL FP64 all-reduce of the block's profile (%d bytes) per bench step"
+                                   % (cfg["dispersion"], cfg["equilibrium"], SUB_STEPS, bins[0], bins[1], bins[2], cells*8),
+                       "rays_per_gpu": rays, "rays_total": total_rays, "dt": cfg["dt"], "options": args.options,
+                       "state_larger_than_L2": rays*72 > 126e6},
+            "collective": {"what": "torch.distributed all_reduce(SUM, float64) on NCCL, issued on the tracer's stream" if ranks.dist else "none at 1 GPU",
+                           "bytes": cells*8, "ms_per_step": (total_ms_max - compute_ms_max)/steps,
+                           "share_of_step": (total_ms_max - compute_ms_max)/total_ms_max,
+                           "note": "includes the add into the running profile (one %d-element kernel)" % cells},
+            "deposited_power_per_block_rank0": deposited,
+            "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": fp64_roofline("efit_absorb", tracer.ctx, rays, SUB_STEPS, compute_ms/steps,
+                                      workloads.FLOP_PER_RAY_STEP.get((cfg["dispersion"], cfg["equilibrium"])), peaks,
+                                      workloads.STATE_BYTES_PER_RAY*rays),
+        }
+    tracer.close()
+    return result
+
+
+# ---------------------------------------------------------------------------------------------
+#  configs[4]: the xkorc Boris push
+# ---------------------------------------------------------------------------------------------
+def run_boris(args, ranks, steps, warmup, particles_override=0, with_e2e=True, cpu_baseline=True):
+    """BASELINE configs[4]: the xkorc Boris push (graph_korc/xkorc.cpp:66-121) in the EFIT field."""
+    import numpy as np
+    import torch
+    from graph_framework_b200 import workloads
+    from graph_framework_b200.rays import BorisPusher
+    strong = args.scaling == "strong" or (args.workload == "boris" and not particles_override and not args.rays)
+    if particles_override:
+        n, total = particles_override, particles_override*ranks.world
+        strong = False
+    elif strong:
+        total = args.rays or BORIS["total"]
+        n = shard(total, ranks)
+    else:
+        n = args.rays or BORIS["particles"]
+        total = n*ranks.world
+    state = workloads.boris_ensemble(n, seed=ranks.rank)
+    push = BorisPusher("efit", n, dt=BORIS["dt"], device=ranks.local_rank, options="fused_steps=%d %s" % (SUB_STEPS, args.options))
+    push.set_state(*state)
+    push.compile()
+    peaks = device_peaks(push)
+    # (the pusher keeps particles sorted by the (R, Z) cell of the EFIT tables, re-sorted every 1000 pushes,
+    #  inside the timed region when due; --options bin_rays=0 switches it off)
+    sampler = ClockSampler(ranks.local_rank).start()
+    for _ in range(warmup):
+        push.step(SUB_STEPS)
+    ranks.barrier()
+    sampler.mark()
+    launches0 = push.launch_count()
+    ms = 0.0
+    for _ in range(steps):
+        push.timer_start()
+        push.step(SUB_STEPS)
+        ms += push.timer_stop()
+    launches = push.launch_count() - launches0
+    ranks.barrier()
+    ms_max = ranks.max(ms)
+    e2e = None
+    if with_e2e:
+        e2e_steps = 2
+        host = [np.array(a) for a in state]
+        push.set_state(*host)
+        push.step(SUB_STEPS)
+        push.get_state()
+        ranks.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            push.set_state(*host)               # H2D of x, y, z, ux, uy, uz (+ the initialize_gamma pre-item)
+            push.step(SUB_STEPS)
+            got = push.get_state()              # D2H of the 7 arrays
+        torch.cuda.synchronize()
+        e2e_s = ranks.max(time.perf_counter() - t0)
+        e2e = {"value": total*SUB_STEPS*e2e_steps/e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 6*8*n,
+               "d2h_bytes_per_step": 7*8*n, "steps": e2e_steps, "finite": bool(np.isfinite(got["gamma"]).all()),
+               "api": "BorisPusher.set_state + step(%d) + get_state (pageable host arrays, not pipelined)" % SUB_STEPS}
+    st = push.get_state()
+    finite = bool(np.isfinite(st["gamma"]).all())
+    clocks = sampler.stop()
+    result = None
+    if ranks.rank == 0:
+        flop = workloads.FLOP_PER_PARTICLE_STEP_BORIS
+        result = {
+            "metric": "particle-steps/sec (FP64 Boris)", "value": total*SUB_STEPS*steps/(ms_max*1.0e-3),
+            "unit": "particle-steps/s", "n_gpus": ranks.world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_max/steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "boris (BASELINE configs[4]): xkorc Boris push in the EFIT field, %d fused pushes per bench step" % SUB_STEPS,
+                       "particles_per_gpu": n, "particles_total": total, "dt": BORIS["dt"],
+                       "l2": "state larger than L2 (%d MB per GPU)" % (n*56//1000000) if n*56 > 126e6 else "state fits L2",
+                       "options": args.options,
+                       "binning": "particles kept sorted by EFIT (R, Z) cell, re-sorted every 1000 pushes"},
+            "roofline": fp64_roofline("boris", push.ctx, n, SUB_STEPS, ms/steps, flop, peaks, 112*n),
+            "e2e": e2e, "gpu_launches": launches, "finite": finite, "info": push.info(), "clocks": clocks,
+        }
+        if cpu_baseline and ranks.world == 1:
+            result["cpu_baseline"] = reference_boris_baseline(args.ref_particles)
+    push.close()
+    return result
+
+
+def reference_boris_baseline(n_ref):
+    """The reference's own Boris work items (oracle/_ref korc mode = graph_korc/xkorc.cpp:40-121 on its CPU
+    path), one process per host core as the reference runs one thread per device."""
+    try:
+        from oracle import reference
+        from graph_framework_b200 import workloads
+        if not reference.available():
+            return {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/ref_driver not present"}
+        cores = nproc()
+        per = max(n_ref//cores, 1)
+        results = [None]*cores
+
+        def one(i):
+            x, y, z, ux, uy, uz = workloads.boris_ensemble(per, seed=100 + i)
+            results[i] = reference.korc("efit", x, y, z, ux, uy, uz, SUB_STEPS)[1]
+        threads = [threading.Thread(target=one, args=(i,)) for i in range(cores)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        slowest = max(r["steps_s"] for r in results)
+        return {"value": per*cores*SUB_STEPS/slowest, "unit": "particle-steps/s", "cores": cores, "kind": "reference",
+                "sample": "%d particles x %d pushes per process, %d processes of the unmodified reference work items (g++ -O3 -ffast-math kernel); "
+                          "stepping phase only" % (per, SUB_STEPS, cores)}
+    except Exception as e:
+        return {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+
+
+# ---------------------------------------------------------------------------------------------
+#  The reference arm
+# ---------------------------------------------------------------------------------------------
 def reference_arm(args, rank, world):
     """The reference's own CPU path on this box's host cores, bounded sample."""
     if rank != 0:
         return 0
     from oracle import reference
-    from graph_framework_b200 import workloads
-    disp, eq, _, dt = WORKLOADS[args.workload]
-    cores = nproc()
     if not reference.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built"}))
+        return 0
+    cores = nproc()
+    if args.workload == "boris":
+        t0 = time.perf_counter()
+        b = reference_boris_baseline(args.ref_particles)
+        if not b["value"]:
+            print(json.dumps({"impl": "reference", "unavailable": b["sample"]}))
+            return 0
+        line = {"impl": "reference", "metric": "particle-steps/sec (FP64 Boris)", "value": b["value"], "unit": "particle-steps/s",
+                "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1.0e3*(time.perf_counter() - t0),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "boris (BASELINE configs[4]): xkorc Boris push in the EFIT field", "particles": args.ref_particles, "dt": BORIS["dt"]},
+                "cpu_baseline": b, "e2e": {"value": b["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+    name = "efit_omode" if args.workload == "efit_absorb" else args.workload
+    disp, eq, _, dt, _ = WORKLOADS[name]
+    if args.workload == "efit_absorb":
+        dt = ABSORB["dt"]
+    if eq == "vmec":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference needs ~8 min of graph building + compiling per VMEC kernel; not run inside bench.py"}))
         return 0
     rays = args.ref_rays
     state = generator(eq)(rays, seed=0)
@@ -133,7 +675,8 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": "ray-steps/sec (FP64 RK4)", "value": value, "unit": "ray-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1.0e3*total/len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %s + %s, RK4 FP64, %d steps per block" % (args.workload, disp, eq, SUB_STEPS),
+        "config": {"workload": "%s: %s + %s, RK4 FP64, %d steps per block%s" % (args.workload, disp, eq, SUB_STEPS,
+                                                                                " (stepping only: the reference's absorption stages are file-coupled)" if args.workload == "efit_absorb" else ""),
                    "rays": rays, "dt": dt},
         "cpu_baseline": {"value": value, "unit": "ray-steps/s", "cores": cores, "kind": "reference",
                          "sample": "%d rays x %d RK4 steps per timed step, reference graph+solver, kernels by g++ -O3 -ffast-math, %d threads (setup %.1fs, Newton init %.1fs, JIT %.1fs excluded as in xrays_bench.cpp)"
@@ -145,65 +688,14 @@ def reference_arm(args, rank, world):
     return 0
 
 
-def boris_arm(args, rank, local_rank, world):
-    """BASELINE configs[4]: the xkorc Boris push (graph_korc/xkorc.cpp:66-121) in the EFIT field.
-    Strong scaling: --rays is the TOTAL particle count, sharded over ranks."""
-    import numpy as np
-    import torch
-    from graph_framework_b200 import workloads, parallel
-    from graph_framework_b200.rays import BorisPusher
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    total = args.rays or 100000000
-    off, n = parallel.my_shard(total, rank, world)
-    x, y, z, ux, uy, uz = workloads.boris_ensemble(n, seed=rank)
-    push = BorisPusher("efit", n, dt=0.5, device=local_rank, options="fused_steps=%d %s" % (SUB_STEPS, args.options))
-    push.set_state(x, y, z, ux, uy, uz)
-    push.compile()
-    # (the pusher keeps particles sorted by the (R, Z) cell of the EFIT tables, re-sorted every 1000 pushes,
-    #  inside the timed region when due; --options bin_rays=0 switches it off)
-    for _ in range(args.warmup):
-        push.step(SUB_STEPS)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    launches0 = push.launch_count()
-    ms = 0.0
-    for _ in range(args.steps):
-        push.timer_start()
-        push.step(SUB_STEPS)
-        ms += push.timer_stop()
-    launches = push.launch_count() - launches0
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    st = push.get_state()
-    finite = bool(np.isfinite(st["gamma"]).all())
-    if rank == 0:
-        value = total*SUB_STEPS*args.steps/(ms*1.0e-3)
-        flop = workloads.FLOP_PER_PARTICLE_STEP_BORIS
-        print(json.dumps({
-            "metric": "particle-steps/sec (FP64 Boris)", "value": value, "unit": "particle-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms/args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "boris: xkorc Boris push in the EFIT field, %d fused pushes per bench step" % SUB_STEPS,
-                       "particles_total": total, "dt": 0.5, "state_larger_than_L2": n*56 > 126e6, "options": args.options,
-                       "binning": "particles kept sorted by EFIT (R, Z) cell, re-sorted every 1000 pushes"},
-            "roofline": {"bound": "fp64", "achieved": flop*value/world/1.0e12, "peak": None, "unit": "TFLOP/s", "frac": None,
-                         "traffic": None, "algorithmic_flop_per_particle_step": flop,
-                         "hbm": {"algorithmic_bytes_per_launch": 112*n, "achieved_gbs": 112*n/(ms/args.steps*1.0e-3)/1.0e9}},
-            "gpu_launches": launches, "finite": finite, "info": push.info()}))
-    push.close()
-    if dist:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+def run_workload(name, args, ranks, steps, warmup, extra):
+    """extra = True: a short side measurement (no CPU baseline for the ray workloads that the headline covers)."""
+    if name == "boris":
+        return run_boris(args, ranks, steps, warmup, particles_override=BORIS["particles"] if extra and args.scaling != "strong" else 0,
+                         with_e2e=True, cpu_baseline=True)
+    if name == "efit_absorb":
+        return run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True)
+    return run_rays(name, args, ranks, steps, warmup, with_e2e=True, cpu_baseline=True)
 
 
 def main():
@@ -212,184 +704,57 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="efit_xmode", choices=sorted(WORKLOADS) + ["boris"])
-    ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="efit_xmode", choices=sorted(WORKLOADS) + ["boris", "efit_absorb"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: the BASELINE totals (10^6 EFIT rays, 10^7 VMEC rays, 10^8 particles) sharded over the ranks")
+    ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's); Boris: total particles")
     ap.add_argument("--ref-rays", type=int, default=20000, help="rays of the bounded CPU sample")
+    ap.add_argument("--ref-particles", type=int, default=400000, help="particles of the bounded CPU sample (Boris)")
     ap.add_argument("--options", default="", help="emit/launch options passed to gfb_rays_create")
     ap.add_argument("--chunks", type=int, default=5, help="pieces of the ensemble pipelined by the e2e call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="time the headline workload only")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
-    if args.workload == "boris":
-        if args.impl == "reference":
-            if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "the Boris workload has no CPU arm in bench.py (see oracle/ref_driver korc mode)"}))
-            return 0
-        return boris_arm(args, rank, local_rank, world)
+    ranks = Ranks()
     if args.impl == "reference":
-        return reference_arm(args, rank, world)
+        return reference_arm(args, ranks.rank, ranks.world)
 
-    import numpy as np
     import torch
-    from graph_framework_b200 import workloads
-    from graph_framework_b200.rays import RayTracer, STATE
-    from graph_framework_b200 import _lib
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 back end has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ranks.init()
 
-    disp, eq, default_rays, dt = WORKLOADS[args.workload]
-    rays = args.rays or default_rays                      # per GPU: weak scaling
-    gen = generator(eq)
-    state0 = gen(rays, seed=rank)
-
-    t_setup = time.perf_counter()
-    tracer = RayTracer(disp, eq, rays, dt, solver="rk4", device=local_rank,
-                       options=("fused_steps=%d " % SUB_STEPS) + args.options)
-    tracer.set_state(state0)
-    t_init = time.perf_counter()
-    tracer.init("kx")                                      # device-resident per-ray Newton
-    t_compile = time.perf_counter()
-    tracer.compile()
-    # (tabulated equilibria: the tracer keeps rays sorted by table cell while stepping -- EFIT (R, Z) cells,
-    #  VMEC radial cells; re-sorted after about half a cell of travel, inside the timed region when due;
-    #  --options bin_rays=0 switches it off)
-    t_ready = time.perf_counter()
-    stats = tracer.kernel_stats()
-    fp64_peak = tracer.fp64_peak()
-
-    # ---- kernel-resident measurement -------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(args.warmup):
-        tracer.step(SUB_STEPS)
-    tracer.wait()
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.mark()                                         # clocks are kept from here to the end of the e2e region
-    launches0 = tracer.launch_count()
-    kernel_ms = 0.0
-    for _ in range(args.steps):
-        tracer.flush_l2()                                  # untimed: evict state + tables from L2
-        tracer.timer_start()
-        tracer.step(SUB_STEPS)
-        kernel_ms += tracer.timer_stop()
-    tracer.wait()
-    launches = tracer.launch_count() - launches0                    # solver_kernel launches (L2 fills not counted)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-        t = torch.tensor([kernel_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        kernel_ms_max = float(t.item())
+    if args.workload == "boris":
+        line = run_boris(args, ranks, args.steps, args.warmup, with_e2e=not args.no_e2e, cpu_baseline=not args.no_cpu_baseline)
+    elif args.workload == "efit_absorb":
+        line = run_absorb(args, ranks, args.steps, args.warmup, with_e2e=not args.no_e2e, check=True)
     else:
-        kernel_ms_max = kernel_ms
-
-    # ---- end to end through the public API with host buffers -------------------------
-    host = {k: torch.empty(rays, dtype=torch.float64).pin_memory() for k in STATE + ("residual",)}
-    host_out = {k: v.numpy() for k, v in host.items()}
-    tracer.get_state(out=host_out)
-    host_in = {k: torch.empty(rays, dtype=torch.float64).pin_memory() for k in STATE}
-    for k in STATE:
-        host_in[k].copy_(host[k])
-    host_np = {k: host_in[k].numpy() for k in STATE}
-    e2e_steps = max(2, min(args.steps, 10))
-    for _ in range(2):
-        out = tracer.step_host(SUB_STEPS, host_np, host_out, chunks=args.chunks)
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        # one public-API call: H2D of the 8 state arrays from pinned memory, SUB_STEPS fused steps,
-        # D2H of the 8 arrays + residual into pinned memory; pieces of the ensemble are pipelined
-        out = tracer.step_host(SUB_STEPS, host_np, host_out, chunks=args.chunks)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    finite = bool(np.isfinite(out["x"]).all())
-    clocks = sampler.stop()
-
-    total_rays = rays*world
-    value = total_rays*SUB_STEPS*args.steps/(kernel_ms_max*1.0e-3)
-    e2e_value = total_rays*SUB_STEPS*e2e_steps/e2e_s
-
-    if rank == 0:
-        flop = workloads.FLOP_PER_RAY_STEP.get((disp, eq))
-        per_launch_ms = kernel_ms/args.steps
-        achieved = flop*rays*SUB_STEPS/(per_launch_ms*1.0e-3)/1.0e12 if flop else None
-        hbm_bytes = workloads.STATE_BYTES_PER_RAY*rays
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except OSError:
-            pass
-        line = {
-            "metric": "ray-steps/sec (FP64 RK4)", "value": value, "unit": "ray-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": kernel_ms_max/args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %s + %s, RK4 FP64, %d RK4 steps per bench step (one fused launch)"
-                                   % (args.workload, disp, eq, SUB_STEPS),
-                       "rays_per_gpu": rays, "dt": dt, "newton_init": "device-resident per-ray",
-                       "l2": "flushed between timed steps (256 MiB fill, untimed)",
-                       "options": args.options},
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": (achieved/fp64_peak) if achieved else None,
-                         "traffic": NCU.get(args.workload, {}).get("traffic"),
-                         "fp64_pipe_active_pct_ncu": NCU.get(args.workload, {}).get("fp64_pipe_active_pct"),
-                         "ncu_source": NCU.get(args.workload, {}).get("source"),
-                         "note": "achieved = the REFERENCE kernel's flop count per ray-step (BASELINE.md section 2) x ray-steps / time, the unit of work SURVEY.md 8d fixes; this back end executes fewer FP64 instructions for the same step (reverse-mode gradient, shared reciprocals), so frac can exceed the FP64-pipe busy share and, for cold plasma, 1.0",
-                         "peak_source": "DFMA peak measured live by gfb_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure); nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
-                         "algorithmic_flop_per_ray_step": flop,
-                         "hbm": {"algorithmic_bytes_per_launch": hbm_bytes,
-                                 "achieved_gbs": hbm_bytes/(per_launch_ms*1.0e-3)/1.0e9,
-                                 "peak_gbs": peaks.get("hbm_gbs")}},
-            "e2e": {"value": e2e_value, "unit": "ray-steps/s", "h2d_bytes_per_step": 8*8*rays,
-                    "d2h_bytes_per_step": 9*8*rays, "steps": e2e_steps, "finite": finite,
-                    "api": "RayTracer.step_host (gfb_rays_step_host): upload, %d fused steps, read-back; %d pipelined chunks" % (SUB_STEPS, args.chunks)},
-            "gpu_launches": launches,
-            "kernel": dict(stats, block=128, min_blocks_per_sm=int(_lib.lib.gfb_compiled_min_blocks(tracer.ctx))),
-            "clocks": clocks,
-            "phases_s": {"setup": t_init - t_setup, "newton_init": t_compile - t_init, "jit": t_ready - t_compile},
-        }
-        if not args.no_cpu_baseline and world == 1:          # reported baseline, rank 0 at N = 1 only
+        override = args.rays if args.scaling == "weak" else 0
+        line = run_rays(args.workload, args, ranks, args.steps, args.warmup, with_e2e=not args.no_e2e,
+                        cpu_baseline=not args.no_cpu_baseline, rays_override=override)
+    if not args.no_extras:
+        extras = {}
+        saved_options, saved_rays = args.options, args.rays
+        args.rays = 0
+        for name in EXTRAS:
+            if name == args.workload:
+                continue
             try:
-                from oracle import reference
-                if reference.available():
-                    cores = nproc()
-                    n_ref = args.ref_rays
-                    ref_state = gen(n_ref, seed=0)
-                    r = reference.bench(disp, eq, n_ref, dt, SUB_STEPS, cores, ref_state)
-                    line["cpu_baseline"] = {
-                        "value": r["ray_steps_per_s"], "unit": "ray-steps/s", "cores": cores, "kind": "reference",
-                        "sample": "%d rays x %d RK4 steps, unmodified reference graph+solver, kernel compiled by g++ -O3 -ffast-math, %d threads; stepping phase only (setup %.1fs, init %.1fs, JIT %.1fs excluded)"
-                                  % (n_ref, SUB_STEPS, cores, r["setup_s"], r["init_s"], r["compile_s"])}
-                else:
-                    line["cpu_baseline"] = {"value": None, "unit": "ray-steps/s", "cores": 0, "kind": "reference",
-                                            "sample": "oracle/_ref/ref_driver not present"}
-            except Exception as e:      # the baseline must never take the headline down
-                line["cpu_baseline"] = {"value": None, "unit": "ray-steps/s", "cores": 0, "kind": "reference",
-                                        "sample": "failed: %r" % (e,)}
+                extras[name] = run_workload(name, args, ranks, EXTRA_STEPS, EXTRA_WARMUP, extra=True)
+            except Exception as e:                              # a side measurement must never take the headline down
+                extras[name] = {"failed": repr(e)}
+                if ranks.world > 1:
+                    raise
+        args.options, args.rays = saved_options, saved_rays
+        if ranks.rank == 0:
+            line["extra"] = {"workloads": extras,
+                             "note": "the other BASELINE configurations, %d timed steps after %d warm-up steps each, same contract per entry"
+                                     % (EXTRA_STEPS, EXTRA_WARMUP)}
+    if ranks.rank == 0:
         print(json.dumps(line))
-    tracer.close()
-    if dist:
-        dist.barrier()
-        dist.destroy_process_group()
+    ranks.finish()
     return 0
 
 

@@ -60,6 +60,7 @@ def _load():
         "gfb_timer_stop": (I, [P, ctypes.POINTER(ctypes.c_float)]),
         "gfb_stream": (P, [P]),
         "gfb_deposit": (I, [P, P, P, P, P, SZ, P, c_double_p, c_double_p, ctypes.POINTER(I)]),
+        "gfb_allreduce_sum_f64": (I, [c_void_pp, I, ctypes.POINTER(U64), SZ]),
         "gfb_measure_fp64_peak": (I, [P, c_double_p, ctypes.POINTER(ctypes.c_float)]),
         "gfb_flush_l2": (I, [P]),
         # gfb_rays.h
@@ -79,6 +80,9 @@ def _load():
         "gfb_rays_trace_absorb": (I, [P, SZ, SZ, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                       ctypes.POINTER(ctypes.c_int)]),
         "gfb_rays_absorption_reset": (I, [P]),
+        "gfb_rays_deposit_block": (I, [P, SZ, P, c_double_p, c_double_p, ctypes.POINTER(I)]),
+        "gfb_rays_get_absorbed": (I, [P, ctypes.POINTER(c_double_p)]),
+        "gfb_rays_profile": (I, [P, ctypes.POINTER(U64), ctypes.POINTER(SZ)]),
         "gfb_rays_set_binning": (I, [P, I, D, D, ctypes.c_uint, SZ]),
         "gfb_bin_rays": (I, [P, ctypes.c_uint64, D, D, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64), I, SZ]),
         "gfb_bin_rays_rz": (I, [P, ctypes.POINTER(ctypes.c_uint64), c_double_p, c_double_p, ctypes.POINTER(ctypes.c_uint),

@@ -586,6 +586,46 @@ int gfb_rays_trace_absorb(gfb_rays *r, size_t num_blocks, size_t sub_steps, doub
     if (profile && gfb_copy_d2h(ctx, profile_key, profile, sizeof(double)*cells)) return 1;
     return gfb_wait(ctx);
 }
+int gfb_rays_deposit_block(gfb_rays *r, size_t sub_steps, double *profile_device,
+                           const double *lo, const double *hi, const int *bins) {
+    if (!r->compiled) return rays_fail("deposit_block before compile");
+    if (!r->impl->damping) return rays_fail("created without absorption=1");
+    if (!profile_device || !lo || !hi || !bins) return rays_fail("deposit_block needs a device profile with lo/hi/bins");
+    tracer_base &t = *r->impl;
+    gfb_ctx *ctx = t.context().device();
+    if (!r->absorption_started && gfb_rays_absorption_reset(r)) return 1;
+    auto d_power = t.deposition->get_d_power();
+    if (sub_steps) t.step(sub_steps);
+    t.damping->run();
+    t.deposition->run();
+//  State and d_power are in the same (possibly binned) ray order; the histogram does not care.
+    const double *xd = static_cast<const double *> (t.context().device_pointer(r->vars[GFB_X]));
+    const double *yd = static_cast<const double *> (t.context().device_pointer(r->vars[GFB_Y]));
+    const double *zd = static_cast<const double *> (t.context().device_pointer(r->vars[GFB_Z]));
+    const double *wd = static_cast<const double *> (t.context().device_pointer(d_power));
+    return gfb_deposit(ctx, xd, yd, zd, wd, r->n, profile_device, lo, hi, bins);
+}
+int gfb_rays_get_absorbed(gfb_rays *r, double *const out[3]) {
+    if (!r->compiled) return rays_fail("get_absorbed before compile");
+    if (!r->impl->damping) return rays_fail("created without absorption=1");
+    tracer_base &t = *r->impl;
+    gfb_ctx *ctx = t.context().device();
+    const leaf_ptr nodes[3] = {t.kamp_im, t.power, t.deposition->get_d_power()};
+    for (int i = 0; i < 3; i++) {
+        if (out[i] && gfb_copy_rays_d2h(ctx, reinterpret_cast<uint64_t> (nodes[i].get()), out[i], r->n)) return 1;
+    }
+    return 0;
+}
+int gfb_rays_profile(gfb_rays *r, uint64_t *key, size_t *cells) {
+    const uint64_t k = reinterpret_cast<uint64_t> (&r->profile_tag);
+    size_t bytes = 0;
+    if (!r->compiled || gfb_buffer_lookup(r->impl->context().device(), k, nullptr, &bytes)) {
+        return rays_fail("gfb_rays_profile: no profile yet (gfb_rays_trace_absorb with a profile creates it)");
+    }
+    if (key) *key = k;
+    if (cells) *cells = bytes/sizeof(double);
+    return 0;
+}
 int gfb_rays_device_ptr(gfb_rays *r, int which, void **device_ptr) {
     if (!r->compiled) return rays_fail("device_ptr before compile");
     r->impl->order().restore();

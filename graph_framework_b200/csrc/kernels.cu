@@ -224,6 +224,32 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, const int i
     }
 }
 
+//  One slice of an all-reduce over peer memory: dst[i] = sum over devices of src[d][i], always in
+//  device order, so every device ends up with bit-identical sums.  src[d] may live on another GPU of
+//  the NVSwitch domain (peer access enabled): the loads travel over NVLink, 16 bytes per lane.
+struct peer_sources {
+    const double *ptr[16];
+};
+__global__ void __launch_bounds__(256) sum_peers_kernel(double *__restrict__ dst, const peer_sources src, const int num,
+                                                        const size_t count) {
+    const size_t stride = static_cast<size_t> (gridDim.x)*blockDim.x;
+    const size_t pairs = count/2;
+    for (size_t i = static_cast<size_t> (blockIdx.x)*blockDim.x + threadIdx.x; i < pairs; i += stride) {
+        double2 acc = reinterpret_cast<const double2 *> (src.ptr[0])[i];
+        for (int d = 1; d < num; d++) {
+            const double2 v = reinterpret_cast<const double2 *> (src.ptr[d])[i];
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        reinterpret_cast<double2 *> (dst)[i] = acc;
+    }
+    if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double acc = src.ptr[0][count - 1];
+        for (int d = 1; d < num; d++) acc += src.ptr[d][count - 1];
+        dst[count - 1] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(double *p, const size_t n, const double v) {
     for (size_t i = static_cast<size_t> (blockIdx.x)*blockDim.x + threadIdx.x; i < n;
          i += static_cast<size_t> (gridDim.x)*blockDim.x) {
@@ -302,6 +328,16 @@ int gfb_k_compose(unsigned *total, const unsigned *first, const unsigned *second
 }
 int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s) {
     fp64_peak_kernel<<<sms*8, 256, 0, s>>> (scratch, iters, 0.999999, 1.0e-6);
+    return static_cast<int> (cudaGetLastError());
+}
+//  src: `num` (<= 16) pointers to `count` doubles each, 16-byte aligned; dst likewise.
+int gfb_k_sum_peers(double *dst, const double *const *src, int num, size_t count, int sms, cudaStream_t s) {
+    if (num < 1 || num > 16) return 1;
+    peer_sources p;
+    for (int d = 0; d < 16; d++) p.ptr[d] = d < num ? src[d] : nullptr;
+    const size_t blocks_needed = (count/2 + 255)/256;
+    const unsigned grid = static_cast<unsigned> (blocks_needed < static_cast<size_t> (sms)*4 ? blocks_needed : static_cast<size_t> (sms)*4);
+    sum_peers_kernel<<<grid ? grid : 1, 256, 0, s>>> (dst, p, num, count);
     return static_cast<int> (cudaGetLastError());
 }
 int gfb_k_fill(double *p, size_t n, double v, int sms, cudaStream_t s) {

@@ -47,6 +47,7 @@ int gfb_k_bin_breaks(const double *const values[3], unsigned n, const double lo[
                      const unsigned cells01[2], unsigned *breaks, int sms, cudaStream_t s);
 int gfb_k_compose(unsigned *total, const unsigned *first, const unsigned *second, unsigned n, int sms, cudaStream_t s);
 int gfb_k_fill(double *p, size_t n, double v, int sms, cudaStream_t s);
+int gfb_k_sum_peers(double *dst, const double *const *src, int num, size_t count, int sms, cudaStream_t s);
 }
 
 namespace {
@@ -248,6 +249,10 @@ struct gfb_ctx {
     double *bin_scratch = nullptr;
     size_t bin_capacity = 0, bin_cells = 0, bin_n = 0;
     bool binned = false;
+//  All-reduce over peer memory (gfb_allreduce_sum_f64): this device's summed slice, hand-over events.
+    double *reduce_scratch = nullptr;
+    size_t reduce_capacity = 0;
+    cudaEvent_t reduce_ready = nullptr, reduce_summed = nullptr, reduce_done = nullptr;
 };
 
 namespace {
@@ -333,6 +338,8 @@ void gfb_ctx_destroy(gfb_ctx *c) {
     if (c->bin_work) cudaFree(c->bin_work);
     if (c->bin_scratch) cudaFree(c->bin_scratch);
     if (c->flush_buffer) cudaFree(c->flush_buffer);
+    if (c->reduce_scratch) cudaFree(c->reduce_scratch);
+    for (cudaEvent_t e : {c->reduce_ready, c->reduce_summed, c->reduce_done}) if (e) cudaEventDestroy(e);
     if (c->upload_stream) {
         cudaStreamSynchronize(c->upload_stream);
         cudaStreamDestroy(c->upload_stream);
@@ -985,6 +992,120 @@ int gfb_deposit(gfb_ctx *c, const double *x, const double *y, const double *z, c
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
     c->launches++;
     if (gfb_k_deposit(x, y, z, weight, n, hist, lo, hi, bins, c->sms, c->stream)) return fail("deposit launch failed");
+    return 0;
+}
+
+//------------------------------------------------------------------------------
+//  Sum of one buffer per device over every device, result in every buffer (the binned
+//  power-deposition profile is the one quantity of a sharded ray trace that is reduced).  For the
+//  reference's model -- one process, one host thread per device (xrays.cpp:419-527) -- where NCCL
+//  communicators are not at hand: a reduce-scatter + all-gather written directly on peer memory.
+//    phase 1  device g sums slice g of all G buffers with P2P loads over NVLink (sum_peers_kernel,
+//             fixed device order => bit-identical result everywhere) into its scratch;
+//    phase 2  device g pulls the G - 1 other summed slices from its peers' scratch (copy engines).
+//  Cross-device ordering is by events only; the host never blocks.  Without peer access between a pair
+//  (no NVLink/NVSwitch) everything is staged through device 0 with cudaMemcpyPeerAsync.
+//------------------------------------------------------------------------------
+int gfb_allreduce_sum_f64(gfb_ctx *const *ctxs, int num_ctx, const uint64_t *keys, size_t n) {
+    if (num_ctx < 1 || num_ctx > 16) return fail("gfb_allreduce_sum_f64: 1 to 16 contexts");
+    if (n == 0) return 0;
+    std::vector<double *> data(num_ctx);
+    for (int g = 0; g < num_ctx; g++) {
+        gfb_ctx *c = ctxs[g];
+        if (flush(c)) return 1;
+        auto it = c->buffers.find(keys[g]);
+        if (it == c->buffers.end()) return fail("gfb_allreduce_sum_f64: unknown key");
+        if (it->second.bytes < n*sizeof(double)) return fail("gfb_allreduce_sum_f64: buffer shorter than n");
+        data[g] = static_cast<double *> (it->second.dev);
+        for (int h = 0; h < g; h++) if (ctxs[h] == c) return fail("gfb_allreduce_sum_f64: a context appears twice");
+    }
+    if (num_ctx == 1) return 0;
+//  Slices of whole 16-byte pairs; the last device takes the remainder.
+    const size_t per = ((n + num_ctx - 1)/num_ctx + 1)/2*2;
+    auto slice_begin = [&] (const int g) { return std::min(n, per*static_cast<size_t> (g)); };
+    auto slice_count = [&] (const int g) { return std::min(n, per*static_cast<size_t> (g + 1)) - slice_begin(g); };
+    bool peers = true;
+    for (int g = 0; g < num_ctx; g++) {
+        gfb_ctx *c = ctxs[g];
+        if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+        for (int h = 0; h < num_ctx; h++) {
+            if (h == g || ctxs[h]->device == c->device) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, c->device, ctxs[h]->device);
+            if (!can) { peers = false; continue; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[h]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peers = false;
+            cudaGetLastError();
+        }
+        if (!c->reduce_ready) {
+            cudaEventCreateWithFlags(&c->reduce_ready, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->reduce_summed, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->reduce_done, cudaEventDisableTiming);
+        }
+        const size_t need = peers ? per : n;
+        if (c->reduce_capacity < need) {
+            cudaStreamSynchronize(c->stream);
+            if (c->reduce_scratch) cudaFree(c->reduce_scratch);
+            if (check(cudaMalloc(&c->reduce_scratch, need*sizeof(double)), "reduce scratch")) return 1;
+            c->reduce_capacity = need;
+        }
+        if (check(cudaEventRecord(c->reduce_ready, c->stream), "reduce ready")) return 1;
+    }
+    if (!peers) {
+//  Staged: every buffer to device 0's scratch in turn, added there, then sent back.
+        gfb_ctx *root = ctxs[0];
+        if (check(cudaSetDevice(root->device), "cudaSetDevice")) return 1;
+        for (int g = 1; g < num_ctx; g++) {
+            cudaStreamWaitEvent(root->stream, ctxs[g]->reduce_ready, 0);
+            if (check(cudaMemcpyPeerAsync(root->reduce_scratch, root->device, data[g], ctxs[g]->device, n*sizeof(double), root->stream), "reduce stage")) return 1;
+            const double *pair[2] = {data[0], root->reduce_scratch};
+            if (gfb_k_sum_peers(data[0], pair, 2, n, root->sms, root->stream)) return fail("reduce sum launch failed");
+            root->launches++;
+        }
+        cudaEventRecord(root->reduce_summed, root->stream);
+        for (int g = 1; g < num_ctx; g++) {
+            gfb_ctx *c = ctxs[g];
+            if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+            cudaStreamWaitEvent(c->stream, root->reduce_summed, 0);
+            if (check(cudaMemcpyPeerAsync(data[g], c->device, data[0], root->device, n*sizeof(double), c->stream), "reduce broadcast")) return 1;
+            cudaEventRecord(c->reduce_done, c->stream);
+        }
+        if (check(cudaSetDevice(root->device), "cudaSetDevice")) return 1;
+        for (int g = 1; g < num_ctx; g++) cudaStreamWaitEvent(root->stream, ctxs[g]->reduce_done, 0);
+        return 0;
+    }
+//  Phase 1: reduce-scatter.
+    for (int g = 0; g < num_ctx; g++) {
+        gfb_ctx *c = ctxs[g];
+        if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+        for (int h = 0; h < num_ctx; h++) if (h != g) cudaStreamWaitEvent(c->stream, ctxs[h]->reduce_ready, 0);
+        const size_t count = slice_count(g);
+        if (count) {
+            std::vector<const double *> src(num_ctx);
+            for (int h = 0; h < num_ctx; h++) src[h] = data[h] + slice_begin(g);
+            if (gfb_k_sum_peers(c->reduce_scratch, src.data(), num_ctx, count, c->sms, c->stream)) return fail("reduce sum launch failed");
+            c->launches++;
+        }
+        if (check(cudaEventRecord(c->reduce_summed, c->stream), "reduce summed")) return 1;
+    }
+//  Phase 2: all-gather (own slice device-to-device, the others pulled from the peers).
+    for (int g = 0; g < num_ctx; g++) {
+        gfb_ctx *c = ctxs[g];
+        if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
+        for (int h = 0; h < num_ctx; h++) if (h != g) cudaStreamWaitEvent(c->stream, ctxs[h]->reduce_summed, 0);
+        for (int h = 0; h < num_ctx; h++) {
+            const size_t count = slice_count(h);
+            if (!count) continue;
+            if (check(cudaMemcpyPeerAsync(data[g] + slice_begin(h), c->device, ctxs[h]->reduce_scratch, ctxs[h]->device,
+                                          count*sizeof(double), c->stream), "reduce gather")) return 1;
+        }
+        if (check(cudaEventRecord(c->reduce_done, c->stream), "reduce done")) return 1;
+    }
+//  A device's scratch may be rewritten by the next reduction only after every peer has pulled it.
+    for (int g = 0; g < num_ctx; g++) {
+        if (check(cudaSetDevice(ctxs[g]->device), "cudaSetDevice")) return 1;
+        for (int h = 0; h < num_ctx; h++) if (h != g) cudaStreamWaitEvent(ctxs[g]->stream, ctxs[h]->reduce_done, 0);
+    }
     return 0;
 }
 

@@ -44,6 +44,24 @@ def allreduce_profile(hist, total_rays=None):
     return hist
 
 
+def allreduce_profiles_in_process(tracers):
+    """Thread-per-device model (one process, one RayTracer per GPU, the reference's xrays.cpp:419-527):
+    sums the device-resident deposition profiles of all tracers in place over NVLink peer memory
+    (gfb_allreduce_sum_f64) and returns the summed profile read back from the first device.
+    Call when no other thread is using the tracers."""
+    import ctypes
+    from ._lib import lib, check
+    keys_cells = [t.profile_key() for t in tracers]
+    cells = keys_cells[0][1]
+    assert all(c == cells for _, c in keys_cells), "profiles differ in size"
+    ctxs = (ctypes.c_void_p*len(tracers))(*[t.ctx for t in tracers])
+    keys = (ctypes.c_uint64*len(tracers))(*[k for k, _ in keys_cells])
+    check(lib.gfb_allreduce_sum_f64(ctxs, len(tracers), keys, cells), "allreduce_sum_f64")
+    out = np.empty(cells, dtype=np.float64)
+    check(lib.gfb_copy_d2h(tracers[0].ctx, keys_cells[0][0], out.ctypes.data_as(ctypes.c_void_p), out.nbytes), "profile d2h")
+    return out
+
+
 def deposit(tracer, weight, hist, lo, hi):
     """Bin per-ray weights at the rays' current positions into `hist` (a contiguous FP64 CUDA
     tensor of shape bins) on the tracer's stream (kernels.cu deposit_kernel).

@@ -175,6 +175,33 @@ class RayTracer:
                                         absorbed.ctypes.data_as(c_double_p), *args), "trace_absorb")
         return rec, absorbed, profile
 
+    def deposit_block(self, sub_steps, profile_ptr, lo, hi, bins):
+        """One output block with the deposition profile resident on the device (gfb_rays_deposit_block):
+        sub_steps RK steps, weak damping, power, d_power added into the device array at `profile_ptr`
+        (bins[0]*bins[1]*bins[2] doubles, e.g. tensor.data_ptr()) on the tracer's stream.  Nothing is
+        copied to the host and the call does not wait."""
+        lo_a = (ctypes.c_double*3)(*lo)
+        hi_a = (ctypes.c_double*3)(*hi)
+        bins_a = (ctypes.c_int*3)(*[int(b) for b in bins])
+        check(lib.gfb_rays_deposit_block(self.h, int(sub_steps), ctypes.c_void_p(int(profile_ptr)), lo_a, hi_a, bins_a),
+              "deposit_block")
+
+    def get_absorbed(self):
+        """Im k_amp, power and d_power of the last absorption block, in the caller's ray order."""
+        arrs = [np.empty(self.n, dtype=np.float64) for _ in range(3)]
+        check(lib.gfb_rays_get_absorbed(self.h, _ptr_array(arrs, 3)), "get_absorbed")
+        return dict(zip(("kamp_im", "power", "d_power"), arrs))
+
+    def profile_key(self):
+        """(buffer key, cells) of the device-resident profile of the last trace_absorb."""
+        key, cells = ctypes.c_uint64(0), ctypes.c_size_t(0)
+        check(lib.gfb_rays_profile(self.h, ctypes.byref(key), ctypes.byref(cells)), "profile")
+        return key.value, cells.value
+
+    def stream(self):
+        """The tracer's cudaStream_t (an integer), e.g. for torch.cuda.ExternalStream."""
+        return int(lib.gfb_stream(self.ctx) or 0)
+
     def set_binning(self, name, lo, hi, cells, rebin_every=0):
         """Keep rays sorted by the table cell of state `name` while stepping (include/gfb_rays.h
         gfb_rays_set_binning); invisible to the caller.  name=None switches it off."""

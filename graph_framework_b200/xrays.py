@@ -118,7 +118,10 @@ def trace_shard(args, shard, n, device, report):
     records = np.concatenate([np.stack(first)[None], records], axis=0)
     t2 = time.perf_counter()
     write_trajectory("%s%d.gfbt" % (args.output, shard), records, names)
-    tr.close()
+    if absorb:
+        report.setdefault("tracers", {})[shard] = tr       # the profile stays on the device until main() has reduced it
+    else:
+        tr.close()
     report[shard] = {"profile": profile,"rays": n, "setup_s": t1 - t0, "trace_s": t2 - t1, "records": records.shape[0],
                      "max_residual": float(np.max(records[-1][8])) if n else 0.0}
 
@@ -140,10 +143,19 @@ def main(argv=None):
         t.join()
     total = time.perf_counter() - t0
     steps = max(args.num_times//args.sub_steps, 1)*args.sub_steps
+    tracers = report.pop("tracers", {})
     slowest = max(r["trace_s"] for r in report.values())
     if args.absorption_model:
-#  bin.py:106: every shard's histogram summed, divided by the total number of rays.
-        total_profile = sum(r.pop("profile") for r in report.values())/float(args.num_rays)
+#  bin.py:106: every shard's histogram summed, divided by the total number of rays.  The shards' profiles
+#  are still on their devices: one all-reduce over NVLink peer memory (gfb_allreduce_sum_f64), one read-back.
+        from .parallel import allreduce_profiles_in_process
+        ordered = [tracers[d] for d in sorted(tracers)]
+        bins = (args.num_x, args.num_y, args.num_z)
+        total_profile = allreduce_profiles_in_process(ordered).reshape(bins)/float(args.num_rays)
+        for r in report.values():
+            r.pop("profile")
+        for tr in ordered:
+            tr.close()
         write_gfbt(os.path.join(os.path.dirname(args.output), "bins.gfbt"),
                    {"bins": total_profile,
                     "xbins": np.linspace(args.min_x, args.max_x, args.num_x + 1),

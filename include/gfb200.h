@@ -166,6 +166,16 @@ void *gfb_stream(gfb_ctx *ctx);
 int gfb_deposit(gfb_ctx *ctx, const double *x, const double *y, const double *z, const double *weight,
                 size_t n, double *hist, const double *lo, const double *hi, const int *bins);
 
+/* Sum of one buffer per device over all devices of ONE process, result left in every buffer
+ * (the reduction of the binned power-deposition profile for the reference's
+ * thread-per-device model, xrays.cpp:419-527, where torch.distributed/NCCL communicators do not exist).
+ * keys[g] names n doubles in ctxs[g].  Reduce-scatter + all-gather written on NVLink peer memory: device g
+ * sums slice g of every buffer with P2P loads, always in device order (bit-identical sums everywhere), then
+ * pulls the other slices; ordering is by CUDA events, the host does not block (call gfb_wait to observe).
+ * Devices without peer access are staged through device 0.  Call from one thread while no other thread
+ * uses these contexts.  (One process per GPU: use NCCL -- graph_framework_b200/parallel.py.) */
+int gfb_allreduce_sum_f64(gfb_ctx *const *ctxs, int num_ctx, const uint64_t *keys, size_t n);
+
 /* Measured FP64 FMA peak of the device in TFLOP/s (roofline denominator). */
 int gfb_measure_fp64_peak(gfb_ctx *ctx, double *tflops, float *milliseconds);
 /* L2 flush helper for benchmarks: writes a buffer larger than L2. */

@@ -94,6 +94,19 @@ int gfb_rays_set_binning(gfb_rays *r, int which_state, double lo, double hi, uns
 int gfb_rays_trace_absorb(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *records, double *absorbed,
                           double *profile, const double *lo, const double *hi, const int *bins);
 int gfb_rays_absorption_reset(gfb_rays *r);
+/* One output block of the same pipeline with the profile RESIDENT ON THE DEVICE and no host
+ * synchronisation: sub_steps RK steps, weak damping, power, then d_power is ADDED to `profile_device`
+ * (bins[0]*bins[1]*bins[2] doubles of device memory owned by the caller, e.g. a torch tensor that is
+ * then all-reduced with NCCL) on the tracer's stream (gfb_stream(gfb_rays_ctx(r))).  Config 3 of
+ * BASELINE.json: the per-GPU histogram that is summed over GPUs once per output block. */
+int gfb_rays_deposit_block(gfb_rays *r, size_t sub_steps, double *profile_device,
+                           const double *lo, const double *hi, const int *bins);
+/* Running absorption state in the caller's ray order: out[0..2] = Im k_amp, power, d_power
+ * (num_rays doubles each, NULL entries skipped) as left by the last absorption block. */
+int gfb_rays_get_absorbed(gfb_rays *r, double *const out[3]);
+/* The device-resident profile the last gfb_rays_trace_absorb accumulated into: buffer key in
+ * gfb_rays_ctx(r) (for gfb_allreduce_sum_f64 / gfb_copy_d2h) and its number of cells. */
+int gfb_rays_profile(gfb_rays *r, uint64_t *key, size_t *cells);
 /* Device pointer of state array `which` (GFB_T..GFB_KZ) or of the residual (which = GFB_NUM_STATE). */
 int gfb_rays_device_ptr(gfb_rays *r, int which, void **device_ptr);
 /* The underlying device context (timers, launch counters, deposit, ...). */

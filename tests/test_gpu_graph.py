@@ -170,6 +170,49 @@ def test_max_reduction_handles_sign_and_size(lib):
     lib.gfb_ctx_destroy(ctx)
 
 
+def test_max_reduction_ignores_nan_like_the_reference(lib):
+    """The reference's reduction is CUDA max() = fmax (cuda_context.hpp:973-985): NaN elements are ignored,
+    so one bad ray does not end workflow::converge_item for every other ray.  All-NaN and n == 0 give NaN."""
+    ctx = lib.gfb_ctx_create(0)
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=100000)
+    a[::977] = np.nan
+    out = ctypes.c_double(0)
+    assert lib.gfb_buffer(ctx, 7001, a.nbytes, a.ctypes.data_as(ctypes.c_void_p), None) == 0
+    assert lib.gfb_max(ctx, 7001, a.size, ctypes.byref(out)) == 0
+    assert out.value == np.nanmax(a)
+    b = np.full(1000, np.nan)
+    assert lib.gfb_buffer(ctx, 7002, b.nbytes, b.ctypes.data_as(ctypes.c_void_p), None) == 0
+    assert lib.gfb_max(ctx, 7002, b.size, ctypes.byref(out)) == 0 and np.isnan(out.value)
+    assert lib.gfb_max(ctx, 7002, 0, ctypes.byref(out)) == 0 and np.isnan(out.value)
+    lib.gfb_ctx_destroy(ctx)
+
+
+def test_converge_item_keeps_iterating_past_a_nan_ray(lib):
+    """Ensemble Newton (the reference's converge_item loop on the maximum residual) with one ray that can
+    only produce NaN: the other rays must still converge."""
+    from graph_framework_b200.rays import RayTracer
+    from graph_framework_b200 import workloads
+    n = 256
+    state = workloads.efit_ensemble(n, seed=21)
+    state["w"][17] = np.nan
+    tr = RayTracer("extra_ordinary_wave", "efit", n, 2.0e-5)
+    tr.set_state(state)
+    tr.init("kx", mode="ensemble")
+    got = tr.get_state(residual=False)
+    tr.close()
+    good = np.arange(n) != 17
+    clean = dict(state, w=np.where(good, state["w"], 700.0))
+    tr = RayTracer("extra_ordinary_wave", "efit", n, 2.0e-5)
+    tr.set_state(clean)
+    tr.init("kx", mode="ensemble")
+    ref = tr.get_state(residual=False)
+    tr.close()
+    assert np.isnan(got["kx"][17])
+    assert np.max(np.abs(got["kx"][good] - ref["kx"][good])/np.abs(ref["kx"][good])) < 1.0e-12
+    assert np.max(np.abs(ref["kx"][good] + 700.0)) > 1.0          # and the solve did move them
+
+
 def test_deposit_matches_oracle(lib):
     """Deposition histogram kernel vs the numpy restatement of utilities/bin.py:53-106."""
     import torch

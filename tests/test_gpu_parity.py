@@ -417,3 +417,32 @@ def test_pipelined_host_stepping_is_bit_identical(lib):
             for k in ORDER + ("residual",):
                 assert np.array_equal(out[k], ref[k]), (reps, chunks, k)
         tr.close()
+
+
+def test_host_stepping_after_device_stepping_sees_the_new_input(lib):
+    """gfb_rays_step_host right after gfb_rays_step on binned rays: the uploads must be ordered after the
+    compute stream's pending work (the step's stores and the scatter restoring the caller's order), or the
+    chunk kernels would start from the previous state."""
+    from graph_framework_b200.rays import RayTracer
+    from graph_framework_b200 import workloads
+    n = 400000
+    a = workloads.efit_ensemble(n, seed=31)
+    b = workloads.efit_ensemble(n, seed=32)
+    tr = RayTracer("extra_ordinary_wave", "efit", n, 2.0e-5)
+    tr.set_state(a)
+    tr.init("kx")
+    tr.compile()
+    kx_a = tr.get_state(residual=False)["kx"]
+    # reference result for input b (own Newton root needed: reuse a's kx as b's, any finite value will do)
+    b["kx"] = kx_a.copy()
+    tr.put_state(b)
+    tr.step(25)
+    ref = tr.get_state()
+    for _ in range(3):
+        tr.put_state(dict(a, kx=kx_a))
+        tr.step(300)                                    # long enough to be running (and binned) when step_host is called
+        out = {k: np.empty(n) for k in ORDER + ("residual",)}
+        tr.step_host(25, b, out, chunks=4)
+        for k in ORDER + ("residual",):
+            assert np.array_equal(out[k], ref[k]), k
+    tr.close()
