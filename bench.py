@@ -45,11 +45,14 @@ WORKLOADS = {
     "vmec_omode": ("ordinary_wave", "vmec", 1250000, 1.0e-4, 10000000),         # configs[3]: 10^7 rays / 8 GPUs
     "vmec_cold": ("cold_plasma", "vmec", 1250000, 1.0e-4, 10000000),
 }
-#  configs[2]: O-mode rays that cross the electron-cyclotron resonance within the timed blocks (dt 5e-4:
-#  0.05 of travel per block, resonance 0.44 from the launch point), device Newton, weak damping + power +
-#  deposition on a 64 x 64 x 128 grid over the EFIT box, one FP64 all-reduce of the profile per block.
-ABSORB = {"dispersion": "ordinary_wave", "equilibrium": "efit", "rays": 1000000, "dt": 5.0e-4, "total": 1000000,
-          "bins": (64, 64, 128), "lo": (0.84, -1.7, -1.6), "hi": (2.54, 1.7, 1.6)}
+#  configs[2]: O-mode rays launched at R = 2.3, just outside the electron-cyclotron resonance layer (Im k_amp
+#  rises from R ~ 2.2, peaks near 2.06; tests/golden/ref_absorb_ordinary_wave_efit.npz), device Newton, weak
+#  damping + power + deposition on a 64 x 64 x 128 grid over the EFIT box, one FP64 all-reduce of the block's
+#  profile per block.  dt 2e-4: 0.02 of travel per block of 100 steps; after `period` blocks (R ~ 2.02, most of
+#  the power absorbed; beyond the layer the weak-damping formula is not meaningful) the ensemble is put back on
+#  its launch circle, untimed, so that every timed block deposits.
+ABSORB = {"dispersion": "ordinary_wave", "equilibrium": "efit", "rays": 1000000, "dt": 2.0e-4, "total": 1000000,
+          "radius": 2.3, "period": 14, "bins": (64, 64, 128), "lo": (0.84, -1.7, -1.6), "hi": (2.54, 1.7, 1.6)}
 BORIS = {"particles": 20000000, "total": 100000000, "dt": 0.5}                  # configs[4]
 EXTRAS = ("efit_cold", "efit_absorb", "vmec_omode", "boris")
 EXTRA_STEPS, EXTRA_WARMUP = 3, 3
@@ -393,7 +396,7 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
     rays = shard(cfg["total"], ranks) if strong else cfg["rays"]
     total_rays = cfg["total"] if strong else rays*ranks.world
     bins, lo, hi = cfg["bins"], cfg["lo"], cfg["hi"]
-    state0 = workloads.efit_ensemble(rays, seed=ranks.rank)
+    state0 = workloads.efit_ensemble(rays, seed=ranks.rank, radius=cfg["radius"])
     tracer = RayTracer(cfg["dispersion"], cfg["equilibrium"], rays, cfg["dt"], device=ranks.local_rank,
                        options=("fused_steps=%d absorption=1 " % SUB_STEPS) + args.options)
     tracer.set_state(state0)
@@ -407,7 +410,16 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
     profile = torch.zeros(bins, dtype=torch.float64, device="cuda")         # running sum over blocks and ranks
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 
+    launch_circle = {k: pinned_empty(rays) for k in STATE}
+    for k in STATE:
+        launch_circle[k][:] = start[k]
+    done = [0]
+
     def block(timed):
+        if done[0] % cfg["period"] == 0 and done[0]:
+            tracer.put_state(launch_circle)                 # untimed: back to the launch circle, power = 1
+            tracer.absorption_reset()
+        done[0] += 1
         with torch.cuda.stream(stream):
             increment.zero_()
             if timed:
@@ -477,6 +489,7 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
         def e2e_step():
             tracer.put_state(host_in)                              # H2D of the 8 state arrays
             tracer.absorption_reset()
+            done[0] = 0
             block(False)
             with torch.cuda.stream(stream):
                 host_profile.copy_(increment, non_blocking=True)   # D2H of the reduced profile of the block
@@ -488,6 +501,7 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
             e2e_step()
         torch.cuda.synchronize()
         e2e_s = ranks.max(time.perf_counter() - t0)
+        del e2e_step, host_profile
         e2e = {"value": total_rays*SUB_STEPS*e2e_steps/e2e_s, "unit": "ray-steps/s", "h2d_bytes_per_step": 8*8*rays,
                "d2h_bytes_per_step": int(np.prod(bins))*8, "steps": e2e_steps,
                "api": "RayTracer.put_state + deposit_block + NCCL all-reduce + profile read-back"}
@@ -505,7 +519,8 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
                                    "deposition on %dx%dx%d bins, one NCCL FP64 all-reduce of the block's profile (%d bytes) per bench step"
                                    % (cfg["dispersion"], cfg["equilibrium"], SUB_STEPS, bins[0], bins[1], bins[2], cells*8),
                        "rays_per_gpu": rays, "rays_total": total_rays, "dt": cfg["dt"], "options": args.options,
-                       "state_larger_than_L2": rays*72 > 126e6},
+                       "launch_radius": cfg["radius"], "restart_every_blocks": cfg["period"],
+                       "l2": "state (72 MB) + absorption state (56 MB) + profile (4 MB) per GPU exceed the 126 MB L2 together; not flushed separately"},
             "collective": {"what": "torch.distributed all_reduce(SUM, float64) on NCCL, issued on the tracer's stream" if ranks.dist else "none at 1 GPU",
                            "bytes": cells*8, "ms_per_step": (total_ms_max - compute_ms_max)/steps,
                            "share_of_step": (total_ms_max - compute_ms_max)/total_ms_max,
@@ -516,6 +531,12 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
                                       workloads.FLOP_PER_RAY_STEP.get((cfg["dispersion"], cfg["equilibrium"])), peaks,
                                       workloads.STATE_BYTES_PER_RAY*rays),
         }
+    #  torch frees record events on the streams a tensor was used on: every tensor that touched the tracer's
+    #  stream must go before the tracer (and with it the stream) does.
+    del block, increment, profile, ev, stream, launch_circle
+    torch.cuda.synchronize()
+    import gc
+    gc.collect()
     tracer.close()
     return result
 

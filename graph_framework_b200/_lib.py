@@ -81,6 +81,7 @@ def _load():
                                       ctypes.POINTER(ctypes.c_int)]),
         "gfb_rays_absorption_reset": (I, [P]),
         "gfb_rays_deposit_block": (I, [P, SZ, P, c_double_p, c_double_p, ctypes.POINTER(I)]),
+        "gfb_rays_get_dt": (I, [P, c_double_p]),
         "gfb_rays_get_absorbed": (I, [P, ctypes.POINTER(c_double_p)]),
         "gfb_rays_profile": (I, [P, ctypes.POINTER(U64), ctypes.POINTER(SZ)]),
         "gfb_rays_set_binning": (I, [P, I, D, D, ctypes.c_uint, SZ]),
@@ -145,6 +146,7 @@ def _load():
         "graph_print": (None, [P, SZ, c_void_pp, SZ]),
         "graph_evaluate": (SZ, [P, P, c_double_p, SZ]),
         "graph_get_source": (S, [P]),
+        "graph_set_fast_division": (None, [P, ctypes.c_bool]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol

@@ -205,6 +205,9 @@ size_t graph_evaluate(graph_c_context *c, graph_node node, double *destination, 
     for (size_t i = 0; i < b.size() && i < capacity; i++) destination[i] = b[i];
     return b.size();
 }
+void graph_set_fast_division(graph_c_context *c, const bool on) {
+    cast(c)->manager().get_context().options.fast_division = on;
+}
 const char *graph_get_source(graph_c_context *c) {
     cast(c)->source = cast(c)->manager().get_context().get_source();
     return cast(c)->source.c_str();
@@ -278,6 +281,7 @@ struct tracer_base {
 
 //  Absorption attached to the solver's device context (absorption.hpp): state that the
 //  Runge-Kutta kernel leaves in HBM is read in place.
+    leaf_ptr step_variable;         // adaptive_rk4: the per-ray dt
     leaf_ptr kamp_re, kamp_im, x_last, y_last, z_last, power, k_sum;
     std::unique_ptr<absorption::weak_damping<>> damping;
     std::unique_ptr<absorption::power_item<>> deposition;
@@ -344,6 +348,13 @@ tracer_base *make_tracer(const std::string &solver_name, std::vector<leaf_ptr> &
     if (solver_name == "rk2") return new tracer<solver::rk2<DF, true>> (s, dt, eq, n, device, o);
     if (solver_name == "rk4_graph") return new tracer<solver::rk4<DF, false>> (s, dt, eq, n, device, o);
     if (solver_name == "rk2_graph") return new tracer<solver::rk2<DF, false>> (s, dt, eq, n, device, o);
+    if (solver_name == "adaptive_rk4") {
+//  dt becomes a per-ray variable that the solver's own Newton item rewrites before every step (solver.hpp:881-1006).
+        auto dt_var = graph::variable(n, dt->value, "dt");
+        auto t = new tracer<solver::adaptive_rk4<DF>> (s, dt_var, eq, n, device, o);
+        t->step_variable = dt_var;
+        return t;
+    }
     if (solver_name == "split_simplextic") {
 //  Only separable Hamiltonians (the constructor aborts otherwise, like the reference's assert).
         if constexpr (std::is_same<DF, dispersion::bohm_gross<>>::value || std::is_same<DF, dispersion::light_wave<>>::value ||
@@ -604,6 +615,12 @@ int gfb_rays_deposit_block(gfb_rays *r, size_t sub_steps, double *profile_device
     const double *zd = static_cast<const double *> (t.context().device_pointer(r->vars[GFB_Z]));
     const double *wd = static_cast<const double *> (t.context().device_pointer(d_power));
     return gfb_deposit(ctx, xd, yd, zd, wd, r->n, profile_device, lo, hi, bins);
+}
+int gfb_rays_get_dt(gfb_rays *r, double *out) {
+    if (!r->compiled) return rays_fail("get_dt before compile");
+    if (!r->impl->step_variable) return rays_fail("get_dt: only solver adaptive_rk4 has a per-ray step");
+    r->impl->work().copy_to_host(r->impl->step_variable, out);
+    return 0;
 }
 int gfb_rays_get_absorbed(gfb_rays *r, double *const out[3]) {
     if (!r->compiled) return rays_fail("get_absorbed before compile");

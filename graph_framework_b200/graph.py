@@ -123,6 +123,10 @@ class Context:
     def add_converge_item(self, inputs, outputs, setters, name, size, tol=1.0e-30, max_iter=1000):
         self._item(lib.graph_add_converge_item, inputs, outputs, setters, name, size, tol, max_iter)
 
+    def set_fast_division(self, on):
+        """graph_set_fast_division: False = IEEE division/sqrt and (x - offset)/scale table indices."""
+        lib.graph_set_fast_division(self.c, bool(on))
+
     def compile(self): lib.graph_compile(self.c)
     def pre_run(self): lib.graph_pre_run(self.c)
     def run(self): lib.graph_run(self.c)

@@ -186,6 +186,12 @@ class RayTracer:
         check(lib.gfb_rays_deposit_block(self.h, int(sub_steps), ctypes.c_void_p(int(profile_ptr)), lo_a, hi_a, bins_a),
               "deposit_block")
 
+    def get_dt(self):
+        """solver="adaptive_rk4": the per-ray step the solver chose last."""
+        out = np.empty(self.n, dtype=np.float64)
+        check(lib.gfb_rays_get_dt(self.h, out.ctypes.data_as(c_double_p)), "get_dt")
+        return out
+
     def get_absorbed(self):
         """Im k_amp, power and d_power of the last absorption block, in the caller's ray order."""
         arrs = [np.empty(self.n, dtype=np.float64) for _ in range(3)]
@@ -256,6 +262,9 @@ class RayTracer:
 
 class BorisPusher:
     """The xkorc step graph (graph_korc/xkorc.cpp:40-121) on one GPU."""
+
+    fp64_peak = RayTracer.fp64_peak
+    flush_l2 = RayTracer.flush_l2
 
     NAMES = ("x", "y", "z", "ux", "uy", "uz", "gamma")
 

@@ -31,9 +31,10 @@ def bench_rays(n):
     return s
 
 
-def efit_ensemble(n, seed=0):
+def efit_ensemble(n, seed=0, radius=2.5):
     """C2: the distribution of graph_driver/efit_example.sh (xrays.cpp:448-453 draw order
-    w, kx, ky, kz, z, then cylindrical x, y with radius 2.5 and angle ~ N(0, 0.05))."""
+    w, kx, ky, kz, z, then cylindrical x, y with radius 2.5 and angle ~ N(0, 0.05)).
+    `radius` moves the launch circle (the absorption workload starts just outside the resonance)."""
     rng = np.random.default_rng(seed)
     s = {"t": np.zeros(n)}
     s["w"] = rng.normal(700.0, 10.0, n)
@@ -42,8 +43,8 @@ def efit_ensemble(n, seed=0):
     s["kz"] = rng.normal(0.0, 10.0, n)
     s["z"] = rng.normal(0.0, 0.05, n)
     phi = rng.normal(0.0, 0.05, n)
-    s["x"] = 2.5*np.cos(phi)
-    s["y"] = 2.5*np.sin(phi)
+    s["x"] = radius*np.cos(phi)
+    s["y"] = radius*np.sin(phi)
     return s
 
 

@@ -101,6 +101,8 @@ int gfb_rays_absorption_reset(gfb_rays *r);
  * BASELINE.json: the per-GPU histogram that is summed over GPUs once per output block. */
 int gfb_rays_deposit_block(gfb_rays *r, size_t sub_steps, double *profile_device,
                            const double *lo, const double *hi, const int *bins);
+/* solver "adaptive_rk4" (solver.hpp:881-1006): the per-ray step length the solver's Newton item chose last. */
+int gfb_rays_get_dt(gfb_rays *r, double *out);
 /* Running absorption state in the caller's ray order: out[0..2] = Im k_amp, power, d_power
  * (num_rays doubles each, NULL entries skipped) as left by the last absorption block. */
 int gfb_rays_get_absorbed(gfb_rays *r, double *const out[3]);

@@ -109,6 +109,13 @@ void graph_print(STRUCT_TAG graph_c_context *c, const size_t index, graph_node *
  * (leaf_node::evaluate, node.hpp:378) and the emitted source text. */
 size_t graph_evaluate(STRUCT_TAG graph_c_context *c, graph_node node, double *destination, const size_t capacity);
 const char *graph_get_source(STRUCT_TAG graph_c_context *c);
+/* Extension: arithmetic mode of the kernels compiled for this context.  on (default): a/b is a times
+ * a refined hardware reciprocal (<= 1 ulp, but x/0 and x/inf give NaN where IEEE gives inf and 0), sqrt
+ * comes from rsqrt, and table indices use (x - offset)*(1/scale) -- what -ffast-math makes of the
+ * reference's own kernels (cpu_context.hpp:155-157; pinned cell by cell in tests/golden/ref_cells_efit.npz).
+ * off: IEEE division and sqrt, indices by (x - offset)/scale exactly as piecewise.hpp:26-65 is written.
+ * Call before graph_compile. */
+void graph_set_fast_division(STRUCT_TAG graph_c_context *c, const bool on);
 
 #ifdef __cplusplus
 }

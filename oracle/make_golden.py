@@ -133,6 +133,54 @@ def vmec_fd_case():
          dDdx=fd["x"], dDdy=fd["y"], dDdz=fd["z"], dDdw=fd["w"])
 
 
+def f3_cases():
+    """split_simplextic (solver.hpp:1017-1130) on the two separable Hamiltonians, and the first
+    steps of adaptive_rk4 (solver.hpp:882-1006).  The reference's adaptive rule -- Newton on (dt, lambda) of
+    1/dt + lambda D_next^2 -- is ill-posed: its own runs give |dt| ~ 1e13 or NaN from the second step on, so
+    only the first step (where some rays are finite) is recorded."""
+    n = 32
+    s = workloads.slab_ensemble(n, seed=6)
+    for disp in ("bohm_gross", "light_wave"):
+        per_step = reference.trace(disp, "no_magnetic_field", s, 1.0e-3, 5, save_every=1, init="kx", solver="split_simplextic")
+        long = reference.trace(disp, "no_magnetic_field", s, 1.0e-3, 200, save_every=100, init="kx", solver="split_simplextic")
+        save("ref_trace_%s_no_magnetic_field_split_simplextic" % disp, state=workloads.pack(s), dt=np.array(1.0e-3),
+             per_step=per_step, long=long)
+    a = workloads.slab_ensemble(n, seed=6)
+    a["w"][:] = 900.0
+    a["kx"][:] = 1000.0
+    a["ky"][:] = 0.25
+    a["kz"][:] = 0.15
+    a["x"] = np.linspace(-0.2, 0.2, n)
+    a["y"][:] = 0.0
+    a["z"][:] = 0.0
+    rec = reference.trace_adaptive("cold_plasma", "gaussian_density", a, 0.5e-4, 2, save_every=1, init="kx")
+    save("ref_trace_cold_plasma_gaussian_density_adaptive_rk4", state=workloads.pack(a), dt=np.array(0.5e-4), records=rec)
+
+
+def cells_case():
+    """Which cell the reference's compiled kernels select within a few ulp of every cell edge of the EFIT
+    R and Z grids (index work must be bit-exact: one cell off is a different polynomial)."""
+    from graph_framework_b200.tools.gfbt import read_gfbt
+    t = read_gfbt(os.path.join(OUT, "efit.gfbt"))
+    out = {}
+    for tag, off, scale, n in (("r", float(np.ravel(t["rmin"])[0]), float(np.ravel(t["dr"])[0]), 64),
+                               ("z", float(np.ravel(t["zmin"])[0]), float(np.ravel(t["dz"])[0]), 64),
+                               ("psi", float(np.ravel(t["psimin"])[0]), float(np.ravel(t["dpsi"])[0]), 138)):
+        edges = off + scale*np.arange(-1, n + 2)
+        xs = [edges]
+        up, down = edges.copy(), edges.copy()
+        for _ in range(3):
+            up, down = np.nextafter(up, np.inf), np.nextafter(down, -np.inf)
+            xs += [up.copy(), down.copy()]
+        rng = np.random.default_rng(17)
+        xs.append(rng.uniform(off - scale, off + (n + 1)*scale, 2000))
+        x = np.concatenate(xs)
+        out["x_" + tag] = x
+        out["grid_" + tag] = np.array([scale, off, n])
+        out["cell_" + tag] = reference.cells(x, scale, off, n)
+    save("ref_cells_efit", **out)
+
+
 def defect_case():
     """Evidence for the reference's symbolic dD/dz defect (cold_plasma in a z-dependent field):
     its own D at z +- h and w +- h next to its own symbolic dkz/dt."""
@@ -175,6 +223,10 @@ if __name__ == "__main__":
         trace_cases()
     if "bench" in which:
         bench_case()
+    if "f3" in which:
+        f3_cases()
+    if "cells" in which:
+        cells_case()
     if "interior" in which:
         interior_case()
     if "korc" in which:

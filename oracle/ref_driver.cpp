@@ -14,6 +14,8 @@
 //       out.bin: record 0 = state after init (9 arrays: t,w,x,y,z,kx,ky,kz,residual[=0]),
 //                then one record after every <save_every> steps (residual = D^2 at
 //                the pre-step state of the last step, solver.hpp:316-319).
+//       solver adaptive_rk4: dt is the initial value of the per-ray step variable; every record holds a tenth
+//       array, the current dt.
 //   ref_driver rhs <dispersion> <equilibrium> <N> <in.bin> <out.bin>
 //       out.bin: 7 arrays dxdt,dydt,dzdt,dkxdt,dkydt,dkzdt,D  (dispersion.hpp:1387-1433)
 //   ref_driver bench <dispersion> <equilibrium> <N> <dt> <nsteps> <threads> <in.bin|-> [blocks]
@@ -31,6 +33,10 @@
 //                does; power/d_power follow the bin_power stage (xrays.cpp:674-793, T = double) fed
 //                with Im kamp (reference_imag_variable, xrays.cpp:743).  Record 0 holds power = 1,
 //                d_power = 0 (the state before the first bin_power kernel).
+//   ref_driver cells <N> <scale> <offset> <ncells> <in.bin> <out.bin>
+//       which table cell the reference's compiled kernel picks: piecewise_1D over the table
+//       [0, 1, ..., ncells - 1] evaluated through its own JIT path (g++ -O3 -ffast-math, as
+//       cpu_context.hpp:155-157 compiles) at N arguments; out = N doubles (the cell numbers).
 //   ref_driver reducer
 //       the reference's reducer defect behind its wrong cold-plasma dD/dz, with four plain variables:
 //       ((A W)^2 B)/(C^2 W^4) built from graph nodes, evaluated by the reference's host evaluate(), next
@@ -148,6 +154,50 @@ static int trace_impl(int argc, char **argv) {
             solve.sync_host();
             for (size_t r = 0; r < n; r++) residual[r] = solve.check_residual(r);
             write_record(out, s, residual);
+        }
+    }
+    return 0;
+}
+
+//  solver::adaptive_rk4 (solver.hpp:881-1006): dt is a per-ray VARIABLE that the solver's own Newton item
+//  rewrites before every step; records carry it as a tenth array.
+template<class D>
+static int trace_adaptive_impl(int argc, char **argv) {
+    const std::string eqn = argv[3];
+    const size_t n = std::stoul(argv[5]);
+    const double dt = std::stod(argv[6]);
+    const size_t nsteps = std::stoul(argv[7]);
+    const size_t every = std::stoul(argv[8]);
+    const std::string init = argv[9];
+    auto in = read_arrays(argv[10], 8, n);
+    std::ofstream out(argv[11], std::ios::binary);
+    state_vars s(n);
+    s.set(in, 0, n);
+    auto eq = make_eq(eqn);
+    auto dtv = graph::variable<T> (n, "dt");
+    graph::variable_cast(dtv)->set(static_cast<T> (dt));
+    struct open_solver : public solver::adaptive_rk4<D> {           // `work` is protected; nothing else is touched
+        using solver::adaptive_rk4<D>::adaptive_rk4;
+        void read(leaf node, T *destination) { this->work.copy_to_host(node, destination); }
+    };
+    open_solver solve(s.w, s.kx, s.ky, s.kz, s.x, s.y, s.z, s.t, dtv, eq, "", n, 0);
+    if (init == "none") solve.init();
+    else solve.init(s.by_name(init));
+    std::vector<double> residual(n, 0.0);
+    auto record = [&] {
+        write_record(out, s, residual);
+        auto var = graph::variable_cast(dtv);
+        out.write(reinterpret_cast<const char *> (var->data()), sizeof(double)*n);
+    };
+    record();
+    solve.compile();
+    for (size_t i = 1; i <= nsteps; i++) {
+        solve.step();
+        if (i%every == 0 || i == nsteps) {
+            solve.sync_host();
+            solve.read(dtv, graph::variable_cast(dtv)->data());
+            for (size_t r = 0; r < n; r++) residual[r] = solve.check_residual(r);
+            record();
         }
     }
     return 0;
@@ -465,7 +515,32 @@ static int erfi_values(int argc, char **argv) {
     if (DNAME == "bohm_gross" && SNAME == "rk4") return FN<solver::rk4<dispersion::bohm_gross<T>>> (argc, argv);            \
     if (DNAME == "simple" && SNAME == "rk4") return FN<solver::rk4<dispersion::simple<T>>> (argc, argv);                    \
     if (DNAME == "cold_plasma" && SNAME == "rk2") return FN<solver::rk2<dispersion::cold_plasma<T>>> (argc, argv);          \
-    if (DNAME == "simple" && SNAME == "rk2") return FN<solver::rk2<dispersion::simple<T>>> (argc, argv);
+    if (DNAME == "simple" && SNAME == "rk2") return FN<solver::rk2<dispersion::simple<T>>> (argc, argv);                    \
+    if (DNAME == "bohm_gross" && SNAME == "split_simplextic") return FN<solver::split_simplextic<dispersion::bohm_gross<T>>> (argc, argv); \
+    if (DNAME == "light_wave" && SNAME == "split_simplextic") return FN<solver::split_simplextic<dispersion::light_wave<T>>> (argc, argv); \
+    if (DNAME == "light_wave" && SNAME == "rk4") return FN<solver::rk4<dispersion::light_wave<T>>> (argc, argv);
+
+//  The cell a compiled reference kernel selects (piecewise.hpp:26-65 under -ffast-math).
+static int cells(int argc, char **argv) {
+    const size_t n = std::stoul(argv[2]);
+    const double scale = std::stod(argv[3]), offset = std::stod(argv[4]);
+    const size_t ncells = std::stoul(argv[5]);
+    auto in = read_arrays(argv[6], 1, n);
+    std::ofstream out(argv[7], std::ios::binary);
+    auto x = graph::variable<T> (n, "x");
+    graph::variable_cast(x)->set(in[0]);
+    std::vector<T> ids(ncells);
+    for (size_t i = 0; i < ncells; i++) ids[i] = static_cast<T> (i);
+    auto cell = graph::piecewise_1D<T> (ids, x, scale, offset);
+    workflow::manager<T> work(0);
+    work.add_item({graph::variable_cast(x)}, {cell}, {}, graph::shared_random_state<T> (), "cells_kernel", n);
+    work.compile();
+    work.run();
+    std::vector<double> buf(n);
+    work.copy_to_host(cell, buf.data());
+    out.write(reinterpret_cast<const char *> (buf.data()), sizeof(double)*n);
+    return 0;
+}
 
 //  Minimal reproduction of the reducer rule at fault.
 static int reducer_defect() {
@@ -501,6 +576,8 @@ int main(int argc, char **argv) {
     const std::string mode = argv[1];
     if (mode == "trace" && argc == 12) {
         const std::string d = argv[2], s = argv[4];
+        if (s == "adaptive_rk4" && d == "cold_plasma") return trace_adaptive_impl<dispersion::cold_plasma<T>> (argc, argv);
+        if (s == "adaptive_rk4" && d == "ordinary_wave") return trace_adaptive_impl<dispersion::ordinary_wave<T>> (argc, argv);
         DISPATCH_SOLVER(trace_impl, d, s)
     } else if (mode == "bench" && (argc == 9 || argc == 10)) {
         const std::string d = argv[2], s = "rk4";
@@ -520,6 +597,8 @@ int main(int argc, char **argv) {
 #endif
     } else if (mode == "erfi" && argc == 5) {
         return erfi_values(argc, argv);
+    } else if (mode == "cells" && argc == 8) {
+        return cells(argc, argv);
     } else if (mode == "reducer") {
         return reducer_defect();
     }

@@ -53,6 +53,17 @@ def trace(dispersion, equilibrium, state, dt, nsteps, save_every=None, init="kx"
         return np.fromfile(fout).reshape(-1, 9, n)
 
 
+def trace_adaptive(dispersion, equilibrium, state, dt, nsteps, save_every=1, init="kx"):
+    """solver::adaptive_rk4: records [records, 10, N] = t, w, x, y, z, kx, ky, kz, residual, dt (per ray)."""
+    arr = _pack(state)
+    n = arr.shape[1]
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        arr.tofile(fin)
+        _run(["trace", dispersion, equilibrium, "adaptive_rk4", n, repr(float(dt)), nsteps, save_every, init or "none", fin, fout])
+        return np.fromfile(fout).reshape(-1, 10, n)
+
+
 def rhs(dispersion, equilibrium, state):
     """dxdt, dydt, dzdt, dkxdt, dkydt, dkzdt, D  as a [7, N] array."""
     arr = _pack(state)
@@ -114,3 +125,13 @@ def reducer_defect():
     """The four-variable reproduction of the reducer rule behind the reference's wrong cold-plasma
     dD/dz (ref_driver reducer); tests/golden/ref_reducer_defect.json is its committed output."""
     return json.loads(_run(["reducer"]).strip().splitlines()[-1])
+
+
+def cells(x, scale, offset, ncells):
+    """Table cell the reference's compiled kernel selects for each argument (ref_driver cells)."""
+    arr = np.ascontiguousarray(x, dtype=np.float64)
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        arr.tofile(fin)
+        _run(["cells", arr.size, repr(float(scale)), repr(float(offset)), ncells, fin, fout])
+        return np.fromfile(fout)

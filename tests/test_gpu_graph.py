@@ -154,6 +154,36 @@ def test_piecewise_kernels_match_host(g):
     assert "gfb::smem" in src and "__ldg" in src
 
 
+@pytest.mark.parametrize("fast", [True, False])
+def test_cell_selection_at_cell_edges_matches_the_reference(lib, fast):
+    """Index work must be bit-exact.  7925 arguments on, and 1-3 ulp either side of, every cell edge of the
+    EFIT R, Z and psi grids (plus random ones): the default kernels pick exactly the cell the reference's own
+    compiled kernels pick (tests/golden/ref_cells_efit.npz from `ref_driver cells`; under -ffast-math they
+    multiply by 1/scale and differ from the written rule in 78 of these arguments); with
+    graph_set_fast_division(false) the kernels follow (x - offset)/scale as piecewise.hpp:26-65 is written."""
+    from graph_framework_b200.graph import Context
+    from conftest import golden
+    g = golden("ref_cells_efit")
+    differ = 0
+    for tag in ("r", "z", "psi"):
+        x = g["x_" + tag]
+        scale, off, n = g["grid_" + tag]
+        n = int(n)
+        c = Context()
+        c.set_fast_division(fast)
+        xv = c.variable(x.size, "x", x)
+        cell = c.piecewise_1D(xv, scale, off, np.arange(n, dtype=np.float64))
+        c.add_item([xv], [cell], [], "cells", x.size)
+        c.compile()
+        c.run()
+        got = c.copy_to_host(cell, x.size)
+        c.close()
+        written = np.trunc(np.clip((x - off)/scale, 0, n - 1))
+        differ += int((g["cell_" + tag] != written).sum())
+        assert np.array_equal(got, g["cell_" + tag] if fast else written), (tag, fast)
+    assert differ >= 50          # the two rules are distinguishable on this set
+
+
 def test_max_reduction_handles_sign_and_size(lib):
     """cuda_context.hpp:954-995 replacement: grid-wide maximum, any sign, ragged sizes."""
     ctx = lib.gfb_ctx_create(0)

@@ -41,3 +41,17 @@ def test_reference_front_end_on_b200_context(disp, eq, solver):
     for rec in range(ref.shape[0]):
         for i in range(8):
             assert rel_dev(got[rec][i], ref[rec][i]) < 1.0e-11, (rec, i, rel_dev(got[rec][i], ref[rec][i]))
+
+
+C_BINDING_TEST = os.path.join(ROOT, "integration", "_build", "c_binding_reference_test")
+
+
+@pytest.mark.skipif(not os.path.exists(C_BINDING_TEST), reason="integration/_build not built (needs the reference tree)")
+def test_reference_c_binding_test_passes_on_libgfb200():
+    """The reference's own graph_tests/c_binding_test.c with its own header, unmodified, linked against
+    libgfb200.so: run_tests(DOUBLE, false) asserts node identity after reduction, the line
+    example and its four derivatives, the converge item, piecewise_1D/2D and index_1D/2D.  (The off-path
+    random/complex entry points are supplied by integration/c_binding_reference_test.c, see there.)"""
+    out = subprocess.run([C_BINDING_TEST], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all assertions passed" in out.stdout
