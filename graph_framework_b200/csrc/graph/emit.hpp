@@ -48,6 +48,13 @@ namespace jit {
         bool raw = false;               ///< packed was filled by the emitter (Fourier tables), do not repack
         int alias_input = -1;           ///< >= 0: no table of its own, the pointer of that kernel input (index_1D/2D)
         bool mode_table = false;        ///< the small [mode][xm, xn, row start, 0] table of a Fourier loop
+///  Cubic-spline families (graph::spline_1d / spline_2d): one group per (table, arguments); `orders` are
+///  the derivative orders (a, b) this kernel needs; all of them come out of ONE pass over the cell's row.
+        bool spline = false;
+        graph::table_ptr spline_table;
+        std::set<std::pair<unsigned, unsigned>> orders;
+        std::vector<const graph::leaf_node *> spline_nodes;     ///< in scan order (deterministic kernel text)
+        bool emitted = false;
         size_t bytes() const { return packed.size()*sizeof(double); }
     };
 
@@ -260,13 +267,43 @@ namespace jit {
                 if (n->op == graph::op_t::index_2d) scan(n->args[2].get());
                 return;
             }
+            if (n->is_spline()) {
+                const graph::leaf_node *a0 = strip(n->args[0].get());
+                const graph::leaf_node *a1 = n->args[1].get() ? strip(n->args[1].get()) : nullptr;
+                const graph::spline_order o = graph::spline_order::unpack(n->num_cols);
+                size_t g = 0;
+                for (; g < info.groups.size(); g++) {
+                    auto &grp = info.groups[g];
+                    if (grp.spline && grp.op == n->op && grp.spline_table == n->table && grp.arg0.get() == a0 &&
+                        grp.arg1.get() == a1 && grp.scale == n->scale && grp.offset == n->offset) break;
+                }
+                if (g == info.groups.size()) {
+                    table_group grp;
+                    grp.op = n->op;
+                    grp.arg0 = std::const_pointer_cast<graph::leaf_node> (a0->shared_from_this());
+                    if (a1) grp.arg1 = std::const_pointer_cast<graph::leaf_node> (a1->shared_from_this());
+                    grp.num_cols = o.columns;
+                    grp.scale = n->scale;
+                    grp.offset = n->offset;
+                    grp.stride = n->op == graph::op_t::spline_2d ? 16 : 4;
+                    grp.cells = n->table->values.size()/grp.stride;
+                    grp.raw = true;
+                    grp.spline = true;
+                    grp.spline_table = n->table;
+                    grp.packed = n->table->values;
+                    info.groups.push_back(grp);
+                }
+                info.groups[g].orders.insert({o.a, o.b});
+                info.groups[g].spline_nodes.push_back(n);
+                slot[n] = {g, 0};
+            }
             if (n->is_piecewise()) {
                 const graph::leaf_node *a0 = strip(n->args[0].get());
                 const graph::leaf_node *a1 = n->args[1].get() ? strip(n->args[1].get()) : nullptr;
                 size_t g = 0;
                 for (; g < info.groups.size(); g++) {
                     auto &grp = info.groups[g];
-                    if (grp.op == n->op && grp.arg0.get() == a0 && grp.arg1.get() == a1 &&
+                    if (!grp.spline && grp.op == n->op && grp.arg0.get() == a0 && grp.arg1.get() == a1 &&
                         grp.num_cols == n->num_cols && grp.scale == n->scale && grp.offset == n->offset &&
                         grp.cells == n->table->values.size()) break;
                 }
@@ -329,7 +366,7 @@ namespace jit {
                 if (g.raw) {
 //  Fourier tables keep their layout; the small [mode][4] mode-number table is staged.
                     if (g.packed.size() & 1) g.packed.push_back(0.0);
-                    g.staged = opt.stage_tables && g.mode_table && g.bytes() <= opt.stage_limit_bytes &&
+                    g.staged = opt.stage_tables && (g.mode_table || g.spline) && g.bytes() <= opt.stage_limit_bytes &&
                                staged_total + g.bytes() <= opt.stage_total_bytes;
                     if (g.staged) {
                         g.smem_offset = offset;
@@ -365,10 +402,13 @@ namespace jit {
         }
 
         std::string index_expr(const std::string &x, const double scale, const double offset, const size_t n) {
-//  The reference's contract: (uint)min(max((x - offset)/scale, 0), n - 1)  (piecewise.hpp:26-65).
+//  The reference's contract: (uint)min(max((x - offset)/scale, 0), n - 1)  (piecewise.hpp:26-65).  The clamp
+//  is done on the integer side: the saturating conversion cvt.rzi.u32.f64 already maps everything below
+//  zero (and NaN, which the reference's max(x, 0) also turns into 0) to 0, so min(trunc_sat(u), n - 1) is the
+//  same cell for every double u -- one FP64-pipe instruction instead of two compares and a conversion.
             const std::string u = opt.fast_division ? "(" + x + " - " + literal(offset) + ")*" + literal(1.0/scale)
                                                     : "(" + x + " - " + literal(offset) + ")/" + literal(scale);
-            return "static_cast<unsigned> (fmin(fmax(" + u + ", 0.0), " + literal(static_cast<double> (n - 1)) + "))";
+            return "min(__double2uint_rz(" + u + "), " + std::to_string(n - 1) + "u)";
         }
 
         std::string group_pointer(const size_t g) {
@@ -497,6 +537,103 @@ namespace jit {
             out << "        }" << std::endl;
         }
 
+//  Every needed member of a spline family in one pass over the cell's coefficients (see graph::spline_2d):
+//  per power of u the cubic in z and its derivatives by the Horner chain and its derivative recurrences,
+//  then the same in u.  Members not asked for cost nothing.
+        void emit_spline(const size_t g) {
+            auto &grp = info.groups[g];
+            if (grp.emitted) return;
+            grp.emitted = true;
+            using graph::op_t;
+            const bool two = grp.op == op_t::spline_2d;
+            const std::string id = std::to_string(g);
+            const std::string x = emit(grp.arg0.get());
+            const std::string z = two ? emit(grp.arg1.get()) : x;
+            std::string cell;
+            if (two) {
+                cell = index_expr(x, grp.scale[0], grp.offset[0], grp.cells/grp.num_cols) + "*" + std::to_string(grp.num_cols) + "u + " +
+                       index_expr(z, grp.scale[1], grp.offset[1], grp.num_cols);
+            } else {
+                cell = index_expr(x, grp.scale[0], grp.offset[0], grp.cells);
+            }
+            out << "        const double2 *sr" << id << " = reinterpret_cast<const double2 *> (" << group_pointer(g) << " + (" << cell << ")*"
+                << grp.stride << "u);" << std::endl;
+            info.num_statements++;
+//  Which derivative orders along each direction are needed.
+            std::set<unsigned> zorders;
+            for (auto &o : grp.orders) zorders.insert(two ? o.second : o.first);
+            auto need = [] (const std::set<unsigned> &set, std::initializer_list<unsigned> any) {
+                for (unsigned v : any) if (set.count(v)) return true;
+                return false;
+            };
+//  Chain + recurrences over coefficients k0..k3 (names) in variable `v`; returns the register of each order
+//  WITHOUT the factors 2 and 6 of the second and third derivative.
+            auto chain = [&] (const std::string &tag, const std::string &v, const std::array<std::string, 4> &k,
+                              const std::set<unsigned> &orders) {
+                std::array<std::string, 4> result;
+                auto line = [&] (const std::string &name, const std::string &expr) {
+                    out << "        const double " << name << " = " << expr << ";" << std::endl;
+                    info.num_statements++;
+                };
+                if (need(orders, {0, 1, 2})) line(tag + "p1", "fma(" + v + ", " + k[3] + ", " + k[2] + ")");
+                if (need(orders, {0, 1})) line(tag + "p2", "fma(" + v + ", " + tag + "p1, " + k[1] + ")");
+                if (need(orders, {0})) { line(tag + "p3", "fma(" + v + ", " + tag + "p2, " + k[0] + ")"); result[0] = tag + "p3"; }
+                if (need(orders, {1, 2})) line(tag + "q1", "fma(" + v + ", " + k[3] + ", " + tag + "p1)");
+                if (need(orders, {1})) { line(tag + "q2", "fma(" + v + ", " + tag + "q1, " + tag + "p2)"); result[1] = tag + "q2"; }
+                if (need(orders, {2})) { line(tag + "s1", "fma(" + v + ", " + k[3] + ", " + tag + "q1)"); result[2] = tag + "s1"; }
+                if (need(orders, {3})) result[3] = k[3];
+                return result;
+            };
+            const size_t pairs = grp.stride/2;
+            for (size_t p = 0; p < pairs; p++) {
+                out << "        const double2 sk" << id << "_" << p << " = " << (grp.staged ? "sr" + id + "[" + std::to_string(p) + "]"
+                                                                                           : "__ldg(sr" + id + " + " + std::to_string(p) + ")")
+                    << ";" << std::endl;
+                info.num_statements++;
+            }
+            auto coefficient = [&] (const size_t index) {
+                return "sk" + id + "_" + std::to_string(index/2) + (index & 1 ? ".y" : ".x");
+            };
+            static const double factorial[4] = {1.0, 1.0, 2.0, 6.0};
+            if (!two) {
+                const auto r = chain("s" + id + "_", x, {coefficient(0), coefficient(1), coefficient(2), coefficient(3)}, zorders);
+                for (const graph::leaf_node *node : grp.spline_nodes) {
+                    if (reg.count(node)) continue;
+                    const unsigned a = graph::spline_order::unpack(node->num_cols).a;
+                    const std::string name = "t" + std::to_string(node->id);
+                    out << "        const double " << name << " = " << (a >= 2 ? literal(factorial[a]) + "*" : std::string()) << r[a] << ";" << std::endl;
+                    info.num_statements++;
+                    reg.emplace(node, name);
+                }
+                return;
+            }
+//  u = (r - offset)/scale as a multiplication, like every division by a constant in this front end.
+            const double inv = 1.0/grp.scale[0];
+            out << "        const double su" << id << " = (" << x << " - " << literal(grp.offset[0]) << ")*" << literal(inv) << ";" << std::endl;
+            info.num_statements++;
+            std::array<std::array<std::string, 4>, 4> rows;      // rows[i][b]: d^b/dz^b of the cubic multiplying u^i
+            for (size_t i = 0; i < 4; i++) {
+                rows[i] = chain("s" + id + "_" + std::to_string(i), z,
+                                {coefficient(4*i), coefficient(4*i + 1), coefficient(4*i + 2), coefficient(4*i + 3)}, zorders);
+            }
+            for (const unsigned b : zorders) {
+                std::set<unsigned> uorders;
+                for (auto &o : grp.orders) if (o.second == b) uorders.insert(o.first);
+                const auto r = chain("s" + id + "_u" + std::to_string(b), "su" + id, {rows[0][b], rows[1][b], rows[2][b], rows[3][b]}, uorders);
+                for (const graph::leaf_node *node : grp.spline_nodes) {
+                    if (reg.count(node)) continue;
+                    const graph::spline_order o = graph::spline_order::unpack(node->num_cols);
+                    if (o.b != b) continue;
+                    double factor = factorial[o.b]*factorial[o.a];
+                    for (unsigned i = 0; i < o.a; i++) factor *= inv;
+                    const std::string name = "t" + std::to_string(node->id);
+                    out << "        const double " << name << " = " << (factor != 1.0 ? literal(factor) + "*" : std::string()) << r[o.a] << ";" << std::endl;
+                    info.num_statements++;
+                    reg.emplace(node, name);
+                }
+            }
+        }
+
         const std::string &emit(const graph::leaf_node *n) {
             n = strip(n);
             auto found = reg.find(n);
@@ -513,6 +650,10 @@ namespace jit {
             }
             if (n->op == op_t::fourier) {
                 emit_fourier_loop(floops[floop_of.at(n)]);
+                return reg.at(n);
+            }
+            if (n->is_spline()) {
+                emit_spline(slot.at(n).first);
                 return reg.at(n);
             }
             if (n->is_index()) {

@@ -224,17 +224,28 @@ namespace equilibrium {
 ///  physical coordinate (equilibrium.hpp:1121-1133).  The rewrite happens in
 ///  table space (fold_tables_scope), giving four tables on the same cells.
 //------------------------------------------------------------------------------
+    inline std::array<leaf_ptr, 4> fold_1D_spline(graph::output_nodes<> c, const double scale, const double offset) {
+        graph::fold_tables_scope fold;
+        const double s2 = scale*scale, s3 = scale*scale*scale;
+        std::array<leaf_ptr, 4> k;
+        k[3] = c[3]/s3;
+        k[2] = c[2]/s2 - 3.0*offset*c[3]/s3;
+        k[1] = c[1]/scale - 2.0*offset*c[2]/s2 + 3.0*offset*offset*c[3]/s3;
+        k[0] = c[0] - offset*c[1]/scale + offset*offset*c[2]/s2 - offset*offset*offset*c[3]/s3;
+        return k;
+    }
     inline leaf_ptr build_1D_spline(graph::output_nodes<> c, leaf_ptr x, const double scale, const double offset) {
-        leaf_ptr c0, c1, c2, c3;
-        {
-            graph::fold_tables_scope fold;
-            const double s2 = scale*scale, s3 = scale*scale*scale;
-            c3 = c[3]/s3;
-            c2 = c[2]/s2 - 3.0*offset*c[3]/s3;
-            c1 = c[1]/scale - 2.0*offset*c[2]/s2 + 3.0*offset*offset*c[3]/s3;
-            c0 = c[0] - offset*c[1]/scale + offset*offset*c[2]/s2 - offset*offset*offset*c[3]/s3;
-        }
-        return graph::fma(graph::fma(graph::fma(c3, x, c2), x, c1), x, c0);
+        const auto k = fold_1D_spline(c, scale, offset);
+        return graph::fma(graph::fma(graph::fma(k[3], x, k[2]), x, k[1]), x, k[0]);
+    }
+
+///  Whether tabulated equilibria build their cubics as graph::spline_1d / spline_2d nodes (one node per
+///  evaluated quantity, closed under df(); all derivative orders a kernel needs come out of one pass over
+///  the cell's coefficients) or as the reference's Horner chains of piecewise nodes (build_1D_spline,
+///  build_psi), differentiated link by link.  Same mathematics; GFB_SPLINE_NODES=0 selects the chains.
+    inline bool &spline_nodes() {
+        static thread_local bool on = !(std::getenv("GFB_SPLINE_NODES") && std::getenv("GFB_SPLINE_NODES")[0] == '0');
+        return on;
     }
 
 //------------------------------------------------------------------------------
@@ -257,23 +268,27 @@ namespace equilibrium {
         vector_ptr b_cache;
 
         leaf_ptr profile(const std::array<std::vector<double>, 4> &c, leaf_ptr psi) {
-            return build_1D_spline({graph::piecewise_1D(c[0], psi, tab.dpsi, tab.psimin),
-                                    graph::piecewise_1D(c[1], psi, tab.dpsi, tab.psimin),
-                                    graph::piecewise_1D(c[2], psi, tab.dpsi, tab.psimin),
-                                    graph::piecewise_1D(c[3], psi, tab.dpsi, tab.psimin)},
-                                   psi, tab.dpsi, tab.psimin);
+            graph::output_nodes<> raw = {graph::piecewise_1D(c[0], psi, tab.dpsi, tab.psimin),
+                                         graph::piecewise_1D(c[1], psi, tab.dpsi, tab.psimin),
+                                         graph::piecewise_1D(c[2], psi, tab.dpsi, tab.psimin),
+                                         graph::piecewise_1D(c[3], psi, tab.dpsi, tab.psimin)};
+            if (spline_nodes()) return graph::spline_1d(fold_1D_spline(raw, tab.dpsi, tab.psimin), psi);
+            return build_1D_spline(raw, psi, tab.dpsi, tab.psimin);
         }
 
 ///  equilibrium.hpp:1279-1313.
         leaf_ptr build_psi(leaf_ptr r, leaf_ptr z) {
             std::array<leaf_ptr, 4> c;
+            std::array<std::array<leaf_ptr, 4>, 4> folded;
             for (size_t i = 0; i < 4; i++) {
                 graph::output_nodes<> row;
                 for (size_t j = 0; j < 4; j++) {
                     row.push_back(graph::piecewise_2D(tab.psi[i][j], tab.num_cols, r, tab.dr, tab.rmin, z, tab.dz, tab.zmin));
                 }
-                c[i] = build_1D_spline(row, z, tab.dz, tab.zmin);
+                if (spline_nodes()) folded[i] = fold_1D_spline(row, tab.dz, tab.zmin);
+                else c[i] = build_1D_spline(row, z, tab.dz, tab.zmin);
             }
+            if (spline_nodes()) return graph::spline_2d(folded, r, z);
             auto r_norm = (r - tab.rmin)/tab.dr;
             return ((c[3]*r_norm + c[2])*r_norm + c[1])*r_norm + c[0];
         }

@@ -91,7 +91,8 @@ namespace graph {
         piecewise_1d, piecewise_2d,
         fourier,
         erfi, nan_to_zero,
-        index_1d, index_2d
+        index_1d, index_2d,
+        spline_1d, spline_2d
     };
 
     class leaf_node;
@@ -162,7 +163,7 @@ namespace graph {
                 case op_t::constant: case op_t::variable: return 0;
                 case op_t::pseudo: case op_t::sqrt: case op_t::exp: case op_t::log:
                 case op_t::sin: case op_t::cos: case op_t::piecewise_1d: case op_t::erfi:
-                case op_t::nan_to_zero: return 1;
+                case op_t::nan_to_zero: case op_t::spline_1d: return 1;
                 case op_t::fma: case op_t::fourier: case op_t::index_2d: return 3;
                 default: return 2;
             }
@@ -172,6 +173,7 @@ namespace graph {
         bool is_constant(const double v) const { return op == op_t::constant && value == v; }
         bool is_piecewise() const { return op == op_t::piecewise_1d || op == op_t::piecewise_2d; }
         bool is_index() const { return op == op_t::index_1d || op == op_t::index_2d; }
+        bool is_spline() const { return op == op_t::spline_1d || op == op_t::spline_2d; }
 
 //  -- reference API -----------------------------------------------------------
 ///  Host evaluation (node.hpp:378 evaluate()).
@@ -721,6 +723,116 @@ namespace graph {
     }
 
 //------------------------------------------------------------------------------
+///  Cubic splines as ONE node per evaluated quantity -- the EFIT equilibrium's building blocks
+///  (equilibrium.hpp:1121-1133 build_1D_spline, :1279-1313 build_psi).
+///
+///      G[a](x)       = d^a/dx^a      sum_j   c_j  x^j                    (cell picked by x)
+///      F[a, b](r, z) = d^(a+b)/dr^a dz^b  sum_ij c_ij u^i z^j,  u = (r - offset_r)/scale_r  (cell by r, z)
+///
+///  with the cell's coefficients folded to the physical argument exactly as build_1D_spline does
+///  (F: folded in z, normalised in r, like build_psi).  Coefficients are constant within a cell, so --
+///  like a piecewise node's -- their derivative is zero and each family is closed under df() and
+///  gradient(): the ray equations need psi, its two first and three second derivatives, and the emitter
+///  evaluates all six in one pass over the cell's 16 coefficients (38 FMAs) instead of differentiating
+///  through the Horner chains (the reference ends up with 90 folded tables; reverse mode through the
+///  chains costs ~3x the direct form).  num_cols packs (a, b, columns of the 2-D grid).
+///
+///  Evaluation order, shared by host and device so they agree to the last bit except for FMA
+///  contraction: value and first derivative follow the Horner chain and its derivative recurrence
+///  (the forms df() gives the reference), the second derivative extends the recurrence once more:
+///      p1 = x k3 + k2, p2 = x p1 + k1, p3 = x p2 + k0          value
+///      q1 = x k3 + p1, q2 = x q1 + p2                          first derivative
+///      s1 = x k3 + q1                                          second derivative = 2 s1, third = 6 k3
+//------------------------------------------------------------------------------
+    struct spline_order {
+        unsigned a, b;
+        size_t columns;
+        size_t pack() const { return a | (b << 8) | (columns << 16); }
+        static spline_order unpack(const size_t p) {
+            return {static_cast<unsigned> (p & 255), static_cast<unsigned> ((p >> 8) & 255), p >> 16};
+        }
+    };
+    namespace detail {
+///  d^a/dx^a of the cubic with coefficients k[0..3] (powers 0..3).
+        inline double cubic(const double *k, const double x, const unsigned a) {
+            const double p1 = std::fma(x, k[3], k[2]);
+            if (a == 3) return 6.0*k[3];
+            const double q1 = std::fma(x, k[3], p1);
+            if (a == 2) return 2.0*std::fma(x, k[3], q1);
+            const double p2 = std::fma(x, p1, k[1]);
+            if (a == 1) return std::fma(x, q1, p2);
+            return std::fma(x, p2, k[0]);
+        }
+///  Values of a table-like node (piecewise on `cells` cells, or a constant) as one vector.
+        inline std::vector<double> cell_values(const leaf_ptr &n, const size_t cells) {
+            if (n->is_constant()) return std::vector<double> (cells, n->value);
+            assert(n->is_piecewise() && n->table->values.size() == cells && "Spline coefficients must be tables on the same cells.");
+            return n->table->values;
+        }
+    }
+
+///  c[j]: coefficient of x^j, piecewise_1D nodes (or constants) on the same cells, already folded.
+    inline leaf_ptr spline_1d(const std::array<leaf_ptr, 4> &c, leaf_ptr x, const unsigned a=0) {
+        const leaf_node *shape = nullptr;
+        for (auto &n : c) if (n->op == op_t::piecewise_1d) shape = n.get();
+        if (!shape) return a == 0 ? fma(fma(fma(c[3], x, c[2]), x, c[1]), x, c[0]) : zero();      // all constants: a plain cubic
+        const size_t cells = shape->table->values.size();
+        std::vector<double> v(cells*4);
+        for (size_t j = 0; j < 4; j++) {
+            const auto col = detail::cell_values(c[j], cells);
+            for (size_t i = 0; i < cells; i++) v[i*4 + j] = col[i];
+        }
+        if (a > 3) return zero();
+        return detail::intern(op_t::spline_1d, x, nullptr, nullptr, 0.0, detail::intern_table(v),
+                              spline_order {a, 0, 0}.pack(), shape->scale, shape->offset);
+    }
+///  c[i][j]: coefficient of u^i z^j, piecewise_2D nodes (or constants) on the same cells, folded in z.
+    inline leaf_ptr spline_2d(const std::array<std::array<leaf_ptr, 4>, 4> &c, leaf_ptr r, leaf_ptr z,
+                              const unsigned a=0, const unsigned b=0) {
+        const leaf_node *shape = nullptr;
+        for (auto &row : c) for (auto &n : row) if (n->op == op_t::piecewise_2d) shape = n.get();
+        assert(shape && "spline_2d needs at least one table.");
+        const size_t cells = shape->table->values.size();
+        std::vector<double> v(cells*16);
+        for (size_t i = 0; i < 4; i++) {
+            for (size_t j = 0; j < 4; j++) {
+                const auto col = detail::cell_values(c[i][j], cells);
+                for (size_t k = 0; k < cells; k++) v[k*16 + i*4 + j] = col[k];
+            }
+        }
+        if (a > 3 || b > 3) return zero();
+        return detail::intern(op_t::spline_2d, r, z, nullptr, 0.0, detail::intern_table(v),
+                              spline_order {a, b, shape->num_cols}.pack(), shape->scale, shape->offset);
+    }
+///  Another member of the family of `n`.
+    inline leaf_ptr spline_member(const leaf_node *n, const unsigned a, const unsigned b) {
+        if (a > 3 || b > 3) return zero();
+        const spline_order o = spline_order::unpack(n->num_cols);
+        return detail::intern(n->op, n->args[0], n->args[1], nullptr, 0.0, n->table, spline_order {a, b, o.columns}.pack(),
+                              n->scale, n->offset);
+    }
+///  Host values (also the oracle of the device code in tests).
+    inline double spline_1d_value(const leaf_node *n, const double x) {
+        const spline_order o = spline_order::unpack(n->num_cols);
+        const size_t cell = table_index(x, n->scale[0], n->offset[0], n->table->values.size()/4);
+        return detail::cubic(&n->table->values[cell*4], x, o.a);
+    }
+    inline double spline_2d_value(const leaf_node *n, const double r, const double z) {
+        const spline_order o = spline_order::unpack(n->num_cols);
+        const size_t rows = n->table->values.size()/16/o.columns;
+        const size_t cell = table_index(r, n->scale[0], n->offset[0], rows)*o.columns +
+                            table_index(z, n->scale[1], n->offset[1], o.columns);
+        const double *k = &n->table->values[cell*16];
+        double row[4];
+        for (size_t i = 0; i < 4; i++) row[i] = detail::cubic(k + 4*i, z, o.b);
+        const double inv = 1.0/n->scale[0];
+        const double u = (r - n->offset[0])*inv;
+        double value = detail::cubic(row, u, o.a);
+        for (unsigned i = 0; i < o.a; i++) value *= inv;
+        return value;
+    }
+
+//------------------------------------------------------------------------------
 //  Operators (double operands become constants).
 //------------------------------------------------------------------------------
     inline leaf_ptr operator+(leaf_ptr l, leaf_ptr r) { return add(l, r); }
@@ -835,6 +947,8 @@ namespace graph {
                                                b[b.size() == 1 ? 0 : i], c[c.size() == 1 ? 0 : i]);
                     break;
                 }
+                case op_t::spline_1d: un([&] (double a) { return spline_1d_value(n, a); }); break;
+                case op_t::spline_2d: bin([&] (double a, double b) { return spline_2d_value(n, a, b); }); break;
                 case op_t::piecewise_2d: {
                     const auto &t = n->table->values;
                     const size_t rows = t.size()/n->num_cols;
@@ -899,6 +1013,16 @@ namespace graph {
                 r = div(sub(mul(a, b->df(x)), mul(b, a->df(x))), add(mul(a, a), mul(b, b)));
                 break;
             }
+            case op_t::spline_1d: {
+                const spline_order o = spline_order::unpack(num_cols);
+                r = mul(spline_member(this, o.a + 1, 0), a->df(x));
+                break;
+            }
+            case op_t::spline_2d: {
+                const spline_order o = spline_order::unpack(num_cols);
+                r = add(mul(spline_member(this, o.a + 1, o.b), a->df(x)), mul(spline_member(this, o.a, o.b + 1), b->df(x)));
+                break;
+            }
             case op_t::fourier: {
                 const fourier_order o = fourier_order::unpack(num_cols);
                 r = add(add(mul(fourier_series(table, a, b, args[2], scale[0], offset[0], {o.a + 1, o.b, o.c, o.base}), a->df(x)),
@@ -935,7 +1059,7 @@ namespace graph {
             case op_t::pseudo: return pseudo_variable(a);
             case op_t::piecewise_1d: case op_t::piecewise_2d:
                 return detail::intern(n->op, a, b, nullptr, 0.0, n->table, n->num_cols, n->scale, n->offset);
-            case op_t::fourier: case op_t::index_1d: case op_t::index_2d:
+            case op_t::fourier: case op_t::index_1d: case op_t::index_2d: case op_t::spline_1d: case op_t::spline_2d:
                 return detail::intern(n->op, a, b, c, 0.0, n->table, n->num_cols, n->scale, n->offset);
             default: return std::const_pointer_cast<leaf_node> (n->shared_from_this());
         }
@@ -1044,6 +1168,17 @@ namespace graph {
                     accumulate(y, mul(q, x));
                     break;
                 }
+                case op_t::spline_1d: {
+                    const spline_order o = spline_order::unpack(n->num_cols);
+                    accumulate(x, mul(a, spline_member(n, o.a + 1, 0)));
+                    break;
+                }
+                case op_t::spline_2d: {
+                    const spline_order o = spline_order::unpack(n->num_cols);
+                    accumulate(x, mul(a, spline_member(n, o.a + 1, o.b)));
+                    accumulate(y, mul(a, spline_member(n, o.a, o.b + 1)));
+                    break;
+                }
                 case op_t::fourier: {
                     const fourier_order o = fourier_order::unpack(n->num_cols);
                     const leaf_ptr &v = n->args[2];
@@ -1072,7 +1207,8 @@ namespace graph {
 
     inline std::string leaf_node::to_string() {
         static const char *names[] = {"const", "var", "pseudo", "+", "-", "*", "/", "fma", "sqrt", "exp", "log",
-                                      "pow", "sin", "cos", "atan", "pw1d", "pw2d", "fourier", "erfi", "nan0", "idx1d", "idx2d"};
+                                      "pow", "sin", "cos", "atan", "pw1d", "pw2d", "fourier", "erfi", "nan0", "idx1d", "idx2d",
+                                      "spline1d", "spline2d"};
         std::ostringstream s;
         s.precision(17);
         if (op == op_t::constant) { s << value; return s.str(); }

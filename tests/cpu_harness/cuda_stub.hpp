@@ -21,4 +21,9 @@ inline void __syncthreads() {}
 using std::fma; using std::fmin; using std::fmax; using std::sqrt; using std::fabs;
 using std::exp; using std::log; using std::pow; using std::sin; using std::cos; using std::atan2;
 inline void sincos(const double x, double *s, double *c) { *s = std::sin(x); *c = std::cos(x); }
+//  cvt.rzi.u32.f64: truncation, saturating; negative values and NaN give 0.
+inline unsigned __double2uint_rz(const double x) {
+    return !(x > 0.0) ? 0u : (x >= 4294967295.0 ? 4294967295u : static_cast<unsigned> (x));
+}
+inline unsigned min(const unsigned a, const unsigned b) { return a < b ? a : b; }
 #endif

@@ -86,7 +86,9 @@ TRACE_CASES = [("extra_ordinary_wave", "efit", "rk4", "efit"), ("ordinary_wave",
 ILL_CONDITIONED = {("cold_plasma", "efit"): {"kz": 1.0e-6}}
 #  The residual is D^2 at a Newton root = the square of D's rounding noise; for cold plasma + EFIT that
 #  noise is ~1e-11 (folded spline coefficients up to 4e7, conftest.assert_rhs_close), elsewhere < 1e-14.
-RESIDUAL_FLOOR = {("cold_plasma", "efit"): 1.0e-10, ("cold_plasma", "efit_interior"): 1.0e-10}
+#  bohm_gross / light_wave: D = w_pe^2 + ... - w^2 is a difference of terms ~1.2e6, one ulp of which is 2.3e-10.
+RESIDUAL_FLOOR = {("cold_plasma", "efit"): 1.0e-10, ("cold_plasma", "efit_interior"): 1.0e-10,
+                  ("bohm_gross", "no_magnetic_field"): 2.0e-9, ("light_wave", "no_magnetic_field"): 2.0e-9}
 
 
 @pytest.mark.parametrize("disp,eq,solver,tag", TRACE_CASES)
