@@ -112,6 +112,9 @@ namespace jit {
 ///  Fourier loops: inside a row of modes with equal m and equally spaced n, step the angle by one
 ///  rotation (4 FMAs) instead of a sincos per mode; each row starts from a fresh sincos.
         bool mode_recurrence = true;
+///  Expressions that depend only on inputs the kernel never writes (the wave frequency of a ray: 1/w,
+///  w^2, 1/w^2 ...) are evaluated once per launch, before the step loop, instead of in every stage.
+        bool hoist_invariants = true;
         size_t unroll_stages_below = 640;       ///< unroll the RK stage loop for bodies up to this many statements
         unsigned block_size = 128;
 ///  Resident blocks per SM promised to ptxas; 0 = let the device layer pick the highest
@@ -149,6 +152,60 @@ namespace jit {
         std::unordered_map<const graph::leaf_node *, size_t> floop_of;
 ///  Arguments that occur under both sin and cos in this kernel: one sincos() serves both.
         std::unordered_map<const graph::leaf_node *, std::pair<const graph::leaf_node *, const graph::leaf_node *>> trig;
+///  Launch invariants: their statements go to K::invariants(), the body reads h[k].  While they are being
+///  emitted `out`, `reg` and `inv_reg` hold the invariant function's text and names.
+        std::unordered_map<const graph::leaf_node *, bool> invariant_memo;
+        std::unordered_map<const graph::leaf_node *, std::string> reg_other, inv_reg_other;
+        std::string text_other;
+        bool in_invariants = false;
+        size_t num_invariants = 0;
+
+        bool is_invariant(const graph::leaf_node *n) {
+            n = strip(n);
+            auto it = invariant_memo.find(n);
+            if (it != invariant_memo.end()) return it->second;
+            bool result = true;
+            if (n->op == graph::op_t::variable) {
+                result = false;
+                for (size_t i = 0; i < info.inputs.size(); i++)
+                    if (info.inputs[i].get() == n) result = !info.input_written[i];
+            } else if (n->is_piecewise() || n->is_spline() || n->is_index() || n->op == graph::op_t::fourier) {
+                result = false;         // table look-ups stay in the body: their row pointers are per context
+            } else {
+                for (size_t i = 0, ie = n->num_args(); i < ie && result; i++) result = is_invariant(n->args[i].get());
+            }
+            invariant_memo.emplace(n, result);
+            return result;
+        }
+        void switch_context() {
+            std::string mine = out.str();
+            out.str(text_other);
+            out.seekp(0, std::ios_base::end);
+            text_other.swap(mine);
+            reg.swap(reg_other);
+            inv_reg.swap(inv_reg_other);
+            in_invariants = !in_invariants;
+        }
+///  Body context: the name under which the body reads invariant node n (or its reciprocal).
+        std::string hoisted(const graph::leaf_node *n, const bool reciprocal) {
+            switch_context();
+            std::string local = emit(n);
+            if (reciprocal) {
+                auto f = inv_reg.find(n);
+                if (f == inv_reg.end()) {
+                    const std::string iname = "i" + std::to_string(n->id);
+                    out << "        const double " << iname << " = "
+                        << (opt.fast_division ? "gfb::rcp(" + local + ")" : "1.0/" + local) << ";" << std::endl;
+                    info.num_reciprocals++;
+                    f = inv_reg.emplace(n, iname).first;
+                }
+                local = f->second;
+            }
+            const std::string slot_name = "h[" + std::to_string(num_invariants++) + "]";
+            out << "        " << slot_name << " = " << local << ";" << std::endl;
+            switch_context();
+            return slot_name;
+        }
 
         static const graph::leaf_node *strip(const graph::leaf_node *n) {
             while (n->op == graph::op_t::pseudo) n = n->args[0].get();
@@ -643,6 +700,10 @@ namespace jit {
             if (n->op == op_t::constant) {
                 return reg.emplace(n, literal(n->value)).first->second;
             }
+            if (opt.hoist_invariants && !in_invariants && n->op != op_t::variable && is_invariant(n)) {
+                const std::string name = hoisted(n, false);
+                return reg.emplace(n, name).first->second;
+            }
             if (n->op == op_t::variable) {
                 for (size_t i = 0; i < info.inputs.size(); i++)
                     if (info.inputs[i].get() == n)
@@ -745,6 +806,10 @@ namespace jit {
                     const graph::leaf_node *d = strip(n->args[1].get());
                     if ((opt.share_reciprocals && denominators[d] > 1) || opt.fast_division) {
                         auto inv = inv_reg.find(d);
+                        if (inv == inv_reg.end() && opt.hoist_invariants && !in_invariants && !d->is_constant() && is_invariant(d)) {
+                            const std::string name = hoisted(d, true);
+                            inv = inv_reg.emplace(d, name).first;
+                        }
                         if (inv == inv_reg.end()) {
                             const std::string dreg = emit(d);
                             inv = inv_reg.find(d);      // a sqrt denominator registers its rsqrt while being emitted
@@ -874,11 +939,20 @@ namespace jit {
             for (auto &[pi, ri] : store_r) out << "        a.ptr[" << pi << "][i] = r[" << ri << "];" << std::endl;
             out << "    }" << std::endl;
 
-            out << "    __device__ static __forceinline__ void body(const double (&v)[NI + 1], double (&r)[NR + 1], const double *(&tg)[NG + 1]) {" << std::endl;
+//  The statements of body() and of invariants() are collected apart (emit() switches between them).
+            const std::string head = out.str();
+            out.str("");
             std::vector<std::string> regs;
             for (auto &r : results) regs.push_back(emit(r.get()));
             for (size_t j = 0; j < nr; j++) out << "        r[" << j << "] = " << regs[j] << ";" << std::endl;
-            out << "    }" << std::endl << "};" << std::endl;
+            const std::string body_text = out.str();
+            out.str(head);
+            out.seekp(0, std::ios_base::end);
+            out << "    static constexpr int NH = " << num_invariants << ";" << std::endl
+                << "    __device__ static __forceinline__ void invariants(const double (&v)[NI + 1], double (&h)[NH + 1]) {" << std::endl
+                << text_other << "    }" << std::endl
+                << "    __device__ static __forceinline__ void body(const double (&v)[NI + 1], const double (&h)[NH + 1], double (&r)[NR + 1], const double *(&tg)[NG + 1]) {" << std::endl
+                << body_text << "    }" << std::endl << "};" << std::endl;
 
             out << "extern \"C\" __global__ void __launch_bounds__(" << opt.block_size << ", "
                 << (opt.min_blocks ? std::to_string(opt.min_blocks) : std::string("GFB_MIN_BLOCKS")) << ") "

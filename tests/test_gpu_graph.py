@@ -284,7 +284,9 @@ struct add_one_k {
     __device__ static __forceinline__ void load(double (&v)[2], const gfb_args &a, const unsigned long long i) { v[0] = a.ptr[0][i]; }
     __device__ static __forceinline__ void apply(double (&v)[2], const double (&r)[2]) { v[0] = r[0]; }
     __device__ static __forceinline__ void store(const double (&v)[2], const double (&r)[2], const gfb_args &a, const unsigned long long i) { a.ptr[0][i] = v[0]; }
-    __device__ static __forceinline__ void body(const double (&v)[2], double (&r)[2], const double *(&tg)[1]) { r[0] = v[0] + 1.0; }
+    static constexpr int NH = 0;
+    __device__ static __forceinline__ void invariants(const double (&v)[2], double (&h)[1]) {}
+    __device__ static __forceinline__ void body(const double (&v)[2], const double (&h)[1], double (&r)[2], const double *(&tg)[1]) { r[0] = v[0] + 1.0; }
 };
 extern "C" __global__ void add_one(const __grid_constant__ gfb_args a) { gfb::generic_item<add_one_k> (a); }
 '''

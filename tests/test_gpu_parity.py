@@ -171,7 +171,7 @@ def test_adaptive_rk4_runs_the_reference_rule(lib):
     from graph_framework_b200.rays import RayTracer
     g = golden("ref_trace_cold_plasma_gaussian_density_adaptive_rk4")
     ref_dt = g["records"][1][9]
-    assert np.mean(~np.isfinite(ref_dt) | (np.abs(ref_dt) > 1.0e10)) > 0.8
+    assert np.mean(~np.isfinite(ref_dt) | (np.abs(ref_dt) > 1.0e10)) > 0.7          # 24 of 32 rays; the other 8 have |dt| ~ 1e-2 .. 1e9
     state = unpack(g["state"])
     n = state["w"].size
     tr = RayTracer("cold_plasma", "gaussian_density", n, float(g["dt"]), solver="adaptive_rk4")
