@@ -62,6 +62,7 @@ def _load():
         "gfb_deposit": (I, [P, P, P, P, P, SZ, P, c_double_p, c_double_p, ctypes.POINTER(I)]),
         "gfb_allreduce_sum_f64": (I, [c_void_pp, I, ctypes.POINTER(U64), SZ]),
         "gfb_measure_fp64_peak": (I, [P, c_double_p, ctypes.POINTER(ctypes.c_float)]),
+        "gfb_measure_fp64_peak_registers": (I, [P, c_double_p, ctypes.POINTER(ctypes.c_float)]),
         "gfb_flush_l2": (I, [P]),
         # gfb_rays.h
         "gfb_rays_create": (P, [S, S, S, S, SZ, D, I, S]),

@@ -12,6 +12,7 @@
 #include "../../include/gfb_rays.h"
 
 #include "graph/graph_framework.hpp"
+#include "graph/boris.hpp"
 
 using graph::leaf_ptr;
 
@@ -723,50 +724,20 @@ gfb_boris *gfb_boris_create(const char *equilibrium_name, const char *table_file
     b->n = num_particles;
 //  xkorc.cpp:40-64
     auto b0 = eq->get_characteristic_field(device);
-    const double q = 1.602176634E-19;
-    const double me = 9.1093837139E-31;
-    const double c = 299792458.0;
-    auto gryo_period = me/(q*b0);
-    auto larmor_radius = c*gryo_period;
     b->b0 = b0->evaluate().at(0);
-    b->larmor = larmor_radius->evaluate().at(0);
-
     static const char *symbols[7] = {"x", "y", "z", "u_{x}", "u_{y}", "u_{z}", "\\gamma"};
     for (int i = 0; i < 7; i++) b->vars.push_back(graph::variable(num_particles, symbols[i]));
     auto x = b->vars[0], y = b->vars[1], z = b->vars[2], ux = b->vars[3], uy = b->vars[4], uz = b->vars[5];
     auto gamma = b->vars[6];
-    auto pos = graph::vector(x, y, z);
-    auto u_vec = graph::vector(ux, uy, uz);
-    auto dt = graph::constant(dt_value);
-//  xkorc.cpp:66-121
-    auto gamma_init = 1.0/graph::sqrt(1.0 - u_vec->dot(u_vec));
-    auto u_init = gamma_init*u_vec;
-    auto b_vec = eq->get_magnetic_field(x, y, z)/b0;
+//  xkorc.cpp:66-121 (csrc/graph/boris.hpp)
+    const boris::push_graph push = boris::build(eq, b->vars, b0, dt_value);
+    b->larmor = push.larmor_radius;
 
     b->work = std::make_unique<workflow::manager<>> (device);
     b->work->get_context().options = o.emit;
     if (o.fused_steps) gfb_set_max_fused_steps(b->work->get_context().device(), o.fused_steps);
-    b->work->add_preitem({ux, uy, uz, gamma}, {}, {
-        {u_init->get_x(), ux}, {u_init->get_y(), uy}, {u_init->get_z(), uz}, {gamma_init, gamma}
-    }, graph::shared_random_state<> (), "initialize_gamma", num_particles);
-
-    auto u_prime = u_vec - dt*u_vec->cross(b_vec)/(2.0*gamma);
-    auto tau = -0.5*dt*b_vec;
-    auto tau_sq = tau->dot(tau);
-    auto speed_sq = u_prime->dot(u_prime);
-    auto sigma = 1.0 + speed_sq - tau_sq;
-    auto ustar = u_prime->dot(tau);
-    auto gamma_next = graph::sqrt(0.5*(sigma + graph::sqrt(sigma*sigma + 4.0*(tau_sq + ustar*ustar))));
-    auto t = tau/gamma_next;
-    auto s = 1.0 + t->dot(t);
-    auto u_prime_dot_t = u_prime->dot(t);
-    auto u_next = (u_prime + u_prime_dot_t*t + u_prime->cross(t))/s;
-    auto pos_next = pos + larmor_radius*dt*u_next/gamma_next;
-
-    b->work->add_item({x, y, z, ux, uy, uz, gamma}, {}, {
-        {pos_next->get_x(), x}, {pos_next->get_y(), y}, {pos_next->get_z(), z},
-        {u_next->get_x(), ux}, {u_next->get_y(), uy}, {u_next->get_z(), uz}, {gamma_next, gamma}
-    }, graph::shared_random_state<> (), "step", num_particles);
+    b->work->add_preitem({ux, uy, uz, gamma}, {}, push.initialize, graph::shared_random_state<> (), "initialize_gamma", num_particles);
+    b->work->add_item({x, y, z, ux, uy, uz, gamma}, {}, push.step, graph::shared_random_state<> (), "step", num_particles);
 //  Particles of one (R, Z) cell share the coefficient rows of the field tables: keep them sorted by
 //  cell while stepping (options: bin_rays=0 off, bin_rays=<steps> how often the order is checked).
     if (o.bin_rays != 0) b->grid = eq->get_cell_grid();

@@ -775,6 +775,14 @@ namespace jit {
                 return reg.emplace(n, name).first->second;
             }
 
+            if (n->op == op_t::sqrt && opt.fast_division && !denominators.count(n)) {
+//  Nobody divides by this root: no need for its reciprocal.
+                const std::string arg = emit(n->args[0].get());
+                const std::string name = "t" + std::to_string(n->id);
+                out << "        const double " << name << " = gfb::sqrt_only(" << arg << ");" << std::endl;
+                info.num_statements++;
+                return reg.emplace(n, name).first->second;
+            }
             if (n->op == op_t::sqrt && opt.fast_division) {
                 const std::string arg = emit(n->args[0].get());
                 const std::string qname = "q" + std::to_string(n->id);

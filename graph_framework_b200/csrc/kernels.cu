@@ -250,6 +250,33 @@ __global__ void __launch_bounds__(256) sum_peers_kernel(double *__restrict__ dst
     }
 }
 
+//  The same stream with all three FMA operands in (non-uniform) registers, the shape real ray code has:
+//  8 chains r_i = fma(r_i, s_j, t_k) whose multipliers and addends rotate through 8 + 8 per-thread values.
+//  Measures what the register file can feed the FP64 pipe, which the uniform-operand probe above does not.
+__global__ void __launch_bounds__(256) fp64_peak_regs_kernel(double *out, const int iters, const double a, const double b) {
+    double r[8], s[8], t[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        r[j] = threadIdx.x + j;
+        s[j] = a + 1.0e-9*(threadIdx.x + 3*j);
+        t[j] = b*(1.0 + 1.0e-3*(threadIdx.x + 5*j));
+    }
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = fma(r[j], s[(j + k) & 7], t[(j + 3*k) & 7]);
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) sum += r[j];
+    if (sum == 12345.678) {
+        out[0] = sum;
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(double *p, const size_t n, const double v) {
     for (size_t i = static_cast<size_t> (blockIdx.x)*blockDim.x + threadIdx.x; i < n;
          i += static_cast<size_t> (gridDim.x)*blockDim.x) {
@@ -328,6 +355,10 @@ int gfb_k_compose(unsigned *total, const unsigned *first, const unsigned *second
 }
 int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s) {
     fp64_peak_kernel<<<sms*8, 256, 0, s>>> (scratch, iters, 0.999999, 1.0e-6);
+    return static_cast<int> (cudaGetLastError());
+}
+int gfb_k_fp64_peak_regs(double *scratch, int iters, int sms, cudaStream_t s) {
+    fp64_peak_regs_kernel<<<sms*4, 256, 0, s>>> (scratch, iters, 0.999999, 1.0e-6);
     return static_cast<int> (cudaGetLastError());
 }
 //  src: `num` (<= 16) pointers to `count` doubles each, 16-byte aligned; dst likewise.

@@ -40,6 +40,7 @@ double gfb_k_unorder(unsigned long long key);
 int gfb_k_deposit(const double *x, const double *y, const double *z, const double *w, unsigned long long n,
                   double *hist, const double *lo, const double *hi, const int *bins, int sms, cudaStream_t s);
 int gfb_k_fp64_peak(double *scratch, int iters, int sms, cudaStream_t s);
+int gfb_k_fp64_peak_regs(double *scratch, int iters, int sms, cudaStream_t s);
 int gfb_k_bin_permutation(const double *const values[3], unsigned n, const double lo[2], const double hi[2],
                           const unsigned cells01[2], unsigned *work, unsigned *perm, int sms, cudaStream_t s);
 int gfb_k_permute(double *dst, const double *src, const unsigned *perm, unsigned n, int scatter, int sms, cudaStream_t s);
@@ -1109,27 +1110,35 @@ int gfb_allreduce_sum_f64(gfb_ctx *const *ctxs, int num_ctx, const uint64_t *key
     return 0;
 }
 
-int gfb_measure_fp64_peak(gfb_ctx *c, double *tflops, float *milliseconds) {
+namespace {
+int measure_peak(gfb_ctx *c, const int variant, double *tflops, float *milliseconds) {
     if (flush(c)) return 1;
     if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
     const int iters = 4096;
     double *scratch = reinterpret_cast<double *> (c->scratch);
-    gfb_k_fp64_peak(scratch, 64, c->sms, c->stream);      // warm up
+    auto launch = [&] (const int n) {
+        return variant ? gfb_k_fp64_peak_regs(scratch, n, c->sms, c->stream) : gfb_k_fp64_peak(scratch, n, c->sms, c->stream);
+    };
+    launch(64);      // warm up
     float best = 1.0e30f;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(c->ev_start, c->stream);
-        if (gfb_k_fp64_peak(scratch, iters, c->sms, c->stream)) return fail("peak kernel launch failed");
+        if (launch(iters)) return fail("peak kernel launch failed");
         cudaEventRecord(c->ev_stop, c->stream);
         if (check(cudaEventSynchronize(c->ev_stop), "peak sync")) return 1;
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop);
         if (ms < best) best = ms;
     }
-    const double flops = 2.0*8.0*16.0*static_cast<double> (iters)*256.0*8.0*c->sms;
+    const double blocks_per_sm = variant ? 4.0 : 8.0;
+    const double flops = 2.0*8.0*16.0*static_cast<double> (iters)*256.0*blocks_per_sm*c->sms;
     *tflops = flops/(best*1.0e-3)/1.0e12;
     if (milliseconds) *milliseconds = best;
     return 0;
 }
+}
+int gfb_measure_fp64_peak(gfb_ctx *c, double *tflops, float *milliseconds) { return measure_peak(c, 0, tflops, milliseconds); }
+int gfb_measure_fp64_peak_registers(gfb_ctx *c, double *tflops, float *milliseconds) { return measure_peak(c, 1, tflops, milliseconds); }
 
 int gfb_flush_l2(gfb_ctx *c) {
     if (flush(c)) return 1;

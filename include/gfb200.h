@@ -176,8 +176,11 @@ int gfb_deposit(gfb_ctx *ctx, const double *x, const double *y, const double *z,
  * uses these contexts.  (One process per GPU: use NCCL -- graph_framework_b200/parallel.py.) */
 int gfb_allreduce_sum_f64(gfb_ctx *const *ctxs, int num_ctx, const uint64_t *keys, size_t n);
 
-/* Measured FP64 FMA peak of the device in TFLOP/s (roofline denominator). */
+/* Measured FP64 FMA rate of the device in TFLOP/s: independent DFMA chains whose multiplier and addend
+ * are uniform values (the friendliest stream there is) ... */
 int gfb_measure_fp64_peak(gfb_ctx *ctx, double *tflops, float *milliseconds);
+/* ... and the same chains with all three operands in per-thread registers, the shape compiled ray code has. */
+int gfb_measure_fp64_peak_registers(gfb_ctx *ctx, double *tflops, float *milliseconds);
 /* L2 flush helper for benchmarks: writes a buffer larger than L2. */
 int gfb_flush_l2(gfb_ctx *ctx);
 

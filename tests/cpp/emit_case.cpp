@@ -4,6 +4,7 @@
 #include <fstream>
 #include <iostream>
 #include "../../graph_framework_b200/csrc/graph/graph_framework.hpp"
+#include "../../graph_framework_b200/csrc/graph/boris.hpp"
 
 using graph::leaf_ptr;
 
@@ -133,7 +134,15 @@ int main(int argc, char **argv) {
     if (const char *s = std::getenv("GFB_MINB")) opt.min_blocks = std::atoi(s);
     std::ostringstream src;
     jit::kernel_info info;
-    if (kind == "kamp" || kind == "power") info = build_absorption(kind, eq, src, opt);
+    if (kind == "boris") {
+//  The xkorc push with the on-axis field given (GFB_B0; the device search for it is tested on the GPU).
+        const size_t n = 1;
+        std::vector<leaf_ptr> vars;
+        for (const char *name : {"x", "y", "z", "ux", "uy", "uz", "gamma"}) vars.push_back(graph::variable(n, name));
+        const auto push = boris::build(eq, vars, graph::constant(std::atof(std::getenv("GFB_B0") ? std::getenv("GFB_B0") : "1.0")),
+                                       std::getenv("GFB_DT") ? std::atof(std::getenv("GFB_DT")) : 0.5);
+        info = jit::emit_item(src, opt, jit::kernel_kind::generic, "step", vars, {}, push.step, n);
+    } else if (kind == "kamp" || kind == "power") info = build_absorption(kind, eq, src, opt);
     else if (kind == "pic_push" || kind == "pic_field") info = build_pic(kind, src, opt);
     else if (d == "cold_plasma") info = build<dispersion::cold_plasma<>> (kind, eq, src, opt);
     else if (d == "ordinary_wave") info = build<dispersion::ordinary_wave<>> (kind, eq, src, opt);

@@ -8,7 +8,7 @@ OUT=gpurun_out/ncu; mkdir -p $OUT
 KERNEL=solver_kernel; UNITS=1000000
 case $W in
   boris) KERNEL=step; UNITS=20000000; ARGS="--workload boris --rays 20000000 --scaling weak";;
-  vmec_*) UNITS=1250000; ARGS="--workload $W";;
+  vmec_*) UNITS=1250000; ARGS="--workload $W --options bin_rays=100";;     # order checked every 100 steps: one launch = one bench step
   *) ARGS="--workload $W";;
 esac
 CMD="python bench.py $ARGS --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-e2e $*"
