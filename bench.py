@@ -406,48 +406,71 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
     peaks = device_peaks(tracer)
     #  All torch work (zeroing, NCCL) is issued on the tracer's own stream: one timeline, no host waits.
     stream = torch.cuda.ExternalStream(tracer.stream(), device=torch.device("cuda", ranks.local_rank))
-    increment = torch.zeros(bins, dtype=torch.float64, device="cuda")       # d_power of one block, this rank
+    #  Two per-block histograms in flight: while block b + 1 is being traced, the NCCL all-reduce of block b runs on
+    #  NCCL's own stream over NVLink; its result is added to the running profile just before its buffer is reused.
+    increments = [torch.zeros(bins, dtype=torch.float64, device="cuda") for _ in range(2)]      # d_power of one block, this rank
+    pending = [None, None]
     profile = torch.zeros(bins, dtype=torch.float64, device="cuda")         # running sum over blocks and ranks
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     launch_circle = {k: pinned_empty(rays) for k in STATE}
     for k in STATE:
         launch_circle[k][:] = start[k]
     done = [0]
 
-    def block(timed):
+    def retire(i):
+        """Wait (on the tracer's stream) for the reduction of buffer i and fold it into the running profile."""
+        if pending[i] is not None:
+            if pending[i] is not True:
+                pending[i].wait()
+            profile.add_(increments[i])
+            pending[i] = None
+
+    def block(timed=None):
         if done[0] % cfg["period"] == 0 and done[0]:
             tracer.put_state(launch_circle)                 # untimed: back to the launch circle, power = 1
             tracer.absorption_reset()
+        i = done[0] % 2
         done[0] += 1
         with torch.cuda.stream(stream):
-            increment.zero_()
             if timed:
-                ev[0].record(stream)
-            tracer.deposit_block(SUB_STEPS, increment.data_ptr(), lo, hi, bins)
+                timed[0].record(stream)
+            retire(i)
+            increments[i].zero_()
+            tracer.deposit_block(SUB_STEPS, increments[i].data_ptr(), lo, hi, bins)
             if timed:
-                ev[1].record(stream)
+                timed[1].record(stream)
             if ranks.dist:
-                ranks.dist.all_reduce(increment, op=ranks.dist.ReduceOp.SUM)       # NCCL, FP64, over NVLink
-            profile.add_(increment)
-            if timed:
-                ev[2].record(stream)
+                pending[i] = ranks.dist.all_reduce(increments[i], op=ranks.dist.ReduceOp.SUM, async_op=True)   # NCCL, FP64, NVLink
+            else:
+                pending[i] = True
+        return i
+
+    def drain():
+        with torch.cuda.stream(stream):
+            for i in (done[0] % 2, (done[0] + 1) % 2):      # older buffer first
+                retire(i)
 
     sampler = ClockSampler(ranks.local_rank).start()
     for _ in range(warmup):
-        block(False)
+        block()
+    drain()
     tracer.wait()
     ranks.barrier()
     sampler.mark()
     launches0 = tracer.launch_count()
-    total_ms = compute_ms = 0.0
-    deposited = []
-    for _ in range(steps):
-        block(True)
-        ev[2].synchronize()
-        compute_ms += ev[0].elapsed_time(ev[1])
-        total_ms += ev[0].elapsed_time(ev[2])
-        deposited.append(float(increment.sum().item()))
+    compute_ms = 0.0
+    stamps = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        ev[2].record(stream)
+    for k in range(steps):
+        block(stamps[k])
+    drain()
+    with torch.cuda.stream(stream):
+        ev[3].record(stream)
+    ev[3].synchronize()
+    total_ms = ev[2].elapsed_time(ev[3])
+    for a, b in stamps:
+        compute_ms += a.elapsed_time(b)                     # includes the wait for the reduction two blocks back, if it is late
     launches = tracer.launch_count() - launches0
     ranks.barrier()
     total_ms_max = ranks.max(total_ms)
@@ -455,10 +478,17 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
 
     # ---- parity of the reduced profile: one more block of the production path, ALL rays -----------
     parity = None
+    increment = None
     if check:
-        block(False)
+        last = block()
+        with torch.cuda.stream(stream):
+            if pending[last] is not True:
+                pending[last].wait()
+        pending[last] = None                                    # checked below, not folded into the profile twice
         tracer.wait()
         torch.cuda.synchronize()
+        increment = increments[last]
+        profile.add_(increment)
         pos = tracer.get_state(residual=False)                  # caller's ray order
         absorbed = tracer.get_absorbed()                        # Im k_amp, power, d_power of that block, same order
         from oracle import port
@@ -490,9 +520,12 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
             tracer.put_state(host_in)                              # H2D of the 8 state arrays
             tracer.absorption_reset()
             done[0] = 0
-            block(False)
+            i = block()
             with torch.cuda.stream(stream):
-                host_profile.copy_(increment, non_blocking=True)   # D2H of the reduced profile of the block
+                if pending[i] is not True:
+                    pending[i].wait()
+                pending[i] = None
+                host_profile.copy_(increments[i], non_blocking=True)   # D2H of the reduced profile of the block
             stream.synchronize()
         e2e_step()
         ranks.barrier()
@@ -521,11 +554,10 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
                        "rays_per_gpu": rays, "rays_total": total_rays, "dt": cfg["dt"], "options": args.options,
                        "launch_radius": cfg["radius"], "restart_every_blocks": cfg["period"],
                        "l2": "state (72 MB) + absorption state (56 MB) + profile (4 MB) per GPU exceed the 126 MB L2 together; not flushed separately"},
-            "collective": {"what": "torch.distributed all_reduce(SUM, float64) on NCCL, issued on the tracer's stream" if ranks.dist else "none at 1 GPU",
-                           "bytes": cells*8, "ms_per_step": (total_ms_max - compute_ms_max)/steps,
+            "collective": {"what": "torch.distributed all_reduce(SUM, float64, async) on NCCL: the reduction of block b overlaps the tracing of block b + 1 (two histograms in flight)" if ranks.dist else "none at 1 GPU",
+                           "bytes": cells*8, "exposed_ms_per_step": (total_ms_max - compute_ms_max)/steps,
                            "share_of_step": (total_ms_max - compute_ms_max)/total_ms_max,
-                           "note": "includes the add into the running profile (one %d-element kernel)" % cells},
-            "deposited_power_per_block_rank0": deposited,
+                           "note": "exposed = whole timed loop minus the trace+absorb+deposit intervals; includes zeroing and the add into the running profile (two %d-element kernels)" % cells},
             "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": fp64_roofline("efit_absorb", tracer.ctx, rays, SUB_STEPS, compute_ms/steps,
                                       workloads.FLOP_PER_RAY_STEP.get((cfg["dispersion"], cfg["equilibrium"])), peaks,
@@ -533,7 +565,7 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
         }
     #  torch frees record events on the streams a tensor was used on: every tensor that touched the tracer's
     #  stream must go before the tracer (and with it the stream) does.
-    del block, increment, profile, ev, stream, launch_circle
+    del block, drain, retire, increments, increment, pending, profile, ev, stamps, stream, launch_circle
     torch.cuda.synchronize()
     import gc
     gc.collect()
