@@ -480,6 +480,9 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
     parity = None
     increment = None
     if check:
+        while done[0] % cfg["period"] != cfg["period"] - 2:    # check a block in which the beam is being absorbed
+            block()
+        drain()
         last = block()
         with torch.cuda.stream(stream):
             if pending[last] is not True:

@@ -193,7 +193,7 @@ namespace jit {
             if (reciprocal) {
                 auto f = inv_reg.find(n);
                 if (f == inv_reg.end()) {
-                    const std::string iname = "i" + std::to_string(n->id);
+                    const std::string iname = "i" + local_id(n);
                     out << "        const double " << iname << " = "
                         << (opt.fast_division ? "gfb::rcp(" + local + ")" : "1.0/" + local) << ";" << std::endl;
                     info.num_reciprocals++;
@@ -205,6 +205,14 @@ namespace jit {
             out << "        " << slot_name << " = " << local << ";" << std::endl;
             switch_context();
             return slot_name;
+        }
+
+///  Register names count nodes in the order this kernel first names them, not by the thread-wide creation
+///  counter: the text of a kernel (and its sha256, which ties ncu captures to binaries) must not depend on
+///  what else the thread built before.
+        std::unordered_map<const graph::leaf_node *, size_t> local_ids;
+        std::string local_id(const graph::leaf_node *n) {
+            return std::to_string(local_ids.emplace(n, local_ids.size()).first->second);
         }
 
         static const graph::leaf_node *strip(const graph::leaf_node *n) {
@@ -486,7 +494,7 @@ namespace jit {
             for (auto &set : loop.sets) {
                 for (auto *m : set.members) {
                     if (reg.count(m)) continue;
-                    const std::string name = "t" + std::to_string(m->id);
+                    const std::string name = "t" + local_id(m);
                     out << "        double " << name << " = 0.0;" << std::endl;
                     reg.emplace(m, name);
                 }
@@ -657,7 +665,7 @@ namespace jit {
                 for (const graph::leaf_node *node : grp.spline_nodes) {
                     if (reg.count(node)) continue;
                     const unsigned a = graph::spline_order::unpack(node->num_cols).a;
-                    const std::string name = "t" + std::to_string(node->id);
+                    const std::string name = "t" + local_id(node);
                     out << "        const double " << name << " = " << (a >= 2 ? literal(factorial[a]) + "*" : std::string()) << r[a] << ";" << std::endl;
                     info.num_statements++;
                     reg.emplace(node, name);
@@ -683,7 +691,7 @@ namespace jit {
                     if (o.b != b) continue;
                     double factor = factorial[o.b]*factorial[o.a];
                     for (unsigned i = 0; i < o.a; i++) factor *= inv;
-                    const std::string name = "t" + std::to_string(node->id);
+                    const std::string name = "t" + local_id(node);
                     out << "        const double " << name << " = " << (factor != 1.0 ? literal(factor) + "*" : std::string()) << r[o.a] << ";" << std::endl;
                     info.num_statements++;
                     reg.emplace(node, name);
@@ -729,7 +737,7 @@ namespace jit {
                     expr = index_expr(x, n->scale[0], n->offset[0], length/n->num_cols) + "*" +
                            std::to_string(n->num_cols) + "u + " + index_expr(y, n->scale[1], n->offset[1], n->num_cols);
                 }
-                const std::string name = "t" + std::to_string(n->id);
+                const std::string name = "t" + local_id(n);
                 out << "        const double " << name << " = tg[" << g << "][" << expr << "];" << std::endl;
                 info.num_statements++;
                 return reg.emplace(n, name).first->second;
@@ -778,15 +786,15 @@ namespace jit {
             if (n->op == op_t::sqrt && opt.fast_division && !denominators.count(n)) {
 //  Nobody divides by this root: no need for its reciprocal.
                 const std::string arg = emit(n->args[0].get());
-                const std::string name = "t" + std::to_string(n->id);
+                const std::string name = "t" + local_id(n);
                 out << "        const double " << name << " = gfb::sqrt_only(" << arg << ");" << std::endl;
                 info.num_statements++;
                 return reg.emplace(n, name).first->second;
             }
             if (n->op == op_t::sqrt && opt.fast_division) {
                 const std::string arg = emit(n->args[0].get());
-                const std::string qname = "q" + std::to_string(n->id);
-                const std::string name = "t" + std::to_string(n->id);
+                const std::string qname = "q" + local_id(n);
+                const std::string name = "t" + local_id(n);
                 out << "        const double " << qname << " = gfb::rsqrt(" << arg << ");" << std::endl;
                 out << "        const double " << name << " = gfb::sqrt_from_rsqrt(" << arg << ", " << qname << ");" << std::endl;
                 info.num_statements += 2;
@@ -798,8 +806,8 @@ namespace jit {
                 auto both = trig.find(arg);
                 if (both != trig.end() && both->second.first && both->second.second) {
                     const std::string areg = emit(arg);
-                    const std::string sname = "t" + std::to_string(both->second.first->id);
-                    const std::string cname = "t" + std::to_string(both->second.second->id);
+                    const std::string sname = "t" + local_id(both->second.first);
+                    const std::string cname = "t" + local_id(both->second.second);
                     out << "        double " << sname << ", " << cname << ";" << std::endl
                         << "        sincos(" << areg << ", &" << sname << ", &" << cname << ");" << std::endl;
                     info.num_statements += 2;
@@ -824,7 +832,7 @@ namespace jit {
                         }
                         if (inv == inv_reg.end()) {
                             const std::string dreg = emit(d);
-                            const std::string iname = "i" + std::to_string(d->id);
+                            const std::string iname = "i" + local_id(d);
                             out << "        const double " << iname << " = "
                                 << (opt.fast_division ? "gfb::rcp(" + dreg + ")" : "1.0/" + dreg) << ";" << std::endl;
                             info.num_statements++;
@@ -861,7 +869,7 @@ namespace jit {
                 case op_t::atan: rhs = "atan2(" + a[1] + ", " + a[0] + ")"; break;
                 default: rhs = "0.0"; break;
             }
-            const std::string name = "t" + std::to_string(n->id);
+            const std::string name = "t" + local_id(n);
             out << "        const double " << name << " = " << rhs << ";" << std::endl;
             info.num_statements++;
             return reg.emplace(n, name).first->second;
