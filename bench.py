@@ -50,9 +50,11 @@ WORKLOADS = {
 #  damping + power + deposition on a 64 x 64 x 128 grid over the EFIT box, one FP64 all-reduce of the block's
 #  profile per block.  dt 2e-4: 0.02 of travel per block of 100 steps; after `period` blocks (R ~ 2.02, most of
 #  the power absorbed; beyond the layer the weak-damping formula is not meaningful) the ensemble is put back on
-#  its launch circle, untimed, so that every timed block deposits.
+#  its launch circle, untimed, so that every timed block deposits.  The beam is monochromatic (w = 700): with the
+#  frequency spread of efit_example.sh the low-frequency tail of 10^6 rays passes ITS resonance layer early, and
+#  behind the layer the reference's weak-damping formula returns Im k < 0, i.e. exp(+...) "absorbed power".
 ABSORB = {"dispersion": "ordinary_wave", "equilibrium": "efit", "rays": 1000000, "dt": 2.0e-4, "total": 1000000,
-          "radius": 2.3, "period": 14, "bins": (64, 64, 128), "lo": (0.84, -1.7, -1.6), "hi": (2.54, 1.7, 1.6)}
+          "radius": 2.3, "period": 12, "w": 700.0, "bins": (64, 64, 128), "lo": (0.84, -1.7, -1.6), "hi": (2.54, 1.7, 1.6)}
 BORIS = {"particles": 20000000, "total": 100000000, "dt": 0.5}                  # configs[4]
 EXTRAS = ("efit_cold", "efit_absorb", "vmec_omode", "boris")
 EXTRA_STEPS, EXTRA_WARMUP = 3, 3
@@ -397,6 +399,7 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
     total_rays = cfg["total"] if strong else rays*ranks.world
     bins, lo, hi = cfg["bins"], cfg["lo"], cfg["hi"]
     state0 = workloads.efit_ensemble(rays, seed=ranks.rank, radius=cfg["radius"])
+    state0["w"][:] = cfg["w"]
     tracer = RayTracer(cfg["dispersion"], cfg["equilibrium"], rays, cfg["dt"], device=ranks.local_rank,
                        options=("fused_steps=%d absorption=1 " % SUB_STEPS) + args.options)
     tracer.set_state(state0)
@@ -508,6 +511,7 @@ def run_absorb(args, ranks, steps, warmup, with_e2e=True, check=True):
                   "block_power": float(oracle_sum.sum()), "nonzero_bins": int((reduced != 0).sum()),
                   "rays_depositing": int((absorbed["d_power"] != 0).sum()),
                   "profile_total_all_blocks": float(profile.sum().item()),
+                  "max_power_rank0": float(np.nanmax(absorbed["power"])), "min_kamp_im_rank0": float(np.nanmin(absorbed["kamp_im"])),
                   "median_transmitted_power": float(np.nanmedian(absorbed["power"]))}
 
     # ---- end to end: host state in, reduced profile out ------------------------------------------
