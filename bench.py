@@ -54,7 +54,7 @@ WORKLOADS = {
 #  frequency spread of efit_example.sh the low-frequency tail of 10^6 rays passes ITS resonance layer early, and
 #  behind the layer the reference's weak-damping formula returns Im k < 0, i.e. exp(+...) "absorbed power".
 ABSORB = {"dispersion": "ordinary_wave", "equilibrium": "efit", "rays": 1000000, "dt": 2.0e-4, "total": 1000000,
-          "radius": 2.3, "period": 12, "w": 700.0, "bins": (64, 64, 128), "lo": (0.84, -1.7, -1.6), "hi": (2.54, 1.7, 1.6)}
+          "radius": 2.3, "period": 13, "w": 700.0, "bins": (64, 64, 128), "lo": (0.84, -1.7, -1.6), "hi": (2.54, 1.7, 1.6)}
 BORIS = {"particles": 20000000, "total": 100000000, "dt": 0.5}                  # configs[4]
 EXTRAS = ("efit_cold", "efit_absorb", "vmec_omode", "boris")
 EXTRA_STEPS, EXTRA_WARMUP = 3, 3
