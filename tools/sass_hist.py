@@ -20,5 +20,5 @@ for line in sass.splitlines():
         hist[m.group(2).split(".")[0] + ("." + m.group(2).split(".")[1] if m.group(2).startswith(("MUFU", "F2I", "I2F", "F2F", "LD", "ST")) and "." in m.group(2) else "")] += 1
 total = sum(hist.values())
 print("total", total)
-for k, v in hist.most_common(40):
+for k, v in hist.most_common(60):
     print("%-14s %6d %5.1f%%" % (k, v, 100.0*v/total))
