@@ -771,7 +771,7 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=20000, help="rays of the bounded CPU sample")
     ap.add_argument("--ref-particles", type=int, default=400000, help="particles of the bounded CPU sample (Boris)")
     ap.add_argument("--options", default="", help="emit/launch options passed to gfb_rays_create")
-    ap.add_argument("--chunks", type=int, default=5, help="pieces of the ensemble pipelined by the e2e call")
+    ap.add_argument("--chunks", type=int, default=8, help="pieces of the ensemble pipelined by the e2e call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="time the headline workload only")
     ap.add_argument("--no-e2e", action="store_true")

@@ -243,6 +243,7 @@ struct gfb_ctx {
     cudaEvent_t drained[2] = {nullptr, nullptr};    // slot copied out (copy stream)
     unsigned next_slot = 0;
     cudaStream_t upload_stream = nullptr;
+    cudaStream_t stream2 = nullptr;         // second compute stream of the chunked host pipeline
 //  Ray binning: the permutation in force (perm[slot] = original ray), scratch for the moves.
     unsigned *bin_perm = nullptr;
     unsigned *bin_step = nullptr;       // the permutation of one re-sort, before it is composed into bin_perm
@@ -344,6 +345,10 @@ void gfb_ctx_destroy(gfb_ctx *c) {
     if (c->upload_stream) {
         cudaStreamSynchronize(c->upload_stream);
         cudaStreamDestroy(c->upload_stream);
+    }
+    if (c->stream2) {
+        cudaStreamSynchronize(c->stream2);
+        cudaStreamDestroy(c->stream2);
     }
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
@@ -626,6 +631,9 @@ int gfb_kernel_run_from_host(gfb_kernel *k, unsigned steps, int num_ray_slots,
     if (!c->upload_stream) {
         if (check(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking), "upload stream")) return 1;
     }
+    if (!c->stream2) {
+        if (check(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "second compute stream")) return 1;
+    }
     const unsigned long long total = k->args.n;
     if (chunks < 1) chunks = 1;
 //  Chunk boundaries on whole waves (blocks/SM x SMs x block) so only the last piece has a tail.  The
@@ -658,6 +666,7 @@ int gfb_kernel_run_from_host(gfb_kernel *k, unsigned steps, int num_ray_slots,
         cudaEventCreateWithFlags(&quiet, cudaEventDisableTiming);
         cudaEventRecord(quiet, c->stream);
         cudaStreamWaitEvent(c->upload_stream, quiet, 0);
+        cudaStreamWaitEvent(c->stream2, quiet, 0);
         cudaEventDestroy(quiet);
     }
     std::vector<cudaEvent_t> uploaded, computed;
@@ -678,7 +687,11 @@ int gfb_kernel_run_from_host(gfb_kernel *k, unsigned steps, int num_ray_slots,
         }
         if (rc) break;
         cudaEventRecord(up, c->upload_stream);
-        cudaStreamWaitEvent(c->stream, up, 0);
+//  Pieces alternate between two compute streams: a launch of 100 dependent steps ends with a tail in which
+//  the machine empties (one thread's chain takes ~0.2 ms however few rays are left); the next piece, on the
+//  other stream, fills it.  Pieces are disjoint ranges of rays, so they may overlap freely.
+        cudaStream_t compute = (piece_index & 1) ? c->stream2 : c->stream;
+        cudaStreamWaitEvent(compute, up, 0);
         device_args piece = k->args;
         for (int s = 0; s < num_ray_slots; s++) piece.ptr[s] = static_cast<char *> (k->args.ptr[s]) + off*sizeof(double);
         piece.n = cnt;
@@ -686,10 +699,10 @@ int gfb_kernel_run_from_host(gfb_kernel *k, unsigned steps, int num_ray_slots,
         void *params[] = {&piece};
         c->launches++;
         rc = check_cu(driver.LaunchKernel(k->function, static_cast<unsigned> ((cnt + k->block - 1)/k->block), 1, 1, k->block, 1, 1,
-                                          static_cast<unsigned> (k->smem), reinterpret_cast<CUstream> (c->stream), params, nullptr),
+                                          static_cast<unsigned> (k->smem), reinterpret_cast<CUstream> (compute), params, nullptr),
                       k->name.c_str());
         if (rc) break;
-        cudaEventRecord(done, c->stream);
+        cudaEventRecord(done, compute);
         cudaStreamWaitEvent(c->copy_stream, done, 0);
         for (int s = 0; s < num_ray_slots && !rc; s++) {
             if (host_dst && host_dst[s]) {
@@ -701,6 +714,7 @@ int gfb_kernel_run_from_host(gfb_kernel *k, unsigned steps, int num_ray_slots,
     }
     const int sync_rc = check(cudaStreamSynchronize(c->copy_stream), "pipeline sync") |
                         check(cudaStreamSynchronize(c->stream), "pipeline sync") |
+                        check(cudaStreamSynchronize(c->stream2), "pipeline sync") |
                         check(cudaStreamSynchronize(c->upload_stream), "pipeline sync");
     for (auto e : uploaded) cudaEventDestroy(e);
     for (auto e : computed) cudaEventDestroy(e);

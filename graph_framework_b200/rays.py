@@ -122,7 +122,7 @@ class RayTracer:
             out["residual"] = res
         return out
 
-    def step_host(self, num_steps, state_in, state_out, chunks=5):
+    def step_host(self, num_steps, state_in, state_out, chunks=8):
         """sync_device, num_steps steps and sync_host as one pipelined call (solver.hpp:354-384):
         upload, stepping and read-back of `chunks` pieces of the ensemble overlap.  state_in: dict
         of host arrays (pinned for full speed); state_out: dict of preallocated arrays, may
