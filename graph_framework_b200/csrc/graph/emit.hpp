@@ -98,6 +98,7 @@ namespace jit {
         size_t num_statements;
         size_t num_divides;
         size_t num_reciprocals;
+        bool has_mode_loop = false;             ///< the body contains a device loop over Fourier modes
     };
 
     struct emit_options {
@@ -395,6 +396,7 @@ namespace jit {
 //  Per mode: xm, -xn, row-start flag, then xm^b (-xn)^c for every derivative order (b, c) with
 //  b + c >= 2 that a member of the loop needs -- so that a weight is ONE multiply with the trig value.
         void finish_mode_tables() {
+            info.has_mode_loop = !floops.empty();
             for (auto &loop : floops) {
                 std::set<std::pair<unsigned, unsigned>> need;
                 for (auto &set : loop.sets) {

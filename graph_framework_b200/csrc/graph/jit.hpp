@@ -140,7 +140,9 @@ namespace jit {
                 bool unroll = false;
                 for (auto &k : kernels) {
                     if (k.kind == kernel_kind::rk2 || k.kind == kernel_kind::rk4) {
-                        unroll = k.num_statements <= options.unroll_stages_below;
+//  A body with a Fourier mode loop (VMEC) carries 26 accumulators through that loop: rolled, the stage loop
+//  fits 3 blocks/SM at 168 registers (+12 %, measured); unrolled it needs 230 and gets 2.
+                        unroll = k.num_statements <= options.unroll_stages_below && !k.has_mode_loop;
                     }
                 }
                 opts += unroll ? " -DGFB_UNROLL_STAGES=1" : " -DGFB_UNROLL_STAGES=0";
