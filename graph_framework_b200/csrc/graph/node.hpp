@@ -470,12 +470,8 @@ namespace graph {
                 return mul(mul(l->args[1], l->args[1]), l->args[0]->args[0]);
         }
         if (l->is_constant()) {
-//  (-c)*x -> (-1)*(c*x): +c*x and -c*x (both arise whenever a square is differentiated) then share ONE
-//  multiplication, and a factor of -1 costs nothing once compiled (it becomes an operand's negate modifier).
-            if (l->value < 0.0 && l->value != -1.0 && !r->is_constant())
-                return mul(none(), mul(constant(-l->value), r));
-//  c1*(c2*x) -> (c1*c2)*x   (except (-1)*(c*x), which is the canonical form of a negative factor)
-            if (r->op == op_t::mul && r->args[0]->is_constant() && !(l->value == -1.0 && r->args[0]->value > 0.0))
+//  c1*(c2*x) -> (c1*c2)*x
+            if (r->op == op_t::mul && r->args[0]->is_constant())
                 return mul(constant(l->value*r->args[0]->value), r->args[1]);
 //  c1*(c2/x) -> (c1*c2)/x
             if (r->op == op_t::div && r->args[0]->is_constant())
