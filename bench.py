@@ -132,10 +132,11 @@ class ClockSampler:
 #  Roofline bookkeeping
 # ---------------------------------------------------------------------------------------------
 def kernel_text_sha(ctx):
-    """sha256 of the CUDA text NVRTC compiled for this context (skeleton + emitted bodies): what a
-    committed ncu capture must have been taken from for its counters to describe this binary."""
+    """sha256 of the CUDA text NVRTC compiled for this context (skeleton + emitted bodies) and of the options
+    it was given (stage unrolling, blocks/SM promise): what a committed ncu capture must have been taken from
+    for its counters to describe this binary."""
     from graph_framework_b200 import _lib
-    return hashlib.sha256(_lib.lib.gfb_source(ctx)).hexdigest()
+    return hashlib.sha256(_lib.lib.gfb_source(ctx) + b"\n//options: " + _lib.lib.gfb_compile_options(ctx)).hexdigest()
 
 
 def ncu_capture(workload, sha):

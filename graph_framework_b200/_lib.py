@@ -37,6 +37,7 @@ def _load():
         "gfb_free": (None, [P]),
         "gfb_source": (S, [P]),
         "gfb_compile_log": (S, [P]),
+        "gfb_compile_options": (S, [P]),
         "gfb_buffer": (I, [P, U64, SZ, P, c_void_pp]),
         "gfb_buffer_import": (I, [P, U64, P, SZ]),
         "gfb_buffer_lookup": (I, [P, U64, c_void_pp, ctypes.POINTER(SZ)]),

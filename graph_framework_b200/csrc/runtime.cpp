@@ -225,7 +225,7 @@ struct gfb_ctx {
     CUmodule module = nullptr;
     std::map<uint64_t, buffer> buffers;
     std::vector<std::unique_ptr<gfb_kernel>> kernels;
-    std::string source, log;
+    std::string source, log, options;      // options: what NVRTC was finally given (incl. the chosen GFB_MIN_BLOCKS)
     gfb_kernel *pending = nullptr;
     unsigned pending_steps = 0;
     unsigned max_fused = 1024;
@@ -445,6 +445,7 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
     }
     c->module = natural.module;
     c->min_blocks = 0;
+    c->options = options_for(1);
     if (pinned) return 0;
     const int regs8 = (natural.regs + 7)/8*8;
     int m0 = regs8 > 0 ? 65536/(128*regs8) : 1;
@@ -477,6 +478,7 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
             c->module = v.module;
             c->min_blocks = candidates[i];
             c->log = logs[i];
+            c->options = options_for(candidates[i]);
             return 0;
         }
         driver.ModuleUnload(v.module);
@@ -486,6 +488,7 @@ int gfb_compile(gfb_ctx *c, const char *source, const char *const *names, int nu
 int gfb_compiled_min_blocks(gfb_ctx *c) { return c->min_blocks; }
 const char *gfb_source(gfb_ctx *c) { return c->source.c_str(); }
 const char *gfb_compile_log(gfb_ctx *c) { return c->log.c_str(); }
+const char *gfb_compile_options(gfb_ctx *c) { return c->options.c_str(); }
 
 int gfb_buffer(gfb_ctx *c, uint64_t key, size_t bytes, const void *init, void **device_ptr) {
     GFB_TRACE("buffer key=%llx bytes=%zu init=%p", (unsigned long long)key, bytes, init);
