@@ -56,8 +56,9 @@ void gfb_free(void *p);
 /* Full text (skeleton + bodies) of the last gfb_compile on this context; jit::context::print_source. */
 const char *gfb_source(gfb_ctx *ctx);
 const char *gfb_compile_log(gfb_ctx *ctx);
-/* The options NVRTC was given for the module in use (caller's options + the blocks/SM promise that was chosen):
- * together with gfb_source() this identifies the binary. */
+/* The options NVRTC was given for the module in use (the reference's fixed option array is
+ * cuda_context.hpp:245-254; here: caller's options + the blocks/SM promise that was chosen): together with
+ * gfb_source() this identifies the binary. */
 const char *gfb_compile_options(gfb_ctx *ctx);
 
 /* Buffers are keyed by a 64-bit key (the host node address, as the reference keys its

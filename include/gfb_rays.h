@@ -94,7 +94,9 @@ int gfb_rays_set_binning(gfb_rays *r, int which_state, double lo, double hi, uns
 int gfb_rays_trace_absorb(gfb_rays *r, size_t num_blocks, size_t sub_steps, double *records, double *absorbed,
                           double *profile, const double *lo, const double *hi, const int *bins);
 int gfb_rays_absorption_reset(gfb_rays *r);
-/* One output block of the same pipeline with the profile RESIDENT ON THE DEVICE and no host
+/* One output block of the same pipeline (replaces one iteration of the record loops of
+ * absorption::weak_damping::run, absorption.hpp:466-483, and bin_power, xrays.cpp:757-776, plus the masks of
+ * utilities/bin.py:53-106 for that record) with the profile RESIDENT ON THE DEVICE and no host
  * synchronisation: sub_steps RK steps, weak damping, power, then d_power is ADDED to `profile_device`
  * (bins[0]*bins[1]*bins[2] doubles of device memory owned by the caller, e.g. a torch tensor that is
  * then all-reduced with NCCL) on the tracer's stream (gfb_stream(gfb_rays_ctx(r))).  Config 3 of
@@ -103,7 +105,8 @@ int gfb_rays_deposit_block(gfb_rays *r, size_t sub_steps, double *profile_device
                            const double *lo, const double *hi, const int *bins);
 /* solver "adaptive_rk4" (solver.hpp:881-1006): the per-ray step length the solver's Newton item chose last. */
 int gfb_rays_get_dt(gfb_rays *r, double *out);
-/* Running absorption state in the caller's ray order: out[0..2] = Im k_amp, power, d_power
+/* Running absorption state in the caller's ray order (the variables kamp / power / d_power the reference
+ * writes per record, absorption.hpp:452-456, xrays.cpp:716-724): out[0..2] = Im k_amp, power, d_power
  * (num_rays doubles each, NULL entries skipped) as left by the last absorption block. */
 int gfb_rays_get_absorbed(gfb_rays *r, double *const out[3]);
 /* The device-resident profile the last gfb_rays_trace_absorb accumulated into: buffer key in
