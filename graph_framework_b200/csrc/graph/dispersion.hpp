@@ -270,7 +270,8 @@ namespace dispersion {
             if (axis < 0) return leaf_ptr();
             const elements e = build(w, k_vec, x, y, z, eq);
             leaf_ptr coordinate = axis == 0 ? x : (axis == 1 ? y : z);
-            auto K = -1.0*(e.b_sq->df(coordinate)/e.b_sq)*(e.w2/(e.b_sq*e.b_sq*defect.scale) - 1.0);
+            auto db_sq = defect.b_sq_derivative.get() ? defect.b_sq_derivative : e.b_sq->df(coordinate);
+            auto K = -1.0*(db_sq/e.b_sq)*(e.w2/(e.b_sq*e.b_sq*defect.scale) - 1.0);
             auto n2 = e.npara2 + e.nperp2;
             return K*(n2*(e.m13*e.m13) - (e.npara2*e.m22 + e.m11*n2)*e.m33);
         }

@@ -136,6 +136,7 @@ namespace equilibrium {
         struct reducer_defect {
             int axis = -1;              ///< 0, 1, 2 = x, y, z; -1: none known
             leaf_ptr scale;
+            leaf_ptr b_sq_derivative;   ///< d(B.B)/d(axis) where the equilibrium has a cheaper form than df(); may be null
         };
         virtual reducer_defect get_reducer_defect(leaf_ptr, leaf_ptr, leaf_ptr) { return reducer_defect(); }
     };
@@ -264,7 +265,7 @@ namespace equilibrium {
     private:
         const tables tab;
         leaf_ptr x_cache, y_cache, z_cache;
-        leaf_ptr ne_cache, ni_cache, te_cache, ti_cache, psi_cache;
+        leaf_ptr ne_cache, ni_cache, te_cache, ti_cache, psi_cache, r_cache, fpol_cache;
         vector_ptr b_cache;
 
         leaf_ptr profile(const std::array<std::vector<double>, 4> &c, leaf_ptr psi) {
@@ -300,6 +301,7 @@ namespace equilibrium {
             y_cache = y;
             z_cache = z;
             auto r = graph::sqrt(x*x + y*y);
+            r_cache = r;
             psi_cache = build_psi(r, z);
             ne_cache = graph::constant(tab.ne_scale)*profile(tab.ne, psi_cache);
             te_cache = graph::constant(tab.te_scale)*profile(tab.te, psi_cache);
@@ -310,7 +312,8 @@ namespace equilibrium {
 
             auto phi = graph::atan(x, y);
             auto br = psi_cache->df(z)/r;
-            auto bp = profile(tab.fpol, psi_cache)/r;
+            fpol_cache = profile(tab.fpol, psi_cache);
+            auto bp = fpol_cache/r;
             auto bz = -psi_cache->df(r)/r;
             auto cos = graph::cos(phi);
             auto sin = graph::sin(phi);
@@ -329,12 +332,20 @@ namespace equilibrium {
         leaf_ptr get_psi(leaf_ptr x, leaf_ptr y, leaf_ptr z) { set_cache(x, y, z); return psi_cache; }
 ///  Every field component carries 1/R (equilibrium.hpp:1363-1381): B.B = G/R^2, and the reducer's
 ///  faulty cancellation along z leaves R^8 behind (measured: exact to 10 digits on every state).
-        virtual typename generic<T, SAFE_MATH>::reducer_defect get_reducer_defect(leaf_ptr x, leaf_ptr y, leaf_ptr) {
+        virtual typename generic<T, SAFE_MATH>::reducer_defect get_reducer_defect(leaf_ptr x, leaf_ptr y, leaf_ptr z) {
             typename generic<T, SAFE_MATH>::reducer_defect d;
+            set_cache(x, y, z);
             auto r2 = x*x + y*y;
             auto r4 = r2*r2;
             d.axis = 2;
             d.scale = r4*r4;
+//  B.B = (psi_Z^2 + F^2 + psi_R^2)/R^2 in cylindrical components (the rotation by phi drops out), so
+//  d(B.B)/dz = 2 (psi_Z psi_ZZ + F F' psi_Z + psi_R psi_RZ)/R^2: every factor is already in the kernel.
+            auto psi_z = psi_cache->df(z);
+            auto psi_r = psi_cache->df(r_cache);
+            auto f = fpol_cache;
+//  (two divisions by R: the kernel has 1/R from the square root already, 1/R^2 would be a new reciprocal)
+            d.b_sq_derivative = 2.0*(psi_z*psi_z->df(z) + f*f->df(psi_cache)*psi_z + psi_r*psi_r->df(z))/r_cache/r_cache;
             return d;
         }
 ///  The psi(R, Z) tables: numr x numz cells.  A ray at the speed of light crosses one cell in
