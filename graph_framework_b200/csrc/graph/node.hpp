@@ -498,6 +498,10 @@ namespace graph {
 //  (c*x)/y -> c*(x/y) keeps constants outermost where they merge.
         if (l->op == op_t::mul && l->args[0]->is_constant())
             return mul(l->args[0], div(l->args[1], r));
+//  x/(c*y) -> (1/c)*(x/y): the denominator is then y itself, whose reciprocal the kernel often has already
+//  (d sqrt(u) = du/(2 sqrt(u)) divides by the root, and 1/sqrt(u) comes for free with it).
+        if (r->op == op_t::mul && r->args[0]->is_constant())
+            return mul(constant(1.0/r->args[0]->value), div(l, r->args[1]));
         return detail::intern(op_t::div, l, r, nullptr);
     }
 
