@@ -198,7 +198,7 @@ namespace dispersion {
     protected:
 ///  The named sub-expressions of the determinant (nodes are interned: building them twice costs nothing).
         struct elements {
-            leaf_ptr w2, b_sq, npara2, nperp2, m11, m12, m13, m22, m33;
+            leaf_ptr w2, b_sq, b_len, npara2, nperp2, m11, m12, m13, m22, m33;
         };
         elements build(leaf_ptr w, vector_ptr k_vec, leaf_ptr x, leaf_ptr y, leaf_ptr z,
                        equilibrium::shared<T, SAFE_MATH> &eq) {
@@ -235,6 +235,7 @@ namespace dispersion {
             elements e;
             e.w2 = w2;
             e.b_sq = b_vec->dot(b_vec);
+            e.b_len = b_len;
             e.npara2 = npara2;
             e.nperp2 = nperp2;
             e.m11 = e11 - npara2;
@@ -257,7 +258,7 @@ namespace dispersion {
 ///  a^2 c/(d^2 b^2); four plain variables reproduce it).  n_par^2 and
 ///  n_perp^2 are N^2/(B.B w^2); in the quotient rule of their derivative along a coordinate on which
 ///  B.B depends through a common factor s (the 1/R of the EFIT field components, coordinate z), the
-///  term -n^2 d(B.B)/(B.B) comes out multiplied by w^2/((B.B)^2 s).  The faulty form survives in the
+///  term -n^2 d(B.B)/(B.B) comes out multiplied by w^2/((B.B)^2 s)  (s = R^8 for EFIT, given as 1/s).  The faulty form survives in the
 ///  copies of n_par^2 and n_perp^2 inside m11 and m22; m33 and m13 reduce along another path and are
 ///  right.  With K = -(d(B.B)/B.B) (w^2/((B.B)^2 s) - 1):
 ///      extra = K ((n_par^2 + n_perp^2) m13^2 - (n_par^2 m22 + m11 (n_par^2 + n_perp^2)) m33).
@@ -271,7 +272,9 @@ namespace dispersion {
             const elements e = build(w, k_vec, x, y, z, eq);
             leaf_ptr coordinate = axis == 0 ? x : (axis == 1 ? y : z);
             auto db_sq = defect.b_sq_derivative.get() ? defect.b_sq_derivative : e.b_sq->df(coordinate);
-            auto K = -1.0*(db_sq/e.b_sq)*(e.w2/(e.b_sq*e.b_sq*defect.scale) - 1.0);
+//  1/(B.B) and 1/(B.B)^2 through 1/|B|, which the kernel has as the reciprocal root of B.B.
+            auto inv_b_sq = (1.0/e.b_len)/e.b_len;
+            auto K = -1.0*(db_sq*inv_b_sq)*(e.w2*(inv_b_sq*inv_b_sq)*defect.inverse_scale - 1.0);
             auto n2 = e.npara2 + e.nperp2;
             return K*(n2*(e.m13*e.m13) - (e.npara2*e.m22 + e.m11*n2)*e.m33);
         }

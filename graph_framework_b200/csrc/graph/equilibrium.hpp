@@ -135,7 +135,7 @@ namespace equilibrium {
 ///  the reference's reducer mis-cancels the derivative of B.B in this field, and the factor involved.
         struct reducer_defect {
             int axis = -1;              ///< 0, 1, 2 = x, y, z; -1: none known
-            leaf_ptr scale;
+            leaf_ptr inverse_scale;     ///< 1/s, see dispersion::cold_plasma::reference_defect
             leaf_ptr b_sq_derivative;   ///< d(B.B)/d(axis) where the equilibrium has a cheaper form than df(); may be null
         };
         virtual reducer_defect get_reducer_defect(leaf_ptr, leaf_ptr, leaf_ptr) { return reducer_defect(); }
@@ -335,10 +335,11 @@ namespace equilibrium {
         virtual typename generic<T, SAFE_MATH>::reducer_defect get_reducer_defect(leaf_ptr x, leaf_ptr y, leaf_ptr z) {
             typename generic<T, SAFE_MATH>::reducer_defect d;
             set_cache(x, y, z);
-            auto r2 = x*x + y*y;
-            auto r4 = r2*r2;
+//  1/R^8 from the 1/R the kernel already has (every division by the root node R is a multiplication by its rsqrt).
+            auto inv_r2 = (1.0/r_cache)/r_cache;
+            auto inv_r4 = inv_r2*inv_r2;
             d.axis = 2;
-            d.scale = r4*r4;
+            d.inverse_scale = inv_r4*inv_r4;
 //  B.B = (psi_Z^2 + F^2 + psi_R^2)/R^2 in cylindrical components (the rotation by phi drops out), so
 //  d(B.B)/dz = 2 (psi_Z psi_ZZ + F F' psi_Z + psi_R psi_RZ)/R^2: every factor is already in the kernel.
             auto psi_z = psi_cache->df(z);
