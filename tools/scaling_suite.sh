@@ -1,6 +1,7 @@
 #!/bin/bash
-# Run ON AN 8-GPU BOX (gpurun --gpus 8): weak and strong scaling of the headline workload, config 3 (device
-# deposition + NCCL all-reduce) and the Boris / VMEC totals, at 2, 4 and 8 ranks.  Output: gpurun_out/scale/*.json
+# Run ON AN 8-GPU BOX (gpurun --gpus 8): the default line on 1 GPU, weak and strong scaling of the headline workload,
+# config 3 (device deposition + overlapped NCCL all-reduce), the Boris / VMEC totals and the default line at 8 ranks.
+# Output: gpurun_out/scale/*.json (last line = the bench line)
 set -u
 OUT=gpurun_out/scale; mkdir -p $OUT
 run() {  # name, ranks, bench args...
@@ -21,14 +22,15 @@ except Exception as ex:
     print("$name FAILED", ex)
 PY
 }
+run default_1gpu 1
 for n in 1 2 4 8; do
   run xmode_weak_${n}gpu $n --steps 10 --warmup 3 --no-extras --no-cpu-baseline
   run xmode_strong_${n}gpu $n --steps 10 --warmup 3 --no-extras --no-cpu-baseline --scaling strong
-  run config3_${n}gpu $n --steps 10 --warmup 5 --no-extras --workload efit_absorb
 done
-for n in 1 8; do
-  run config3_strong_${n}gpu $n --steps 10 --warmup 5 --no-extras --workload efit_absorb --scaling strong
+for n in 1 2 4 8; do
+  run config3_${n}gpu $n --steps 20 --warmup 5 --no-extras --workload efit_absorb
 done
+run config3_strong_8gpu 8 --steps 20 --warmup 5 --no-extras --workload efit_absorb --scaling strong
 run boris_strong_8gpu 8 --steps 3 --warmup 2 --no-extras --no-cpu-baseline --no-e2e --workload boris
 run vmec_strong_8gpu 8 --steps 3 --warmup 2 --no-extras --no-cpu-baseline --no-e2e --workload vmec_omode --scaling strong
 run default_8gpu 8
