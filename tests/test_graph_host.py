@@ -221,3 +221,25 @@ def test_reference_kernel_text_pass(tmp_path):
     same = subprocess.run([exe], input=src, capture_output=True, text=True, check=True,
                           env=dict(os.environ, GFB_B200_IEEE_DIVIDE="1")).stdout
     assert same == src
+
+
+def test_spline_node_families_on_the_host(lib):
+    """graph::spline_1d / spline_2d (node.hpp), the building blocks of the EFIT equilibrium, checked without a
+    device (tests/cpp/spline_host.cpp): the family construction and the reference's Horner chains of piecewise
+    nodes give the same fields and the same first and second derivatives, reverse mode equals forward mode
+    through spline nodes, the families are closed under df(), values equal the plain double sum."""
+    import subprocess
+    from conftest import ROOT
+    build = os.path.join(ROOT, "build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "spline_host")
+    src = os.path.join(ROOT, "tests", "cpp", "spline_host.cpp")
+    graph_dir = os.path.join(ROOT, "graph_framework_b200", "csrc", "graph")
+    deps = [src] + [os.path.join(graph_dir, f) for f in os.listdir(graph_dir)]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run(["g++", "-std=c++20", "-O1", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include", src,
+                        "-L" + os.path.join(ROOT, "graph_framework_b200"), "-lgfb200",
+                        "-Wl,-rpath," + os.path.join(ROOT, "graph_framework_b200"), "-o", exe], check=True, cwd=ROOT)
+    out = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "efit.gfbt")], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "0 failure(s)" in out.stdout and out.stdout.count(" ok") >= 17
