@@ -2,6 +2,8 @@
 
 Modelled on the reference's graph_tests/c_binding_test.c:23-140 (node identity after
 reduction, df) and arithmetic_test / math_test (derivative rules checked numerically here)."""
+import os
+
 import numpy as np
 import pytest
 
