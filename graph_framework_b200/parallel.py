@@ -44,6 +44,58 @@ def allreduce_profile(hist, total_rays=None):
     return hist
 
 
+class OverlappedProfileReducer:
+    """One process per GPU: per-block deposition histograms summed over ranks WITHOUT stalling the trace.
+
+    Two histograms are in flight.  Usage per output block:
+        buf = reducer.begin_block()      # a zeroed histogram to deposit into (RayTracer.deposit_block(..., buf.data_ptr(), ...))
+        reducer.end_block()              # starts the asynchronous all-reduce of that histogram (NCCL over NVLink / gloo)
+    The all-reduce of block b runs while block b + 1 is traced; its result is folded into `profile` just before
+    its buffer is handed out again, or by `finish()`.  All tensor work is issued on the CURRENT torch stream: on
+    the GPU wrap the calls in `with torch.cuda.stream(torch.cuda.ExternalStream(tracer.stream()))` so that the
+    tracer's kernels, the zeroing and the collective share one timeline (bench.py --workload efit_absorb).
+    With a single rank (or torch.distributed not initialised) the blocks are simply accumulated."""
+
+    def __init__(self, bins, device="cpu", total_rays=None):
+        import torch
+        self._torch = torch
+        self.buffers = [torch.zeros(tuple(bins), dtype=torch.float64, device=device) for _ in range(2)]
+        self.pending = [None, None]
+        self.profile = torch.zeros(tuple(bins), dtype=torch.float64, device=device)
+        self.total_rays = total_rays
+        self.blocks = 0
+
+    def _distributed(self):
+        import torch.distributed as dist
+        return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
+
+    def _retire(self, i):
+        if self.pending[i] is not None:
+            if self.pending[i] is not True:
+                self.pending[i].wait()
+            self.profile.add_(self.buffers[i])
+            self.pending[i] = None
+
+    def begin_block(self):
+        i = self.blocks % 2
+        self._retire(i)
+        self.buffers[i].zero_()
+        return self.buffers[i]
+
+    def end_block(self):
+        i = self.blocks % 2
+        dist = self._distributed()
+        self.pending[i] = dist.all_reduce(self.buffers[i], op=dist.ReduceOp.SUM, async_op=True) if dist else True
+        self.blocks += 1
+
+    def finish(self):
+        """Folds the blocks still in flight (older first) and returns the profile, divided by total_rays when
+        given (utilities/bin.py:96-106)."""
+        for i in (self.blocks % 2, (self.blocks + 1) % 2):
+            self._retire(i)
+        return self.profile/float(self.total_rays) if self.total_rays else self.profile
+
+
 def allreduce_profiles_in_process(tracers):
     """Thread-per-device model (one process, one RayTracer per GPU, the reference's xrays.cpp:419-527):
     sums the device-resident deposition profiles of all tracers in place over NVLink peer memory

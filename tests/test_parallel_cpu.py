@@ -43,6 +43,17 @@ hist = torch.from_numpy(local.copy())
 parallel.allreduce_profile(hist, total_rays=n)
 full = port.deposit(state["x"], state["y"], state["z"], state["w"], lo, hi, bins)/n
 assert np.allclose(hist.numpy(), full, rtol=1e-13, atol=1e-300), np.abs(hist.numpy() - full).max()
+# the same with the blocks of a trace overlapped: every rank deposits 7 blocks of its shard, the reductions run asynchronously
+reducer = parallel.OverlappedProfileReducer(bins, total_rays=n)
+expected = np.zeros(bins)
+for block in range(7):
+    w = state["w"]*(block + 1)
+    buf = reducer.begin_block()
+    buf += torch.from_numpy(port.deposit(mine["x"], mine["y"], mine["z"], w[off:off + size], lo, hi, bins))
+    reducer.end_block()
+    expected += port.deposit(state["x"], state["y"], state["z"], w, lo, hi, bins)
+got = reducer.finish().numpy()
+assert np.allclose(got, expected/n, rtol=1e-13, atol=1e-300), np.abs(got - expected/n).max()
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
