@@ -779,7 +779,11 @@ namespace graph {
     inline leaf_ptr spline_1d(const std::array<leaf_ptr, 4> &c, leaf_ptr x, const unsigned a=0) {
         const leaf_node *shape = nullptr;
         for (auto &n : c) if (n->op == op_t::piecewise_1d) shape = n.get();
-        if (!shape) return a == 0 ? fma(fma(fma(c[3], x, c[2]), x, c[1]), x, c[0]) : zero();      // all constants: a plain cubic
+        if (!shape) {           // all coefficients constant: a plain cubic, differentiated by df() like any expression
+            leaf_ptr cubic = fma(fma(fma(c[3], x, c[2]), x, c[1]), x, c[0]);
+            for (unsigned i = 0; i < a; i++) cubic = cubic->df(x);
+            return cubic;
+        }
         const size_t cells = shape->table->values.size();
         std::vector<double> v(cells*4);
         for (size_t j = 0; j < 4; j++) {

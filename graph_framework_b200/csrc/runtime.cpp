@@ -1042,6 +1042,7 @@ int gfb_allreduce_sum_f64(gfb_ctx *const *ctxs, int num_ctx, const uint64_t *key
     const size_t per = ((n + num_ctx - 1)/num_ctx + 1)/2*2;
     auto slice_begin = [&] (const int g) { return std::min(n, per*static_cast<size_t> (g)); };
     auto slice_count = [&] (const int g) { return std::min(n, per*static_cast<size_t> (g + 1)) - slice_begin(g); };
+//  First pass: can every device read every other one?  (Decided before any scratch is sized.)
     bool peers = true;
     for (int g = 0; g < num_ctx; g++) {
         gfb_ctx *c = ctxs[g];
@@ -1055,6 +1056,10 @@ int gfb_allreduce_sum_f64(gfb_ctx *const *ctxs, int num_ctx, const uint64_t *key
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peers = false;
             cudaGetLastError();
         }
+    }
+    for (int g = 0; g < num_ctx; g++) {
+        gfb_ctx *c = ctxs[g];
+        if (check(cudaSetDevice(c->device), "cudaSetDevice")) return 1;
         if (!c->reduce_ready) {
             cudaEventCreateWithFlags(&c->reduce_ready, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&c->reduce_summed, cudaEventDisableTiming);
@@ -1064,6 +1069,8 @@ int gfb_allreduce_sum_f64(gfb_ctx *const *ctxs, int num_ctx, const uint64_t *key
         if (c->reduce_capacity < need) {
             cudaStreamSynchronize(c->stream);
             if (c->reduce_scratch) cudaFree(c->reduce_scratch);
+            c->reduce_scratch = nullptr;
+            c->reduce_capacity = 0;
             if (check(cudaMalloc(&c->reduce_scratch, need*sizeof(double)), "reduce scratch")) return 1;
             c->reduce_capacity = need;
         }
