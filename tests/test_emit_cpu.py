@@ -349,3 +349,23 @@ def test_emitted_index_kernels_match_numpy(lib, emit_tool):
         cubin, size, log = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_void_p()
         assert lib.gfb_compile_to_cubin(src, None, ctypes.byref(cubin), ctypes.byref(size), ctypes.byref(log)) == 0
         lib.gfb_free(cubin)
+
+
+def test_emitted_boris_push_matches_reference(emit_tool):
+    """The xkorc step graph (csrc/graph/boris.hpp = graph_korc/xkorc.cpp:66-121) as a fused generic item on the CPU
+    harness: 50 pushes in the EFIT field from the reference's start, against the reference's own run
+    (tests/golden/ref_korc_efit.npz); the on-axis field is taken from the golden (the device search for it is a GPU test)."""
+    g = golden("ref_korc_efit")
+    x, y, z, ux, uy, uz = g["start"]
+    n = x.size
+    gamma = 1.0/np.sqrt(1.0 - (ux*ux + uy*uy + uz*uz))         # the initialize_gamma pre-item
+    env_b0 = repr(float(g["b0"]))
+    os.environ["GFB_B0"] = env_b0
+    try:
+        cu, tab, info = emit(emit_tool, "none", "efit", "boris", "boris_efit", dt=0.5)
+    finally:
+        os.environ.pop("GFB_B0", None)
+    out = run_harness(cu, tab, "step", [x, y, z, gamma*ux, gamma*uy, gamma*uz, gamma], n, 50, 7, 0, "boris_efit")
+    for i, name in enumerate(("x", "y", "z", "ux", "uy", "uz", "gamma")):
+        assert rel_dev(out[i], g["end"][i]) < 1.0e-10, (name, rel_dev(out[i], g["end"][i]))
+    assert info["divides"] == 0 and info["reciprocals"] <= 3
