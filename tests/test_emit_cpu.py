@@ -369,3 +369,23 @@ def test_emitted_boris_push_matches_reference(emit_tool):
     for i, name in enumerate(("x", "y", "z", "ux", "uy", "uz", "gamma")):
         assert rel_dev(out[i], g["end"][i]) < 1.0e-10, (name, rel_dev(out[i], g["end"][i]))
     assert info["divides"] == 0 and info["reciprocals"] <= 3
+
+
+def test_horner_chain_construction_still_steps_like_the_reference(emit_tool):
+    """GFB_SPLINE_NODES=0: EFIT built from Horner chains of piecewise nodes (the reference's build_1D_spline /
+    build_psi shape) instead of the spline node families -- the A/B switch of DESIGN.md section 2 must keep working:
+    same per-step parity, and the family version of the same kernel has fewer statements."""
+    g = golden("ref_trace_extra_ordinary_wave_efit_rk4")
+    rec = g["per_step"]
+    n = rec.shape[2]
+    os.environ["GFB_SPLINE_NODES"] = "0"
+    try:
+        cu, tab, chains = emit(emit_tool, "extra_ordinary_wave", "efit", "rk4", "rk_xmode_chains", dt=float(g["dt"]))
+    finally:
+        os.environ.pop("GFB_SPLINE_NODES", None)
+    assert "fma(v[4], c" in open(cu).read() or "p0_0" in open(cu).read()         # piecewise groups, not spline rows
+    out = run_harness(cu, tab, "solver_kernel", rec[0][:8], n, 1, 8, 1, "rk_xmode_chains")
+    for i in range(8):
+        assert rel_dev(out[i], rec[1][i]) < 1.0e-12, (i, rel_dev(out[i], rec[1][i]))
+    _, _, families = emit(emit_tool, "extra_ordinary_wave", "efit", "rk4", "rk_xmode_families", dt=float(g["dt"]))
+    assert families["statements"] < 0.8*chains["statements"]
