@@ -41,7 +41,7 @@ def parser():
     p.add_argument("--sub_steps", type=int, default=100)
     p.add_argument("--num_rays", type=int, default=1)
     p.add_argument("--endtime", type=float, default=1.0)
-    p.add_argument("--solver", default="rk4", choices=["rk2", "rk4", "split_simplextic"])
+    p.add_argument("--solver", default="rk4", choices=["rk2", "rk4", "split_simplextic", "adaptive_rk4"])     # xrays.cpp:312-360
     p.add_argument("--dispersion", default="ordinary_wave",
                    choices=["simple", "bohm_gross", "ordinary_wave", "extra_ordinary_wave", "cold_plasma"])
     p.add_argument("--equilibrium", default="efit", choices=["efit", "vmec", "slab", "slab_density", "slab_field",
